@@ -1,0 +1,138 @@
+/* met2.h — C ABI of libmet2.so: the B200 (sm_100a) implementation of the per-voxel MET2 inverse-problem path.
+ *
+ * The reference (ejcanalesr/multicomponent-T2-toolbox) is pure Python and has no FFI; the boundary this library
+ * replaces is the set of Python call signatures listed in SURVEY.md §8(b).  Each entry point below names the
+ * reference interface (file:line under the reference tree) whose work it takes over.
+ *
+ * Conventions
+ *   - every array argument is a DEVICE pointer to a contiguous C-order array (float64 unless said otherwise) that the
+ *     caller owns; the library never allocates or frees caller buffers.  Scratch space is passed in as `workspace`
+ *     (size from the matching *_workspace_bytes call; 256-byte aligned device memory).
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = default stream) and is asynchronous;
+ *     the caller synchronises.  One call at a time per stream.
+ *   - return value 0 = success, negative = error (message from met2_last_error(), thread-local).  No exception and
+ *     no abort crosses the ABI.  Per-voxel conditions never fail the batch: they are reported as bit flags in
+ *     `status[v]` (MET2_ST_*), and a skipped voxel gets all-zero outputs exactly like the reference's zero-initialised
+ *     arrays (motor/motor_recon_met2_real_data.py:115-117,191-202).
+ *   - there is no CPU fallback: without a CUDA device every compute entry point returns MET2_ERR_CUDA.
+ */
+#ifndef MET2_H_
+#define MET2_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MET2_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define MET2_OK 0
+#define MET2_ERR_ARG (-1)   /* invalid argument (sizes out of the supported range, NULL pointer, bad enum) */
+#define MET2_ERR_CUDA (-2)  /* CUDA runtime error (message holds cudaGetErrorString) */
+#define MET2_ERR_UNSUPPORTED (-3)
+
+/* supported sizes */
+#define MET2_MAX_NT2 128 /* T2 bins (reference: 60, or 96 for T2SPARC; config 4 uses 100) */
+#define MET2_MAX_NTE 64  /* echoes (reference data: 32; config 4 uses 48) */
+#define MET2_MAX_KNOTS 32
+#define MET2_MAX_LAMBDAS 64
+
+/* per-voxel status bits */
+#define MET2_ST_SKIPPED 1u      /* sum(M) <= 0 or M[0] <= 0: voxel not fitted (fa_estimation.py:100, motor...:124,131) */
+#define MET2_ST_NONFINITE 2u    /* NaN/Inf in the signal (the reference raises ValueError, algorithms.py:56) */
+#define MET2_ST_ITMAX 4u        /* a Lawson-Hanson solve hit itmax = 3n (ignored by the reference, algorithms.py:79-81) */
+#define MET2_ST_SSE_ZERO 8u     /* X2: plain-NNLS residual is exactly 0 -> NaN objective (algorithms.py:231) */
+#define MET2_ST_NOT_PD 16u      /* BayesReg: beta*B + beta*x*K not positive definite (reference: LinAlgError) */
+
+/* flip-angle search methods: run_real_data_script.py --FA_method */
+#define MET2_FA_BRUTE_FORCE 0
+#define MET2_FA_SPLINE 1
+
+/* regularisation methods: run_real_data_script.py --reg_method */
+#define MET2_REG_NNLS 0
+#define MET2_REG_T2SPARC 1
+#define MET2_REG_X2 2
+#define MET2_REG_LCURVE 3
+#define MET2_REG_GCV 4
+#define MET2_REG_BAYESREG 5
+
+typedef struct met2_fa_cfg {
+    int32_t method;       /* MET2_FA_* */
+    int32_t nTE, nT2;     /* echoes, T2 bins */
+    int32_t nA;           /* flip angles of the fine grid (91 brute-force / 273 spline; motor...:231-245) */
+    int32_t nKnots;       /* spline only: angles of the coarse dictionary (15) */
+    int32_t final_solve;  /* 1: also solve NNLS at the chosen angle -> km, fsol_sum (fa_estimation.py:61-65,84-86) */
+    double brent_lo, brent_hi, brent_xatol; /* spline: minimize_scalar(method='Bounded') bounds=(90,180), 1e-5 */
+    int32_t brent_maxfun;                   /* 500 */
+    int32_t reserved;
+} met2_fa_cfg;
+
+typedef struct met2_t2_cfg {
+    int32_t method;   /* MET2_REG_* */
+    int32_t nTE, nT2, nA;
+    int32_t nLambda;  /* L-curve grid size (50) */
+    int32_t maxfun;   /* Brent evaluation cap: X2/GCV 300, BayesReg 200 */
+    double factor;    /* X2 chi-square factor 1.02 (motor...:141) */
+    double lambda_fixed; /* T2SPARC 1.8 (motor...:138) */
+    double brent_lo, brent_hi, brent_xatol; /* X2 [0,10]; GCV [1e-8,10]; BayesReg [1e-8,2]; xtol 1e-5 */
+    double log_det_L;    /* BayesReg: log(det(L)) (bayesian_interpolation.py:100,123); -inf for L2 */
+    int32_t regularised; /* 0: lambda*K term absent (plain NNLS) */
+    int32_t reserved;
+} met2_t2_cfg;
+
+/* Replaces epg/epg.py:155 create_Dic_3D (-> :47 create_met2_design_matrix_epg -> :64 epg_signal).
+ * dic  [nA][nTE][nT2]  (the reference's Dic_3D[:, :, a] slices made contiguous) and
+ * dicT [nA][nT2][nTE]  (same numbers transposed, for coalesced residual evaluation).  Either may be NULL. */
+int met2_epg_dictionary(const double* alphas_deg, int nA, const double* T2s, const double* T1s, int nT2, int nTE,
+                        double tau_ms, double TR_ms, double* dic, double* dicT, void* stream);
+
+/* EPG decay curves for arbitrary (alpha, T2, T1) triples: sig[N][nTE] without the (1-exp(-TR/T1)) factor.
+ * Same kernel as the dictionary; used by the synthetic phantom generator (epg/epg.py:64 epg_signal). */
+int met2_epg_signals(const double* alphas_deg, const double* T2s, const double* T1s, int64_t N, int nTE, double tau_ms,
+                     double* sig, void* stream);
+
+/* Gram tables of the dictionary, G[a] = D_a^T D_a  ([nA][nT2][nT2]), and the 5-band form of K = L^T L
+ * (kband[5][nT2], kband[d][c] = K[c+d-2][c]) for the Tikhonov term of algorithms.py:262-269 (A = [D; sqrt(lambda) L]).
+ * L is the dense [nT2][nT2] matrix of motor...:86-111,254-273; *band_err (device int, may be NULL) is set to 1 if
+ * L^T L has an entry outside the five central diagonals (not the case for I, L1, L2, InvT2).  L/kband may be NULL. */
+int met2_gram_tables(const double* dic, int nA, int nTE, int nT2, const double* L, double* G, double* kband,
+                     int32_t* band_err, void* stream);
+
+/* Replaces the Step-2 joblib loop (motor...:349-373) over fitting_slice_FA_brute_force (fa_estimation.py:92) /
+ * fitting_slice_FA_spline_method (:35) and their per-voxel body compute_optimal_FA (:74).
+ * sig [V][nTE] raw signals of the voxels to fit (mask already applied by the caller).
+ * Search dictionary = (dic_s, dicT_s, G_s) with cfg->nKnots angles for the spline method, or the fine dictionary
+ * itself for brute force (pass the same pointers).  alphas [nA] fine grid (deg), knots [nKnots].
+ * Outputs: fa_index [V] int32, fa_deg [V], km [V] (sum of the NNLS spectrum at the chosen angle),
+ * fsol_sum [nT2] (sum over voxels of those spectra; feeds mean_T2_dist, motor...:362,370), status [V] uint32. */
+int64_t met2_fa_workspace_bytes(int64_t V, const met2_fa_cfg* cfg);
+int met2_fa_fit(const double* sig, int64_t V, const met2_fa_cfg* cfg, const double* dic, const double* dicT,
+                const double* G, const double* alphas, const double* dic_s, const double* dicT_s, const double* G_s,
+                const double* knots, int32_t* fa_index, double* fa_deg, double* km, double* fsol_sum, uint32_t* status,
+                void* workspace, void* stream);
+
+/* Replaces the Step-3 joblib loop (motor...:428-441) over fitting_slice_T2 (motor...:113-162) with its solvers
+ * nnls / nnls_tik / nnls_x2 / nnls_lcurve_wrapper / nnls_gcv (intravoxel_algorithms/algorithms.py:55-296) and
+ * BayesReg_nnls (intravoxel_algorithms/bayesian_interpolation.py:84-126), and the Step-4 metrics loop (motor...:443-472).
+ * sig [V][nTE] raw signals; fa_index [V]; kband from met2_gram_tables; lambdas [nLambda] (L-curve grid);
+ * logT2 [nT2]; comp [nT2] uint8 bit mask per T2 bin: 1 = myelin (ind_m), 2 = intra/extra (ind_t), 4 = free water (ind_csf).
+ * Outputs: fsol [V][nT2], est_signal [V][nTE], reg [V] (motor...:153: 0 | 1.8 | k_est | lambda),
+ * maps [V][6] = MWF, IEWF, FWF, T2_M, T2_IE, TWC, status [V]. */
+int64_t met2_t2_workspace_bytes(int64_t V, const met2_t2_cfg* cfg);
+int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg, const double* dic,
+                const double* dicT, const double* G, const double* kband, const double* lambdas, const double* logT2,
+                const uint8_t* comp, double* fsol, double* est_signal, double* reg, double* maps, uint32_t* status,
+                void* workspace, void* stream);
+
+/* Diagnostics */
+const char* met2_last_error(void);
+int met2_version(void);
+/* number of kernel launches enqueued by this library in this process so far (for bench.py's gpu_launches) */
+int64_t met2_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MET2_H_ */

@@ -1,0 +1,211 @@
+"""Batched host API over libmet2.so: one call per stage for all voxels instead of the reference's joblib row loops.
+
+`Met2Plan` owns the device-resident tables of one reconstruction set-up (EPG dictionaries, Gram tables, band forms of
+the regularisation matrix, grids) — what motor/motor_recon_met2_real_data.py:204-277 builds on the host — and exposes
+
+    fa_fit(signals[V, nTE])                -> FA index / angle / km / sum of spectra      (Step 2, motor...:349-373)
+    t2_fit(signals[V, nTE], fa_index[V])   -> spectra, fitted signals, reg, six maps      (Steps 3+4, motor...:428-472)
+
+PyTorch is used only for device buffers and streams.  There is no CPU path: constructing a plan without CUDA raises.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib, grids
+
+FA_METHOD_CODE = {"brute-force": 0, "spline": 1}
+REG_METHOD_CODE = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3, "GCV": 4, "BayesReg": 5}
+
+ST_SKIPPED, ST_NONFINITE, ST_ITMAX, ST_SSE_ZERO, ST_NOT_PD = 1, 2, 4, 8, 16
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise _lib.Met2Error("met2: no CUDA device available — this package has no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise _lib.Met2Error("met2: device must be a CUDA device, got %s" % dev)
+    return dev
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _dev_f64(a, dev):
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+
+
+class Dictionary:
+    """Device EPG dictionary of one angle grid: dic [nA][nTE][nT2], dicT [nA][nT2][nTE], G [nA][nT2][nT2]."""
+
+    def __init__(self, alphas, T2s, T1s, n_echoes, tau, TR, dev):
+        lib = _lib.load()
+        self.alphas_host = np.ascontiguousarray(alphas, dtype=np.float64)
+        self.nA, self.nT2, self.nTE = len(self.alphas_host), len(T2s), int(n_echoes)
+        self.alphas = _dev_f64(self.alphas_host, dev)
+        t2 = _dev_f64(T2s, dev)
+        t1 = _dev_f64(T1s, dev)
+        self.dic = torch.empty((self.nA, self.nTE, self.nT2), dtype=torch.float64, device=dev)
+        self.dicT = torch.empty((self.nA, self.nT2, self.nTE), dtype=torch.float64, device=dev)
+        self.G = torch.empty((self.nA, self.nT2, self.nT2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.met2_epg_dictionary(_ptr(self.alphas), self.nA, _ptr(t2), _ptr(t1), self.nT2, self.nTE,
+                                               float(tau), float(TR), _ptr(self.dic), _ptr(self.dicT), _stream()),
+                       "met2_epg_dictionary")
+            _lib.check(lib.met2_gram_tables(_ptr(self.dic), self.nA, self.nTE, self.nT2, None, _ptr(self.G), None, None,
+                                            _stream()), "met2_gram_tables")
+
+    def to_reference_layout(self):
+        """Host copy in the reference's layout Dic_3D[nTE, nT2, nA] (epg/epg.py:155-162)."""
+        return np.ascontiguousarray(self.dic.permute(1, 2, 0).cpu().numpy())
+
+
+class Met2Plan:
+    def __init__(self, n_echoes, tau, TR, reg_method="X2", reg_matrix="I", FA_method="spline", myelin_T2=40.0,
+                 npc=None, n_alphas=None, T1=1000.0, device=None, lambda_reg=None, Laplac=None):
+        if reg_method not in REG_METHOD_CODE:
+            raise ValueError("unknown reg_method %r" % (reg_method,))
+        if FA_method not in FA_METHOD_CODE:
+            raise ValueError("Error: Wrong FA_method option!")
+        self.dev = _require_cuda(device)
+        self.lib = _lib.load()
+        self.reg_method, self.reg_matrix, self.FA_method = reg_method, reg_matrix, FA_method
+        self.nTE, self.tau, self.TR = int(n_echoes), float(tau), float(TR)
+        self.npc = grids.default_npc(reg_method) if npc is None else int(npc)
+        self.T2s = grids.t2_grid(self.npc)
+        self.T1s = float(T1) * np.ones_like(self.T2s)
+        self.ind_m, self.ind_t, self.ind_csf = grids.compartment_masks(self.T2s, myelin_T2)
+        self.alpha_values, self.alpha_spline = grids.fa_grids(FA_method, n_alphas)
+        self.lambda_reg = grids.lambda_grid() if lambda_reg is None else np.asarray(lambda_reg, dtype=np.float64)
+        self.Laplac = grids.reg_matrix(reg_matrix, self.T2s) if Laplac is None else np.asarray(Laplac, np.float64)
+        K = self.Laplac.T @ self.Laplac
+        off = np.abs(np.subtract.outer(np.arange(self.npc), np.arange(self.npc))) > 2
+        if np.any(K[off] != 0.0) or np.any(self.Laplac[off] != 0.0):
+            raise ValueError("regularisation matrix must be banded (|i-j| <= 2), like I, L1, L2, InvT2")
+        with torch.cuda.device(self.dev):
+            self.dict_hr = Dictionary(self.alpha_values, self.T2s, self.T1s, self.nTE, tau, TR, self.dev)
+            self.dict_lr = None
+            if FA_method == "spline":
+                self.dict_lr = Dictionary(self.alpha_spline, self.T2s, self.T1s, self.nTE, tau, TR, self.dev)
+                self.knots = _dev_f64(self.alpha_spline, self.dev)
+            self.L_dev = _dev_f64(self.Laplac, self.dev)
+            self.kband = torch.zeros((10, self.npc), dtype=torch.float64, device=self.dev)
+            self.band_err = torch.zeros(1, dtype=torch.int32, device=self.dev)
+            _lib.check(self.lib.met2_gram_tables(None, 0, self.nTE, self.npc, _ptr(self.L_dev), None, _ptr(self.kband),
+                                                 _ptr(self.band_err), _stream()), "met2_gram_tables(L)")
+            self.lambdas = _dev_f64(self.lambda_reg, self.dev)
+            self.logT2 = _dev_f64(np.log(self.T2s), self.dev)
+            comp = (self.ind_m.astype(np.uint8) | (self.ind_t.astype(np.uint8) << 1) | (self.ind_csf.astype(np.uint8) << 2))
+            self.comp = torch.as_tensor(comp).to(self.dev)
+        self._ws = {}
+
+    # ------------------------------------------------------------------ configs
+    def fa_cfg(self, final_solve=True):
+        return _lib.FaCfg(method=FA_METHOD_CODE[self.FA_method], nTE=self.nTE, nT2=self.npc, nA=len(self.alpha_values),
+                          nKnots=(len(self.alpha_spline) if self.alpha_spline is not None else 0),
+                          final_solve=int(final_solve), brent_lo=90.0, brent_hi=180.0, brent_xatol=1e-5,
+                          brent_maxfun=500, reserved=0)
+
+    def t2_cfg(self, reg_method=None):
+        method = self.reg_method if reg_method is None else reg_method
+        cfg = _lib.T2Cfg(method=REG_METHOD_CODE[method], nTE=self.nTE, nT2=self.npc, nA=len(self.alpha_values),
+                         nLambda=len(self.lambda_reg), maxfun=300, factor=1.02, lambda_fixed=1.8, brent_lo=0.0,
+                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, regularised=int(method != "NNLS"), reserved=0)
+        if method == "GCV":
+            cfg.brent_lo = 1e-8
+        if method == "BayesReg":
+            cfg.brent_lo, cfg.brent_hi, cfg.maxfun = 1e-8, 2.0, 200
+            with np.errstate(divide="ignore"):
+                cfg.log_det_L = float(np.log(np.linalg.det(self.Laplac)))
+        return cfg
+
+    def _workspace(self, key, nbytes):
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < nbytes:
+            ws = torch.empty(int(nbytes), dtype=torch.uint8, device=self.dev)
+            self._ws[key] = ws
+        return ws
+
+    def _signals(self, sig):
+        if isinstance(sig, np.ndarray):
+            sig = torch.as_tensor(np.ascontiguousarray(sig, dtype=np.float64))
+        sig = sig.to(device=self.dev, dtype=torch.float64).contiguous()
+        if sig.dim() != 2 or sig.shape[1] != self.nTE:
+            raise ValueError("signals must be [V, %d], got %s" % (self.nTE, tuple(sig.shape)))
+        return sig
+
+    # ------------------------------------------------------------------ Step 2
+    def fa_fit(self, sig, final_solve=True, out=None):
+        """Flip-angle estimation for all voxels.  Returns dict(fa_index int32[V], fa_deg[V], km[V], fsol_sum[nT2], status)."""
+        sig = self._signals(sig)
+        V = sig.shape[0]
+        dev = self.dev
+        if out is None:
+            out = dict(fa_index=torch.empty(V, dtype=torch.int32, device=dev),
+                       fa_deg=torch.empty(V, dtype=torch.float64, device=dev),
+                       km=torch.empty(V, dtype=torch.float64, device=dev),
+                       fsol_sum=torch.zeros(self.npc, dtype=torch.float64, device=dev),
+                       status=torch.empty(V, dtype=torch.int32, device=dev))
+        if V == 0:
+            return out
+        cfg = self.fa_cfg(final_solve)
+        with torch.cuda.device(dev):
+            nbytes = self.lib.met2_fa_workspace_bytes(V, ctypes.byref(cfg))
+            if nbytes < 0:
+                _lib.check(-1, "met2_fa_workspace_bytes")
+            ws = self._workspace("fa", nbytes)
+            hr, lr = self.dict_hr, self.dict_lr
+            _lib.check(self.lib.met2_fa_fit(
+                _ptr(sig), V, ctypes.byref(cfg), _ptr(hr.dic), _ptr(hr.dicT), _ptr(hr.G), _ptr(hr.alphas),
+                _ptr(lr.dic) if lr else None, _ptr(lr.dicT) if lr else None, _ptr(lr.G) if lr else None,
+                _ptr(self.knots) if lr else None, _ptr(out["fa_index"]), _ptr(out["fa_deg"]), _ptr(out["km"]),
+                _ptr(out["fsol_sum"]) if final_solve else None, _ptr(out["status"]), _ptr(ws), _stream()), "met2_fa_fit")
+        return out
+
+    # ------------------------------------------------------------------ Steps 3 + 4
+    def t2_fit(self, sig, fa_index, reg_method=None, out=None):
+        """Spectrum fit + metrics.  Returns dict(fsol[V,nT2], est_signal[V,nTE], reg[V], maps[V,6], status[V])."""
+        sig = self._signals(sig)
+        V = sig.shape[0]
+        dev = self.dev
+        if isinstance(fa_index, np.ndarray):
+            fa_index = torch.as_tensor(fa_index)
+        fa_index = fa_index.to(device=dev, dtype=torch.int32).contiguous()
+        if fa_index.shape != (V,):
+            raise ValueError("fa_index must be [V]")
+        if out is None:
+            out = dict(fsol=torch.empty((V, self.npc), dtype=torch.float64, device=dev),
+                       est_signal=torch.empty((V, self.nTE), dtype=torch.float64, device=dev),
+                       reg=torch.empty(V, dtype=torch.float64, device=dev),
+                       maps=torch.empty((V, 6), dtype=torch.float64, device=dev),
+                       status=torch.empty(V, dtype=torch.int32, device=dev))
+        if V == 0:
+            return out
+        cfg = self.t2_cfg(reg_method)
+        with torch.cuda.device(dev):
+            nbytes = self.lib.met2_t2_workspace_bytes(V, ctypes.byref(cfg))
+            if nbytes < 0:
+                _lib.check(-1, "met2_t2_workspace_bytes")
+            ws = self._workspace("t2", nbytes)
+            hr = self.dict_hr
+            _lib.check(self.lib.met2_t2_fit(
+                _ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(hr.dic), _ptr(hr.dicT), _ptr(hr.G),
+                _ptr(self.kband), _ptr(self.lambdas), _ptr(self.logT2), _ptr(self.comp), _ptr(out["fsol"]),
+                _ptr(out["est_signal"]), _ptr(out["reg"]), _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), _stream()),
+                "met2_t2_fit")
+        return out
+
+    def fit(self, sig, sig_fa=None):
+        """Steps 2-4 for a batch of voxels: FA search on `sig_fa` (defaults to `sig`), spectrum fit on `sig`."""
+        sig = self._signals(sig)
+        fa = self.fa_fit(sig if sig_fa is None else sig_fa)
+        t2 = self.t2_fit(sig, fa["fa_index"])
+        return fa, t2

@@ -1,0 +1,61 @@
+"""Build libmet2.so (hand-written sm_100a CUDA + the C ABI of include/met2.h) in-tree with nvcc."""
+import os
+import shutil
+import subprocess
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(PKG_DIR, "csrc")
+LIB_PATH = os.path.join(PKG_DIR, "libmet2.so")
+SOURCES = ["met2_api.cu", "met2_epg.cu", "met2_fa.cu", "met2_t2.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    # no implicit FMA contraction: Brent / corner-selection comparisons must round like the reference's separate
+    # multiply and add; the hot loops use explicit fma()
+    "-fmad=false",
+    "-Xcompiler", "-fPIC", "-Xptxas", "-v",
+]
+
+
+def _nvcc():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: libmet2.so cannot be built")
+    return nvcc
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(PKG_DIR, "..", "include", "met2.h")]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compile every .cu under csrc/ for sm_100a into libmet2.so.  Returns the library path."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = _nvcc()
+    objs = []
+    logs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".o"))
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        logs.append(r.stderr)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stderr[-8000:]))
+        objs.append(obj)
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n%s" % r.stderr[-4000:])
+    with open(os.path.join(CSRC, "ptxas.log"), "w") as fh:
+        fh.write("\n".join(logs))
+    if verbose:
+        print("\n".join(logs))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

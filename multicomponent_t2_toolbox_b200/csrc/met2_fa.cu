@@ -1,0 +1,416 @@
+// met2_fa.cu — flip-angle estimation for a batch of voxels (Step 2 of the reference orchestrator).
+//
+// Takes over flip_angle_algorithms/fa_estimation.py: compute_optimal_FA (:74-90, brute force),
+// fitting_slice_FA_spline_method (:35-70) and the joblib loop that drives them (motor/motor_recon_met2_real_data.py:349-373).
+//   kernel 1 (fa_search_kernel): residual norm of the plain NNLS fit for every search angle and voxel.  Angles are the
+//       OUTER loop of each CTA so the ~59 KB of tables of one angle (D, D^T, G) are shared by all its warps through L1.
+//   kernel 2 (fa_select_kernel): brute force -> the running arg-min of kernel 1; spline -> not-a-knot cubic through the
+//       15 knot residuals, SciPy's bounded Brent on it, snap to the fine grid; then the NNLS at the chosen angle for
+//       km = sum(f) and the per-warp partial sums of f (mean_T2_dist).
+//   kernel 3: fixed-order reduction of those partial sums (deterministic for a given launch geometry).
+#include <cmath>
+
+#include "met2_device.cuh"
+#include "met2_host.h"
+
+namespace met2 {
+
+struct FaArgs {
+    const double* sig;
+    long long V;
+    met2_fa_cfg cfg;
+    const double *dic, *dicT, *G, *alphas;        // fine grid tables
+    const double *dic_s, *dicT_s, *G_s, *knots;   // search tables (== fine for brute force)
+    int nS;                                        // number of search angles
+    int* fa_index;
+    double *fa_deg, *km, *fsol_sum;
+    unsigned* status;
+    // workspace
+    double* resid;      // spline: [V][nS]; brute force: best residual [V]
+    double* wsp;        // [nK][nK] spline weights
+    double* partial;    // [total warps][nT2]
+    int pmax;
+};
+
+constexpr int FA_WARPS = 8;
+
+template <int NS>
+__device__ __forceinline__ size_t fa_warp_bytes(int pmax) {
+    return align_up256(NnlsWork<NS>::bytes(pmax) + sizeof(double) * 64);
+}
+
+// Load the raw signal of voxel v into ms; returns 0 if it is to be fitted, else the status bits.
+template <int ME>
+__device__ __forceinline__ unsigned load_signal(const double* __restrict__ sig, long long v, int m, double* ms, int lane,
+                                                bool need_m0) {
+    double s = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        int e = lane + 32 * u;
+        if (e < m) {
+            double x = sig[v * m + e];
+            ms[e] = x;
+            s += x;
+            if (!isfinite(x)) bad = true;
+        }
+    }
+    s = warp_sum(s);
+    bad = __any_sync(FULL_MASK, bad);
+    __syncwarp();
+    if (bad) return MET2_ST_NONFINITE | MET2_ST_SKIPPED;
+    if (!(s > 0.0)) return MET2_ST_SKIPPED;
+    if (need_m0 && !(ms[0] > 0.0)) return MET2_ST_SKIPPED;
+    return 0u;
+}
+
+template <int NS, int ME>
+__global__ void __launch_bounds__(FA_WARPS * 32) fa_search_kernel(FaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = A.cfg.nT2, m = A.cfg.nTE;
+    NnlsWork<NS> W;
+    unsigned char* base = smem + (size_t)warp * fa_warp_bytes<NS>(A.pmax);
+    W.carve(base, A.pmax);
+    double* ms = reinterpret_cast<double*>(base + NnlsWork<NS>::bytes(A.pmax));
+    const long long chunk = (A.V + gridDim.x - 1) / gridDim.x;
+    const long long v0 = (long long)blockIdx.x * chunk;
+    const long long v1 = (v0 + chunk < A.V) ? v0 + chunk : A.V;
+    const bool brute = (A.cfg.method == MET2_FA_BRUTE_FORCE);
+    for (int a = 0; a < A.nS; ++a) {
+        const double* D = A.dic_s + (size_t)a * m * n;
+        const double* Dt = A.dicT_s + (size_t)a * n * m;
+        const double* G = A.G_s + (size_t)a * n * n;
+        for (long long v = v0 + warp; v < v1; v += FA_WARPS) {
+            unsigned st = load_signal<ME>(A.sig, v, m, ms, lane, false);
+            if (st) continue;
+            compute_c<NS>(W, D, ms, m, n, lane);
+            int nst = 0;
+            int p = nnls_gram<NS, false>(W, G, nullptr, 0.0, n, m, lane, nst);
+            double fit[ME];
+            double sse = fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
+            double rnorm = sqrt(sse);
+            if (lane == 0) {
+                if (brute) {
+                    // np.argmin: first minimum (fa_estimation.py:83)
+                    if (a == 0 || rnorm < A.resid[v]) {
+                        A.resid[v] = rnorm;
+                        A.fa_index[v] = a;
+                    }
+                } else {
+                    A.resid[v * A.nS + a] = rnorm;
+                }
+                if (nst) atomicOr(&A.status[v], MET2_ST_ITMAX);
+            }
+            __syncwarp();
+        }
+        __syncthreads();   // keep the CTA's warps on the same angle (L1 locality of the tables)
+    }
+}
+
+// Not-a-knot cubic spline as a linear map from knot values to knot second derivatives: Msec = Wsp * y.
+// (scipy.interpolate.interp1d(kind='cubic') -> make_interp_spline(k=3), default not-a-knot; fa_estimation.py:54.)
+__global__ void spline_weights_kernel(const double* __restrict__ knots, int K, double* __restrict__ wsp) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double Aug[MET2_MAX_KNOTS][2 * MET2_MAX_KNOTS];
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < 2 * K; ++j) Aug[i][j] = 0.0;
+    double h[MET2_MAX_KNOTS];
+    for (int i = 0; i + 1 < K; ++i) h[i] = knots[i + 1] - knots[i];
+    Aug[0][0] = -1.0 / h[0];
+    Aug[0][1] = 1.0 / h[0] + 1.0 / h[1];
+    Aug[0][2] = -1.0 / h[1];
+    for (int i = 1; i + 1 < K; ++i) {
+        Aug[i][i - 1] = h[i - 1] / 6.0;
+        Aug[i][i] = (h[i - 1] + h[i]) / 3.0;
+        Aug[i][i + 1] = h[i] / 6.0;
+        Aug[i][K + i - 1] = 1.0 / h[i - 1];
+        Aug[i][K + i] = -1.0 / h[i - 1] - 1.0 / h[i];
+        Aug[i][K + i + 1] = 1.0 / h[i];
+    }
+    Aug[K - 1][K - 3] = -1.0 / h[K - 3];
+    Aug[K - 1][K - 2] = 1.0 / h[K - 3] + 1.0 / h[K - 2];
+    Aug[K - 1][K - 1] = -1.0 / h[K - 2];
+    for (int c = 0; c < K; ++c) {
+        int piv = c;
+        double best = fabs(Aug[c][c]);
+        for (int r = c + 1; r < K; ++r)
+            if (fabs(Aug[r][c]) > best) {
+                best = fabs(Aug[r][c]);
+                piv = r;
+            }
+        if (piv != c)
+            for (int j = 0; j < 2 * K; ++j) {
+                double t = Aug[c][j];
+                Aug[c][j] = Aug[piv][j];
+                Aug[piv][j] = t;
+            }
+        double inv = 1.0 / Aug[c][c];
+        for (int j = 0; j < 2 * K; ++j) Aug[c][j] *= inv;
+        for (int r = 0; r < K; ++r) {
+            if (r == c) continue;
+            double f = Aug[r][c];
+            if (f != 0.0)
+                for (int j = 0; j < 2 * K; ++j) Aug[r][j] -= f * Aug[c][j];
+        }
+    }
+    for (int i = 0; i < K; ++i)
+        for (int j = 0; j < K; ++j) wsp[i * K + j] = Aug[i][K + j];
+}
+
+__device__ __forceinline__ double spline_eval(const double* xk, const double* yk, const double* mk, int K, double x) {
+    int i = 0;
+    while (i + 2 < K && x >= xk[i + 1]) ++i;
+    double h = xk[i + 1] - xk[i];
+    double a = (xk[i + 1] - x) / h;
+    double b = (x - xk[i]) / h;
+    return a * yk[i] + b * yk[i + 1] + ((a * a * a - a) * mk[i] + (b * b * b - b) * mk[i + 1]) * (h * h) / 6.0;
+}
+
+template <int NS, int ME>
+__global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = A.cfg.nT2, m = A.cfg.nTE, nA = A.cfg.nA;
+    NnlsWork<NS> W;
+    unsigned char* base = smem + (size_t)warp * fa_warp_bytes<NS>(A.pmax);
+    W.carve(base, A.pmax);
+    double* ms = reinterpret_cast<double*>(base + NnlsWork<NS>::bytes(A.pmax));
+    const bool brute = (A.cfg.method == MET2_FA_BRUTE_FORCE);
+    const int K = A.cfg.nKnots;
+    double fs[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) fs[s] = 0.0;
+    const long long gw = (long long)blockIdx.x * FA_WARPS + warp;
+    const long long nw = (long long)gridDim.x * FA_WARPS;
+    for (long long v = gw; v < A.V; v += nw) {
+        unsigned st = load_signal<ME>(A.sig, v, m, ms, lane, false);
+        if (st) {
+            if (lane == 0) {
+                A.fa_index[v] = 0;
+                A.fa_deg[v] = 0.0;
+                A.km[v] = 0.0;
+                A.status[v] |= st;
+            }
+            continue;
+        }
+        int index;
+        if (brute) {
+            index = A.fa_index[v];
+        } else {
+            // knot values and second derivatives into shared scratch: gs = y, rs = Msec, xs = knots
+            if (lane < K) {
+                W.gs[lane] = A.resid[v * K + lane];
+                W.xs[lane] = A.knots[lane];
+            }
+            __syncwarp();
+            if (lane < K) {
+                double acc = 0.0;
+                for (int j = 0; j < K; ++j) acc += A.wsp[lane * K + j] * W.gs[j];
+                W.rs[lane] = acc;
+            }
+            __syncwarp();
+            double fval;
+            int nfev;
+            const double* xk = W.xs;
+            const double* yk = W.gs;
+            const double* mk = W.rs;
+            double xmin = brent_bounded([&](double x) { return spline_eval(xk, yk, mk, K, x); }, A.cfg.brent_lo,
+                                        A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.brent_maxfun, fval, nfev);
+            // indexFA = argmin |alpha_values - res.x| (first minimum; fa_estimation.py:57)
+            double bd = 1.0e300;
+            int bi = -1;
+            for (int i = lane; i < nA; i += 32) {
+                double d = fabs(A.alphas[i] - xmin);
+                if (d < bd) {
+                    bd = d;
+                    bi = i;
+                }
+            }
+            double dmin;
+            index = warp_argmin_nonneg(bd, bi, dmin);
+            if (index < 0) index = 0;
+            __syncwarp();
+        }
+        double kmv = 0.0;
+        if (A.cfg.final_solve) {
+            const double* D = A.dic + (size_t)index * m * n;
+            const double* G = A.G + (size_t)index * n * n;
+            compute_c<NS>(W, D, ms, m, n, lane);
+            int nst = 0;
+            int p = nnls_gram<NS, false>(W, G, nullptr, 0.0, n, m, lane, nst);
+            if (nst && lane == 0) A.status[v] |= MET2_ST_ITMAX;
+            // scatter to column space, km = sum(f)
+#pragma unroll
+            for (int s = 0; s < NS; ++s) W.xc[lane + 32 * s] = 0.0;
+            __syncwarp();
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                int i = lane + 32 * t;
+                if (i < p) W.xc[W.idx[i]] = W.xs[i];
+            }
+            __syncwarp();
+            double part = 0.0;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                double xv = W.xc[lane + 32 * s];
+                fs[s] += xv;
+                part += xv;
+            }
+            kmv = warp_sum(part);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            A.fa_index[v] = index;
+            A.fa_deg[v] = A.alphas[index];
+            A.km[v] = kmv;
+        }
+    }
+    if (A.partial) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            int col = lane + 32 * s;
+            if (col < n) A.partial[gw * n + col] = fs[s];
+        }
+    }
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partial, long long nrows, int n,
+                                       double* __restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double acc = 0.0;
+    for (long long r = 0; r < nrows; ++r) acc += partial[r * n + c];
+    out[c] = acc;
+}
+
+struct FaGeom {
+    int grid;
+    size_t smem;
+    int pmax;
+};
+
+template <int NS>
+static FaGeom fa_geometry(const met2_fa_cfg* cfg) {
+    FaGeom g;
+    g.pmax = cfg->nT2 < cfg->nTE ? cfg->nT2 : cfg->nTE;
+    size_t per_warp = align_up256(NnlsWork<NS>::bytes(g.pmax) + sizeof(double) * 64);
+    g.smem = per_warp * FA_WARPS;
+    int per_sm = (int)((size_t)(200 * 1024) / (g.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 8) per_sm = 8;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    g.grid = sms * per_sm;
+    return g;
+}
+
+static FaGeom fa_geometry_any(const met2_fa_cfg* cfg) {
+    int ns = (cfg->nT2 + 31) / 32;
+    if (ns <= 2) return fa_geometry<2>(cfg);
+    if (ns == 3) return fa_geometry<3>(cfg);
+    return fa_geometry<4>(cfg);
+}
+
+template <int NS, int ME>
+static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
+    cudaError_t e;
+    e = cudaFuncSetAttribute(fa_search_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_search attr: %s", cudaGetErrorString(e));
+    e = cudaFuncSetAttribute(fa_select_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_select attr: %s", cudaGetErrorString(e));
+    fa_search_kernel<NS, ME><<<g.grid, FA_WARPS * 32, g.smem, st>>>(A);
+    count_launch();
+    int rc = check_launch("fa_search_kernel");
+    if (rc) return rc;
+    if (A.cfg.method == MET2_FA_SPLINE) {
+        spline_weights_kernel<<<1, 32, 0, st>>>(A.knots, A.cfg.nKnots, A.wsp);
+        count_launch();
+        rc = check_launch("spline_weights_kernel");
+        if (rc) return rc;
+    }
+    fa_select_kernel<NS, ME><<<g.grid, FA_WARPS * 32, g.smem, st>>>(A);
+    count_launch();
+    rc = check_launch("fa_select_kernel");
+    if (rc) return rc;
+    if (A.fsol_sum) {
+        reduce_partials_kernel<<<(A.cfg.nT2 + 127) / 128, 128, 0, st>>>(A.partial, (long long)g.grid * FA_WARPS,
+                                                                        A.cfg.nT2, A.fsol_sum);
+        count_launch();
+        rc = check_launch("reduce_partials_kernel");
+    }
+    return rc;
+}
+
+}  // namespace met2
+
+using namespace met2;
+
+static int fa_check_cfg(const met2_fa_cfg* cfg) {
+    if (!cfg) return set_error(MET2_ERR_ARG, "met2_fa: cfg is NULL");
+    if (cfg->nT2 <= 0 || cfg->nT2 > MET2_MAX_NT2 || cfg->nTE <= 0 || cfg->nTE > MET2_MAX_NTE || cfg->nA <= 0)
+        return set_error(MET2_ERR_ARG, "met2_fa: unsupported sizes nT2=%d nTE=%d nA=%d", cfg->nT2, cfg->nTE, cfg->nA);
+    if (cfg->method != MET2_FA_BRUTE_FORCE && cfg->method != MET2_FA_SPLINE)
+        return set_error(MET2_ERR_ARG, "met2_fa: unknown method %d", cfg->method);
+    if (cfg->method == MET2_FA_SPLINE && (cfg->nKnots < 4 || cfg->nKnots > MET2_MAX_KNOTS))
+        return set_error(MET2_ERR_ARG, "met2_fa: spline needs 4..%d knots, got %d", MET2_MAX_KNOTS, cfg->nKnots);
+    return MET2_OK;
+}
+
+extern "C" int64_t met2_fa_workspace_bytes(int64_t V, const met2_fa_cfg* cfg) {
+    if (fa_check_cfg(cfg) || V < 0) return -1;
+    FaGeom g = fa_geometry_any(cfg);
+    int nS = cfg->method == MET2_FA_SPLINE ? cfg->nKnots : 1;
+    size_t b = align256(sizeof(double) * (size_t)V * nS);
+    b += align256(sizeof(double) * MET2_MAX_KNOTS * MET2_MAX_KNOTS);
+    b += align256(sizeof(double) * (size_t)g.grid * FA_WARPS * cfg->nT2);
+    return (int64_t)b + 256;
+}
+
+extern "C" int met2_fa_fit(const double* sig, int64_t V, const met2_fa_cfg* cfg, const double* dic, const double* dicT,
+                           const double* G, const double* alphas, const double* dic_s, const double* dicT_s,
+                           const double* G_s, const double* knots, int32_t* fa_index, double* fa_deg, double* km,
+                           double* fsol_sum, uint32_t* status, void* workspace, void* stream) {
+    int rc = fa_check_cfg(cfg);
+    if (rc) return rc;
+    if (V < 0 || !sig || !dic || !dicT || !G || !alphas || !fa_index || !fa_deg || !km || !status || !workspace)
+        return set_error(MET2_ERR_ARG, "met2_fa_fit: NULL argument");
+    const bool spline = cfg->method == MET2_FA_SPLINE;
+    if (spline && (!dic_s || !dicT_s || !G_s || !knots))
+        return set_error(MET2_ERR_ARG, "met2_fa_fit: spline method needs the coarse dictionary and knots");
+    if (V == 0) return MET2_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    FaGeom g = fa_geometry_any(cfg);
+    FaArgs A;
+    A.sig = sig;
+    A.V = V;
+    A.cfg = *cfg;
+    A.dic = dic; A.dicT = dicT; A.G = G; A.alphas = alphas;
+    if (spline) {
+        A.dic_s = dic_s; A.dicT_s = dicT_s; A.G_s = G_s; A.knots = knots;
+        A.nS = cfg->nKnots;
+    } else {
+        A.dic_s = dic; A.dicT_s = dicT; A.G_s = G; A.knots = nullptr;
+        A.nS = cfg->nA;
+    }
+    A.fa_index = fa_index; A.fa_deg = fa_deg; A.km = km; A.fsol_sum = fsol_sum; A.status = status;
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    int nSr = spline ? cfg->nKnots : 1;
+    A.resid = reinterpret_cast<double*>(w);
+    w += align256(sizeof(double) * (size_t)V * nSr);
+    A.wsp = reinterpret_cast<double*>(w);
+    w += align256(sizeof(double) * MET2_MAX_KNOTS * MET2_MAX_KNOTS);
+    A.partial = fsol_sum ? reinterpret_cast<double*>(w) : nullptr;
+    A.pmax = g.pmax;
+    cudaError_t e = cudaMemsetAsync(status, 0, sizeof(uint32_t) * (size_t)V, st);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "memset status: %s", cudaGetErrorString(e));
+    int ns = (cfg->nT2 + 31) / 32;
+    int me = (cfg->nTE + 31) / 32;
+    if (ns <= 2 && me == 1) return fa_launch<2, 1>(A, g, st);
+    if (ns <= 2 && me == 2) return fa_launch<2, 2>(A, g, st);
+    if (ns == 3 && me == 1) return fa_launch<3, 1>(A, g, st);
+    if (ns == 3 && me == 2) return fa_launch<3, 2>(A, g, st);
+    if (ns == 4 && me == 1) return fa_launch<4, 1>(A, g, st);
+    if (ns == 4 && me == 2) return fa_launch<4, 2>(A, g, st);
+    return set_error(MET2_ERR_UNSUPPORTED, "met2_fa_fit: unsupported template sizes");
+}

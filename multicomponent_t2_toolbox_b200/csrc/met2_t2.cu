@@ -1,0 +1,490 @@
+// met2_t2.cu — T2-spectrum estimation and derived maps for a batch of voxels (Steps 3 and 4 of the reference).
+//
+// Takes over fitting_slice_T2 (motor/motor_recon_met2_real_data.py:113-162) with the solvers it dispatches to —
+// nnls (algorithms.py:55), nnls_tik (:262), nnls_x2 (:211-233), nnls_lcurve_wrapper + select_corner (:88-113,150-206),
+// BayesReg_nnls (bayesian_interpolation.py:84-126) — the joblib loop around it (motor...:428-441) and the Step-4
+// metrics loop (motor...:443-472).
+//
+// Layout: voxels are counting-sorted by flip-angle index and cut into tiles of <= T2_TILE voxels that share one index.
+// A persistent CTA takes a tile, stages that angle's Gram matrix G (n x n) and the band forms of K = L^T L and L in
+// shared memory, and its warps pull voxels of the tile one at a time.  One warp owns one voxel from its signal load to
+// its outputs: the whole lambda search (Brent / grid) runs in that warp, nothing per-voxel leaves the SM in between.
+#include <cmath>
+
+#include "met2_device.cuh"
+#include "met2_host.h"
+
+namespace met2 {
+
+constexpr int T2_TILE = 64;
+
+struct T2Args {
+    const double* sig;
+    const int* fa_index;
+    long long V;
+    met2_t2_cfg cfg;
+    const double *dic, *dicT, *G, *kband, *lambdas, *logT2;
+    const unsigned char* comp;
+    double *fsol, *est, *reg, *maps;
+    unsigned* status;
+    // workspace
+    int* hist;        // [nA]
+    int* cursor;      // [nA]
+    int* bin_start;   // [nA + 1]
+    int* perm;        // [V]
+    int* tile_fa;     // [max tiles]
+    int* tile_start;
+    int* tile_cnt;
+    int* counters;    // [0] = number of tiles, [1] = next tile
+    int pmax;
+    int warps;
+};
+
+// ---------------------------------------------------------------------------------------------- sort by FA index
+__global__ void t2_hist_kernel(const int* __restrict__ fa_index, long long V, int nA, int* __restrict__ hist) {
+    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int f = fa_index[v];
+    if (f < 0 || f >= nA) f = 0;   // flagged (and skipped) by the fit kernel
+    atomicAdd(&hist[f], 1);
+}
+
+__global__ void t2_tiles_kernel(const int* __restrict__ hist, int nA, int* __restrict__ bin_start,
+                                int* __restrict__ cursor, int* __restrict__ tile_fa, int* __restrict__ tile_start,
+                                int* __restrict__ tile_cnt, int* __restrict__ counters) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int off = 0, nt = 0;
+    for (int a = 0; a < nA; ++a) {
+        int c = hist[a];
+        bin_start[a] = off;
+        cursor[a] = 0;
+        for (int s = 0; s < c; s += T2_TILE) {
+            tile_fa[nt] = a;
+            tile_start[nt] = off + s;
+            tile_cnt[nt] = (c - s < T2_TILE) ? (c - s) : T2_TILE;
+            ++nt;
+        }
+        off += c;
+    }
+    bin_start[nA] = off;
+    counters[0] = nt;
+    counters[1] = 0;
+}
+
+__global__ void t2_scatter_kernel(const int* __restrict__ fa_index, long long V, int nA,
+                                  const int* __restrict__ bin_start, int* __restrict__ cursor, int* __restrict__ perm) {
+    long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int f = fa_index[v];
+    if (f < 0 || f >= nA) f = 0;
+    int pos = bin_start[f] + atomicAdd(&cursor[f], 1);
+    perm[pos] = (int)v;
+}
+
+// ---------------------------------------------------------------------------------------------- L-curve corner
+// Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves lx/ly of length nl in shared memory.
+__device__ __forceinline__ int select_corner_warp(double* lx, double* ly, int nl, int lane) {
+    // scale both curves to [-10, 10]: ((u-l)/(vmax-vmin)) * (a - (u*vmin - l*vmax)/(u-l))
+    for (int c = 0; c < 2; ++c) {
+        double* a = c ? ly : lx;
+        double vmin = INFINITY, vmax = -INFINITY;
+        bool has_nan = false;
+        for (int i = lane; i < nl; i += 32) {
+            double v = a[i];
+            if (v != v) has_nan = true;
+            vmin = fmin(vmin, v);
+            vmax = fmax(vmax, v);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            vmin = fmin(vmin, __shfl_xor_sync(FULL_MASK, vmin, o));
+            vmax = fmax(vmax, __shfl_xor_sync(FULL_MASK, vmax, o));
+        }
+        if (__any_sync(FULL_MASK, has_nan)) vmin = vmax = NAN;   // numpy min/max propagate NaN
+        double scale = 20.0 / (vmax - vmin);
+        double shift = (10.0 * vmin - (-10.0) * vmax) / 20.0;
+        __syncwarp();
+        for (int i = lane; i < nl; i += 32) a[i] = scale * (a[i] - shift);
+        __syncwarp();
+    }
+    const double cte = 7.0 * 3.141592653589793 / 8.0;
+    const double cx = lx[nl - 1], cy = ly[nl - 1];
+    double best_ang = INFINITY;
+    int best_ord = -1;
+    for (int k = lane; k < nl - 2; k += 32) {
+        double bx = lx[k], by = ly[k];
+        for (int j = k + 1; j < nl - 1; ++j) {
+            double ax = lx[j], ay = ly[j];
+            double dx1 = ax - bx, dy1 = ay - by;
+            double ab = sqrt(dx1 * dx1 + dy1 * dy1);
+            double dx2 = ax - cx, dy2 = ay - cy;
+            double ac = sqrt(dx2 * dx2 + dy2 * dy2);
+            double dx3 = bx - cx, dy3 = by - cy;
+            double bc = sqrt(dx3 * dx3 + dy3 * dy3);
+            double cosa = (ab * ab + ac * ac - bc * bc) / (2.0 * ab * ac);
+            // Python: max(-1.0, min(cosa, 1.0)) -> NaN becomes -1.0
+            if (cosa != cosa) cosa = -1.0;
+            else cosa = fmax(-1.0, fmin(cosa, 1.0));
+            double ang = acos(cosa);
+            double area = 0.5 * ((bx - ax) * (ay - cy) - (ax - cx) * (by - ay));
+            if (area > 0.0 && ang < cte && ang < best_ang) {
+                best_ang = ang;
+                best_ord = k * nl + j;
+            }
+        }
+    }
+    // global minimum angle; ties -> earliest (k, j) in the reference's loop order
+    unsigned long long key = (best_ord >= 0) ? (unsigned long long)__double_as_longlong(best_ang + 0.0) : ~0ull;
+    unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
+    unsigned mlo = __reduce_min_sync(FULL_MASK, (hi == mhi) ? lo : 0xffffffffu);
+    if (mhi == 0xffffffffu && mlo == 0xffffffffu) return nl - 1;
+    bool win = (best_ord >= 0) && hi == mhi && lo == mlo;
+    unsigned ord = __reduce_min_sync(FULL_MASK, win ? (unsigned)best_ord : 0xffffffffu);
+    return (int)(ord % (unsigned)nl);
+}
+
+// ---------------------------------------------------------------------------------------------- fit kernel
+template <int NS>
+__host__ __device__ __forceinline__ size_t t2_warp_bytes(int pmax) {
+    // NnlsWork + signal ms[64] + L-curve curves 2 x 64
+    return align_up256(NnlsWork<NS>::bytes(pmax) + sizeof(double) * (64 + 128));
+}
+
+__host__ __device__ __forceinline__ size_t t2_cta_table_bytes(int n) {
+    // G n*n, kband 10*n, logT2 n, lambdas 64, comp n bytes
+    return align_up256(sizeof(double) * (size_t)(n * n + 10 * n + n + MET2_MAX_LAMBDAS) + (size_t)n);
+}
+
+template <int NS, int ME>
+__global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_tile, s_next;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = A.cfg.nT2, m = A.cfg.nTE;
+    const int method = A.cfg.method;
+    double* sG = reinterpret_cast<double*>(smem);
+    double* skb = sG + n * n;           // K band rows 0..4
+    double* slb = skb + 5 * n;          // L band rows 0..4
+    double* slogT2 = slb + 5 * n;
+    double* slam = slogT2 + n;
+    unsigned char* scomp = reinterpret_cast<unsigned char*>(slam + MET2_MAX_LAMBDAS);
+    unsigned char* wbase = smem + t2_cta_table_bytes(n) + (size_t)warp * t2_warp_bytes<NS>(A.pmax);
+    NnlsWork<NS> W;
+    W.carve(wbase, A.pmax);
+    double* ms = reinterpret_cast<double*>(wbase + NnlsWork<NS>::bytes(A.pmax));
+    double* lcx = ms + 64;
+    double* lcy = lcx + 64;
+
+    for (int i = threadIdx.x; i < 10 * n; i += blockDim.x) skb[i] = A.kband ? A.kband[i] : 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        slogT2[i] = A.logT2[i];
+        scomp[i] = A.comp[i];
+    }
+    for (int i = threadIdx.x; i < MET2_MAX_LAMBDAS; i += blockDim.x)
+        slam[i] = (A.lambdas && i < A.cfg.nLambda) ? A.lambdas[i] : 0.0;
+    const int ntiles = A.counters[0];
+
+    while (true) {
+        __syncthreads();   // previous tile fully consumed (G, s_next) before they are overwritten
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(&A.counters[1], 1);
+            s_next = 0;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const int fa = A.tile_fa[tile];
+        const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
+        {
+            const double* Gg = A.G + (size_t)fa * n * n;
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) sG[i] = Gg[i];
+        }
+        __syncthreads();
+        const double* D = A.dic + (size_t)fa * m * n;
+        const double* Dt = A.dicT + (size_t)fa * n * m;
+
+        while (true) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&s_next, 1);
+            it = __shfl_sync(FULL_MASK, it, 0);
+            if (it >= tcnt) break;
+            const long long v = A.perm[tstart + it];
+            unsigned st = 0u;
+            // ---- load, validity (motor...:124-131), normalise by km = M[0]
+            double s = 0.0;
+            bool bad = false;
+#pragma unroll
+            for (int u = 0; u < ME; ++u) {
+                int e = lane + 32 * u;
+                if (e < m) {
+                    double xv = A.sig[v * m + e];
+                    ms[e] = xv;
+                    s += xv;
+                    if (!isfinite(xv)) bad = true;
+                }
+            }
+            s = warp_sum(s);
+            bad = __any_sync(FULL_MASK, bad);
+            __syncwarp();
+            const int fav = A.fa_index[v];
+            const double km = ms[0];
+            if (bad) st = MET2_ST_NONFINITE | MET2_ST_SKIPPED;
+            else if (!(s > 0.0) || !(km > 0.0) || fav < 0 || fav >= A.cfg.nA) st = MET2_ST_SKIPPED;
+            double regv = 0.0;
+            int p = 0;
+            double fit[ME];
+#pragma unroll
+            for (int u = 0; u < ME; ++u) fit[u] = 0.0;
+            if (!st) {
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < ME; ++u) {
+                    int e = lane + 32 * u;
+                    if (e < m) ms[e] = ms[e] / km;
+                }
+                __syncwarp();
+                compute_c<NS>(W, D, ms, m, n, lane);
+                int nst = 0;
+                if (method == MET2_REG_NNLS) {
+                    p = nnls_gram<NS, false>(W, sG, nullptr, 0.0, n, m, lane, nst);
+                    regv = 0.0;
+                } else if (method == MET2_REG_T2SPARC) {
+                    regv = A.cfg.lambda_fixed;
+                    p = nnls_gram<NS, true>(W, sG, skb, regv, n, m + n, lane, nst);
+                } else if (method == MET2_REG_X2) {
+                    // algorithms.py:211-233
+                    p = nnls_gram<NS, false>(W, sG, nullptr, 0.0, n, m, lane, nst);
+                    const double SSE = fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
+                    if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
+                    const double factor = A.cfg.factor;
+                    double fval;
+                    int nfev;
+                    double reg_opt = brent_bounded(
+                        [&](double lamx) {
+                            int pp = nnls_gram<NS, true>(W, sG, skb, lamx, n, m + n, lane, nst);
+                            double sser = fit_and_sse<NS, ME>(W, Dt, ms, m, pp, lane, fit);
+                            return fabs(sser - factor * SSE) / SSE;
+                        },
+                        A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun, fval, nfev);
+                    p = nnls_gram<NS, true>(W, sG, skb, reg_opt, n, m + n, lane, nst);
+                    double sser = fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
+                    regv = sser / SSE;   // the orchestrator stores k_est, not lambda (motor...:141-143)
+                } else if (method == MET2_REG_LCURVE) {
+                    // algorithms.py:88-113 on the 50-point grid, then nnls_tik at the corner (motor...:145-146)
+                    const int nl = A.cfg.nLambda;
+                    for (int i = 0; i < nl; ++i) {
+                        int pp = nnls_gram<NS, true>(W, sG, skb, slam[i], n, m + n, lane, nst);
+                        double sse = fit_and_sse<NS, ME>(W, Dt, ms, m, pp, lane, fit);
+                        double nrm = reg_norm2<NS>(W, slb, n, lane);
+                        if (lane == 0) {
+                            lcx[i] = log(sse + 1e-200);
+                            lcy[i] = log(nrm + 1e-200);
+                        }
+                        __syncwarp();
+                    }
+                    int corner = select_corner_warp(lcx, lcy, nl, lane);
+                    regv = slam[corner];
+                    p = nnls_gram<NS, true>(W, sG, skb, regv, n, m + n, lane, nst);
+                }
+                if (nst) st |= MET2_ST_ITMAX;
+                (void)fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
+            }
+            // ---- outputs: fsol = x*km, Est_Signal = (D x)*km, reg, maps (motor...:153-155, 443-472)
+#pragma unroll
+            for (int sidx = 0; sidx < NS; ++sidx) W.xc[lane + 32 * sidx] = 0.0;
+            __syncwarp();
+            if (!(st & MET2_ST_SKIPPED)) {
+#pragma unroll
+                for (int t = 0; t < NS; ++t) {
+                    int i = lane + 32 * t;
+                    if (i < p) W.xc[W.idx[i]] = W.xs[i];
+                }
+            }
+            __syncwarp();
+            const bool fitted = !(st & MET2_ST_SKIPPED);
+            const double kmo = fitted ? km : 0.0;
+            double xk[NS];
+            double vt = 0.0;
+#pragma unroll
+            for (int sidx = 0; sidx < NS; ++sidx) {
+                int col = lane + 32 * sidx;
+                xk[sidx] = (col < n && fitted) ? W.xc[col] * kmo : 0.0;
+                vt += xk[sidx];
+                if (col < n) A.fsol[v * n + col] = xk[sidx];
+            }
+#pragma unroll
+            for (int u = 0; u < ME; ++u) {
+                int e = lane + 32 * u;
+                if (e < m) A.est[v * m + e] = fitted ? fit[u] * kmo : 0.0;
+            }
+            vt = warp_sum(vt) + 1.0e-16;
+            double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
+#pragma unroll
+            for (int sidx = 0; sidx < NS; ++sidx) {
+                int col = lane + 32 * sidx;
+                if (col < n) {
+                    double xn = xk[sidx] / vt;
+                    unsigned char cm = scomp[col];
+                    if (cm & 1) {
+                        sm += xn;
+                        lm += xn * slogT2[col];
+                    }
+                    if (cm & 2) {
+                        stt += xn;
+                        lt += xn * slogT2[col];
+                    }
+                    if (cm & 4) sc += xn;
+                }
+            }
+            sm = warp_sum(sm);
+            stt = warp_sum(stt);
+            sc = warp_sum(sc);
+            lm = warp_sum(lm);
+            lt = warp_sum(lt);
+            if (lane == 0) {
+                double* mp = A.maps + v * 6;
+                mp[0] = sm;
+                mp[1] = stt;
+                mp[2] = sc;
+                mp[3] = exp(lm / (sm + 1.0e-16));
+                mp[4] = exp(lt / (stt + 1.0e-16));
+                mp[5] = vt;
+                A.reg[v] = fitted ? regv : 0.0;
+                A.status[v] = st;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+struct T2Geom {
+    int grid, warps, pmax, max_tiles;
+    size_t smem;
+};
+
+template <int NS>
+static T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
+    T2Geom g;
+    const int n = cfg->nT2, m = cfg->nTE;
+    const bool plain = (cfg->method == MET2_REG_NNLS);
+    g.pmax = plain ? (n < m ? n : m) : n;
+    size_t tables = t2_cta_table_bytes(n);
+    size_t per_warp = t2_warp_bytes<NS>(g.pmax);
+    size_t budget = 227 * 1024 - 2048;
+    int warps = (int)((budget - tables) / per_warp);
+    if (warps > 16) warps = 16;
+    if (warps < 1) warps = 1;
+    g.warps = warps;
+    g.smem = tables + per_warp * warps;
+    int per_sm = (int)(budget / (g.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    g.grid = sms * per_sm;
+    g.max_tiles = (int)(V / T2_TILE) + cfg->nA + 1;
+    return g;
+}
+
+static T2Geom t2_geometry_any(long long V, const met2_t2_cfg* cfg) {
+    int ns = (cfg->nT2 + 31) / 32;
+    if (ns <= 2) return t2_geometry<2>(V, cfg);
+    if (ns == 3) return t2_geometry<3>(V, cfg);
+    return t2_geometry<4>(V, cfg);
+}
+
+template <int NS, int ME>
+static int t2_launch(const T2Args& A, const T2Geom& g, cudaStream_t st) {
+    cudaError_t e =
+        cudaFuncSetAttribute(t2_fit_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_fit attr (%zu B): %s", g.smem, cudaGetErrorString(e));
+    t2_fit_kernel<NS, ME><<<g.grid, g.warps * 32, g.smem, st>>>(A);
+    count_launch();
+    return check_launch("t2_fit_kernel");
+}
+
+}  // namespace met2
+
+using namespace met2;
+
+static int t2_check_cfg(const met2_t2_cfg* cfg) {
+    if (!cfg) return set_error(MET2_ERR_ARG, "met2_t2: cfg is NULL");
+    if (cfg->nT2 <= 0 || cfg->nT2 > MET2_MAX_NT2 || cfg->nTE <= 0 || cfg->nTE > MET2_MAX_NTE || cfg->nA <= 0)
+        return set_error(MET2_ERR_ARG, "met2_t2: unsupported sizes nT2=%d nTE=%d nA=%d", cfg->nT2, cfg->nTE, cfg->nA);
+    if (cfg->method < MET2_REG_NNLS || cfg->method > MET2_REG_BAYESREG)
+        return set_error(MET2_ERR_ARG, "met2_t2: unknown method %d", cfg->method);
+    if (cfg->method == MET2_REG_GCV || cfg->method == MET2_REG_BAYESREG)
+        return set_error(MET2_ERR_UNSUPPORTED, "met2_t2: method %d not implemented yet", cfg->method);
+    if (cfg->method == MET2_REG_LCURVE && (cfg->nLambda < 3 || cfg->nLambda > MET2_MAX_LAMBDAS))
+        return set_error(MET2_ERR_ARG, "met2_t2: L-curve needs 3..%d lambdas", MET2_MAX_LAMBDAS);
+    return MET2_OK;
+}
+
+extern "C" int64_t met2_t2_workspace_bytes(int64_t V, const met2_t2_cfg* cfg) {
+    if (t2_check_cfg(cfg) || V < 0) return -1;
+    T2Geom g = t2_geometry_any(V, cfg);
+    size_t b = 0;
+    b += align256(sizeof(int) * (size_t)cfg->nA) * 2;
+    b += align256(sizeof(int) * (size_t)(cfg->nA + 1));
+    b += align256(sizeof(int) * (size_t)V);
+    b += align256(sizeof(int) * (size_t)g.max_tiles) * 3;
+    b += align256(sizeof(int) * 4);
+    return (int64_t)b + 256;
+}
+
+extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg,
+                           const double* dic, const double* dicT, const double* G, const double* kband,
+                           const double* lambdas, const double* logT2, const uint8_t* comp, double* fsol,
+                           double* est_signal, double* reg, double* maps, uint32_t* status, void* workspace,
+                           void* stream) {
+    int rc = t2_check_cfg(cfg);
+    if (rc) return rc;
+    if (V < 0 || !sig || !fa_index || !dic || !dicT || !G || !logT2 || !comp || !fsol || !est_signal || !reg || !maps ||
+        !status || !workspace)
+        return set_error(MET2_ERR_ARG, "met2_t2_fit: NULL argument");
+    if (cfg->method != MET2_REG_NNLS && !kband)
+        return set_error(MET2_ERR_ARG, "met2_t2_fit: regularised methods need kband (met2_gram_tables)");
+    if (cfg->method == MET2_REG_LCURVE && !lambdas) return set_error(MET2_ERR_ARG, "met2_t2_fit: L-curve needs lambdas");
+    if (V == 0) return MET2_OK;
+    if (V > 0x7fffffffLL) return set_error(MET2_ERR_ARG, "met2_t2_fit: V too large for one call");
+    cudaStream_t st = (cudaStream_t)stream;
+    T2Geom g = t2_geometry_any(V, cfg);
+    T2Args A;
+    A.sig = sig; A.fa_index = fa_index; A.V = V; A.cfg = *cfg;
+    A.dic = dic; A.dicT = dicT; A.G = G; A.kband = kband; A.lambdas = lambdas; A.logT2 = logT2; A.comp = comp;
+    A.fsol = fsol; A.est = est_signal; A.reg = reg; A.maps = maps; A.status = status;
+    unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    A.hist = reinterpret_cast<int*>(w);        w += align256(sizeof(int) * (size_t)cfg->nA);
+    A.cursor = reinterpret_cast<int*>(w);      w += align256(sizeof(int) * (size_t)cfg->nA);
+    A.bin_start = reinterpret_cast<int*>(w);   w += align256(sizeof(int) * (size_t)(cfg->nA + 1));
+    A.perm = reinterpret_cast<int*>(w);        w += align256(sizeof(int) * (size_t)V);
+    A.tile_fa = reinterpret_cast<int*>(w);     w += align256(sizeof(int) * (size_t)g.max_tiles);
+    A.tile_start = reinterpret_cast<int*>(w);  w += align256(sizeof(int) * (size_t)g.max_tiles);
+    A.tile_cnt = reinterpret_cast<int*>(w);    w += align256(sizeof(int) * (size_t)g.max_tiles);
+    A.counters = reinterpret_cast<int*>(w);
+    A.pmax = g.pmax;
+    A.warps = g.warps;
+    cudaError_t e = cudaMemsetAsync(A.hist, 0, sizeof(int) * (size_t)cfg->nA, st);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "memset hist: %s", cudaGetErrorString(e));
+    const int tb = 256;
+    const unsigned nb = (unsigned)((V + tb - 1) / tb);
+    t2_hist_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.hist);
+    count_launch();
+    if ((rc = check_launch("t2_hist_kernel"))) return rc;
+    t2_tiles_kernel<<<1, 32, 0, st>>>(A.hist, cfg->nA, A.bin_start, A.cursor, A.tile_fa, A.tile_start, A.tile_cnt,
+                                      A.counters);
+    count_launch();
+    if ((rc = check_launch("t2_tiles_kernel"))) return rc;
+    t2_scatter_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);
+    count_launch();
+    if ((rc = check_launch("t2_scatter_kernel"))) return rc;
+    int ns = (cfg->nT2 + 31) / 32;
+    int me = (cfg->nTE + 31) / 32;
+    if (ns <= 2 && me == 1) return t2_launch<2, 1>(A, g, st);
+    if (ns <= 2 && me == 2) return t2_launch<2, 2>(A, g, st);
+    if (ns == 3 && me == 1) return t2_launch<3, 1>(A, g, st);
+    if (ns == 3 && me == 2) return t2_launch<3, 2>(A, g, st);
+    if (ns == 4 && me == 1) return t2_launch<4, 1>(A, g, st);
+    if (ns == 4 && me == 2) return t2_launch<4, 2>(A, g, st);
+    return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: unsupported template sizes");
+}
