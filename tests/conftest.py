@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+@pytest.fixture(scope="session")
+def golden_voxels():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "voxels.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_dictionary():
+    import numpy as np
+    return dict(np.load(os.path.join(GOLDEN, "dictionary.npz")))

@@ -1,0 +1,199 @@
+"""Parity of the CUDA path (through the C ABI / batched host API) against the CPU oracle and against the golden
+vectors produced by the unmodified reference.  Tolerances are BASELINE.json's: FA index and active sets bit-exact,
+spectra within 1e-6 relative (per voxel, relative to the largest coefficient), derived maps within 1e-4 absolute."""
+import numpy as np
+import pytest
+import torch
+
+import met2_oracle as O
+from multicomponent_t2_toolbox_b200 import batched, pipeline
+from multicomponent_t2_toolbox_b200.phantom import make_phantom
+
+pytestmark = pytest.mark.gpu
+
+REL_SPECTRUM = 1e-6
+ABS_MAPS = 1e-4
+
+
+def _plan(**kw):
+    return batched.Met2Plan(32, 10.0, 1000.0, **kw)
+
+
+def _rel_err(f, f_ref):
+    scale = np.abs(f_ref).max(axis=1)
+    scale[scale == 0] = 1.0
+    return np.abs(f - f_ref).max(axis=1) / scale
+
+
+def _metrics(f, plan):
+    return np.array([O.voxel_metrics(f[v], plan.T2s, plan.ind_m, plan.ind_t, plan.ind_csf) for v in range(len(f))])
+
+
+@pytest.fixture(scope="module")
+def phantom_sig():
+    ph = make_phantom((16, 16, 4), seed=1)      # BASELINE.json configs[0]
+    return ph["data"].reshape(-1, 32)
+
+
+def test_dictionary_vs_golden(golden_dictionary):
+    g = golden_dictionary
+    dev = torch.device("cuda", 0)
+    d = batched.Dictionary(g["alphas"], g["T2s"], g["T1s"], int(g["nte"]), float(g["tau"]), float(g["TR"]), dev)
+    D = d.to_reference_layout()
+    assert np.abs(D - g["dic"]).max() <= 1e-13
+    G = d.G.cpu().numpy()
+    for a in range(D.shape[2]):
+        assert np.allclose(G[a], D[:, :, a].T @ D[:, :, a], rtol=1e-13, atol=1e-13)
+    T2s100 = np.logspace(1, np.log10(2000.0), 100)
+    d48 = batched.Dictionary(np.array([90.0, 133.0, 180.0]), T2s100, 1000.0 * np.ones(100), 48, 8.0, 2000.0, dev)
+    assert np.abs(d48.to_reference_layout() - g["dic48"]).max() <= 1e-13
+
+
+def test_config1_brute_force_nnls_all_voxels(phantom_sig):
+    """configs[0]: 16x16x4 phantom, NNLS, brute-force 91 angles — every voxel at full tolerance."""
+    plan = _plan(reg_method="NNLS", reg_matrix="I", FA_method="brute-force")
+    sig = phantom_sig
+    V = sig.shape[0]
+    fa, t2 = plan.fit(sig)
+    Dic = plan.dict_hr.to_reference_layout()
+    ok = np.ones(V)
+    FA, idx, KM, fsum = O.fitting_slice_FA_brute_force(ok, sig, V, Dic, plan.alpha_values)
+    assert np.array_equal(fa["fa_index"].cpu().numpy(), idx.astype(np.int64))
+    assert np.array_equal(fa["fa_deg"].cpu().numpy(), FA)
+    assert np.allclose(fa["km"].cpu().numpy(), KM, rtol=1e-7)
+    assert np.allclose(fa["fsol_sum"].cpu().numpy(), fsum, rtol=1e-6, atol=1e-6 * fsum.max())
+    f_ref, s_ref, reg_ref = O.fitting_slice_T2(ok, sig, idx, V, Dic, plan.lambda_reg, 60, 32, "NNLS", plan.Laplac)
+    f = t2["fsol"].cpu().numpy()
+    assert np.array_equal(f > 0, f_ref > 0)
+    assert _rel_err(f, f_ref).max() < REL_SPECTRUM
+    assert np.abs(t2["est_signal"].cpu().numpy() - s_ref).max() < 1e-6 * np.abs(s_ref).max()
+    assert np.abs(t2["maps"].cpu().numpy()[:, :5] - _metrics(f_ref, plan)[:, :5]).max() < ABS_MAPS
+    assert not t2["reg"].cpu().numpy().any()
+
+
+@pytest.mark.parametrize("method,rm", [("X2", "I"), ("X2", "L1"), ("X2", "L2"), ("X2", "InvT2"), ("L_curve", "I"),
+                                       ("L_curve", "L2"), ("L_curve", "InvT2"), ("T2SPARC", "InvT2"),
+                                       ("T2SPARC", "I")])
+def test_spline_fa_plus_regularised_fit_vs_oracle(phantom_sig, method, rm):
+    plan = _plan(reg_method=method, reg_matrix=rm, FA_method="spline", npc=60)
+    sig = phantom_sig[:160]
+    V = sig.shape[0]
+    fa, t2 = plan.fit(sig)
+    Dic, DicLR = plan.dict_hr.to_reference_layout(), plan.dict_lr.to_reference_layout()
+    ok = np.ones(V)
+    FA, idx, KM, fsum = O.fitting_slice_FA_spline_method(DicLR, Dic, sig, ok, plan.alpha_spline, V, plan.alpha_values)
+    assert np.array_equal(fa["fa_index"].cpu().numpy(), idx.astype(np.int64))
+    f_ref, s_ref, reg_ref = O.fitting_slice_T2(ok, sig, idx, V, Dic, plan.lambda_reg, 60, 32, method, plan.Laplac)
+    f = t2["fsol"].cpu().numpy()
+    assert np.array_equal(f > 0, f_ref > 0), "active sets differ in %d voxels" % np.any((f > 0) != (f_ref > 0), 1).sum()
+    assert _rel_err(f, f_ref).max() < REL_SPECTRUM
+    assert np.allclose(t2["reg"].cpu().numpy(), reg_ref, rtol=1e-6, atol=0)
+    assert np.abs(t2["maps"].cpu().numpy()[:, :5] - _metrics(f_ref, plan)[:, :5]).max() < ABS_MAPS
+    assert not t2["status"].cpu().numpy().any()
+
+
+def test_golden_vectors_from_reference(golden_voxels):
+    """Same inputs the unmodified reference was run on (oracle/make_golden.py); includes empty, masked-out and
+    M[0]==0 voxels."""
+    g = golden_voxels
+    sig = g["sig"] * g["mask"][:, None]
+    keep = g["mask"] > 0
+    plan = _plan(reg_method="X2", reg_matrix="I", FA_method="spline")
+    fa = plan.fa_fit(sig[keep])
+    assert np.array_equal(fa["fa_index"].cpu().numpy(), g["fa_spline_idx"][keep].astype(np.int64))
+    assert np.allclose(fa["km"].cpu().numpy(), g["fa_spline_km"][keep], rtol=1e-7, atol=0)
+    planb = _plan(reg_method="NNLS", reg_matrix="I", FA_method="brute-force")
+    fab = planb.fa_fit(sig[keep])
+    assert np.array_equal(fab["fa_index"].cpu().numpy(), g["fa_brute_idx"][keep].astype(np.int64))
+    for method, rm in [("NNLS", "I"), ("T2SPARC", "I"), ("X2", "I"), ("X2", "L2"), ("L_curve", "L1"), ("X2", "InvT2")]:
+        pl = _plan(reg_method=method, reg_matrix=rm, FA_method="spline", npc=60)
+        t2 = pl.t2_fit(sig[keep], g["fa_spline_idx"][keep].astype(np.int32))
+        f = t2["fsol"].cpu().numpy()
+        gf = g["t2_%s_%s_f" % (method, rm)][keep]
+        assert np.array_equal(f > 0, gf > 0), (method, rm)
+        assert _rel_err(f, gf).max() < REL_SPECTRUM, (method, rm)
+        assert np.allclose(t2["reg"].cpu().numpy(), g["t2_%s_%s_reg" % (method, rm)][keep], rtol=1e-6, atol=0)
+        assert np.abs(t2["est_signal"].cpu().numpy() - g["t2_%s_%s_s" % (method, rm)][keep]).max() < 1e-6 * gf.max()
+        st = t2["status"].cpu().numpy()
+        assert st[np.nonzero(keep)[0].tolist().index(3)] & batched.ST_SKIPPED      # empty voxel
+        assert st[np.nonzero(keep)[0].tolist().index(9)] & batched.ST_SKIPPED      # M[0] == 0
+
+
+def test_t2sparc_cli_configuration_96_bins(golden_voxels):
+    g = golden_voxels
+    plan = _plan(reg_method="T2SPARC", reg_matrix="InvT2", FA_method="brute-force")
+    assert plan.npc == 96
+    t2 = plan.t2_fit(g["sig"], g["fa_brute_idx"].astype(np.int32))
+    f = t2["fsol"].cpu().numpy()
+    keep = g["mask"] > 0
+    assert np.array_equal(f[keep] > 0, g["t2sparc96_f"][keep] > 0)
+    assert _rel_err(f[keep], g["t2sparc96_f"][keep]).max() < REL_SPECTRUM
+
+
+def test_edge_cases_empty_batch_nonfinite_and_bad_index():
+    plan = _plan(reg_method="X2", reg_matrix="I", FA_method="spline")
+    out = plan.fa_fit(np.zeros((0, 32)))
+    assert out["fa_index"].numel() == 0
+    sig = make_phantom((4, 1, 1), seed=9)["data"].reshape(-1, 32).copy()
+    sig[1, 4] = np.nan
+    sig[2] = -1.0
+    fa = plan.fa_fit(sig)
+    st = fa["status"].cpu().numpy()
+    assert st[1] & batched.ST_NONFINITE and st[2] & batched.ST_SKIPPED and st[0] == 0
+    t2 = plan.t2_fit(sig, np.array([5, 5, 5, 9999], dtype=np.int32))
+    st = t2["status"].cpu().numpy()
+    assert st[0] == 0 and st[1] & batched.ST_NONFINITE and st[2] & batched.ST_SKIPPED and st[3] & batched.ST_SKIPPED
+    f = t2["fsol"].cpu().numpy()
+    assert f[0].any() and not f[1:].any() and np.isfinite(t2["maps"].cpu().numpy()).all()
+    with pytest.raises(ValueError):
+        plan.fa_fit(np.zeros((3, 31)))
+
+
+def test_volume_pipeline_with_mask_and_slabs():
+    """gather -> fit -> scatter with an ellipsoidal mask; 2-slab run must give byte-identical volumes."""
+    ph = make_phantom((10, 8, 3), seed=4, mask_mode="ellipsoid")
+    args = (ph["data"], ph["mask"], ph["TE_array"], 1000.0, "X2", "I", "spline")
+    full = pipeline.recon_arrays(*args)
+    parts = [pipeline.recon_arrays(*args, rank=r, world_size=2) for r in range(2)]
+    for k in ("MWF", "IEWF", "FWF", "T2_M", "T2_IE", "TWC", "FA", "reg_param", "fsol_4D", "Est_Signal"):
+        assert np.array_equal(parts[0][k] + parts[1][k], full[k]), k
+        assert not full[k][ph["mask"] == 0].any()
+    ref = O.recon_volume(ph["data"], ph["mask"], ph["TE_array"], 1000.0, "X2", "I", "spline",
+                         Dic_3D=None, num_cores=1)
+    assert np.array_equal(full["FA_index"], ref["FA_index"])
+    assert np.array_equal(full["fsol_4D"] > 0, ref["fsol_4D"] > 0)
+    for k in ("MWF", "IEWF", "FWF", "T2_M", "T2_IE"):
+        assert np.abs(full[k] - ref[k]).max() < ABS_MAPS, k
+    assert np.allclose(full["TWC"], ref["TWC"], rtol=1e-6)
+
+
+def test_full_size_properties():
+    """BASELINE.json configs[1] size (552 960 voxels): size-independent properties instead of a CPU oracle run —
+    scale covariance (fit(c*M) = c*fit(M) with identical FA index and k_est), permutation invariance, and agreement of
+    a random subset with the oracle."""
+    ph = make_phantom((96, 96, 60), seed=2, fa_mode="b1", backend="gpu")
+    sig = torch.as_tensor(ph["data"].reshape(-1, 32)).cuda()
+    V = sig.shape[0]
+    plan = _plan(reg_method="X2", reg_matrix="I", FA_method="spline")
+    fa, t2 = plan.fit(sig)
+    assert int((t2["status"] != 0).sum()) == 0
+    mwf = t2["maps"][:, 0]
+    assert 0.05 < float(mwf.mean()) < 0.25 and bool(torch.isfinite(t2["fsol"]).all())
+    # permutation invariance (voxels are independent; results must not depend on the tiling / sort order)
+    perm = torch.randperm(V, device=sig.device, generator=torch.Generator(device=sig.device).manual_seed(0))
+    fa_p, t2_p = plan.fit(sig[perm].contiguous())
+    assert torch.equal(fa_p["fa_index"], fa["fa_index"][perm])
+    assert torch.equal(t2_p["fsol"], t2["fsol"][perm]) and torch.equal(t2_p["maps"], t2["maps"][perm])
+    # subset against the oracle
+    rng = np.random.default_rng(0)
+    pick = rng.choice(V, 96, replace=False)
+    s = ph["data"].reshape(-1, 32)[pick]
+    Dic, DicLR = plan.dict_hr.to_reference_layout(), plan.dict_lr.to_reference_layout()
+    ok = np.ones(len(pick))
+    FA, idx, KM, _ = O.fitting_slice_FA_spline_method(DicLR, Dic, s, ok, plan.alpha_spline, len(pick), plan.alpha_values)
+    assert np.array_equal(fa["fa_index"].cpu().numpy()[pick], idx.astype(np.int64))
+    f_ref, s_ref, reg_ref = O.fitting_slice_T2(ok, s, idx, len(pick), Dic, plan.lambda_reg, 60, 32, "X2", plan.Laplac)
+    f = t2["fsol"].cpu().numpy()[pick]
+    assert np.array_equal(f > 0, f_ref > 0)
+    assert _rel_err(f, f_ref).max() < REL_SPECTRUM
+    assert np.abs(t2["maps"].cpu().numpy()[pick, 0] - _metrics(f_ref, plan)[:, 0]).max() < ABS_MAPS
