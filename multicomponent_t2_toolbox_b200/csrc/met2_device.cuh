@@ -6,24 +6,61 @@ namespace met2 {
 
 // SciPy's bounded Brent (scipy/optimize/_optimize.py:_minimize_scalar_bounded), reached from
 // algorithms.py:219,280, bayesian_interpolation.py:101 (fminbound) and fa_estimation.py:55 (minimize_scalar 'Bounded').
-// Branch-for-branch restatement; the objective is evaluated warp-uniformly.
-template <class F>
-__device__ __forceinline__ double brent_bounded(F&& func, double x1, double x2, double xatol, int maxfun, double& fval,
-                                                int& nfev) {
-    const double sqrt_eps = 1.4832396974191326e-08;  // sqrt(2.2e-16)
-    const double golden_mean = 0.3819660112501051;   // 0.5 * (3 - sqrt(5))
-    double a = x1, b = x2;
-    double fulc = a + golden_mean * (b - a);
-    double nfc = fulc, xf = fulc;
-    double rat = 0.0, e = 0.0;
-    double x = xf;
-    double fx = func(x);
-    int num = 1;
-    double ffulc = fx, fnfc = fx;
-    double xm = 0.5 * (a + b);
-    double tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
-    double tol2 = 2.0 * tol1;
-    while (fabs(xf - xm) > (tol2 - 0.5 * (b - a))) {
+// Branch-for-branch restatement turned inside out into a resumable state machine so that the
+// caller's objective (an NNLS solve) has a single inlined call site:
+//     x = B.start(lo, hi, xatol, maxfun);  do { f = objective(x); } while (B.feed(f, x));  result = B.xf
+// Warp-uniform: every lane carries the same state.
+struct Brent {
+    double a, b, fulc, nfc, xf, rat, e, fx, ffulc, fnfc, xm, tol1, tol2, xatol, x;
+    int num, maxfun;
+
+    __device__ __forceinline__ double start(double x1, double x2, double xatol_, int maxfun_) {
+        const double golden_mean = 0.3819660112501051;   // 0.5 * (3 - sqrt(5))
+        a = x1;
+        b = x2;
+        xatol = xatol_;
+        maxfun = maxfun_;
+        fulc = a + golden_mean * (b - a);
+        nfc = fulc;
+        xf = fulc;
+        rat = 0.0;
+        e = 0.0;
+        x = xf;
+        num = 0;
+        return x;
+    }
+
+    // Consume fu = f(x) for the abscissa last handed out.  Returns true and sets xnext if another evaluation is needed.
+    __device__ __forceinline__ bool feed(double fu, double& xnext) {
+        const double sqrt_eps = 1.4832396974191326e-08;  // sqrt(2.2e-16)
+        const double golden_mean = 0.3819660112501051;
+        if (num == 0) {
+            fx = fu;
+            num = 1;
+            ffulc = fx;
+            fnfc = fx;
+        } else {
+            ++num;
+            if (fu <= fx) {
+                if (x >= xf) a = xf; else b = xf;
+                fulc = nfc; ffulc = fnfc;
+                nfc = xf; fnfc = fx;
+                xf = x; fx = fu;
+            } else {
+                if (x < xf) a = x; else b = x;
+                if ((fu <= fnfc) || (nfc == xf)) {
+                    fulc = nfc; ffulc = fnfc;
+                    nfc = x; fnfc = fu;
+                } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
+                    fulc = x; ffulc = fu;
+                }
+            }
+        }
+        xm = 0.5 * (a + b);
+        tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
+        tol2 = 2.0 * tol1;
+        if (num > 1 && num >= maxfun) return false;
+        if (!(fabs(xf - xm) > (tol2 - 0.5 * (b - a)))) return false;
         bool golden = true;
         if (fabs(e) > tol1) {
             golden = false;
@@ -37,8 +74,8 @@ __device__ __forceinline__ double brent_bounded(F&& func, double x1, double x2, 
             e = rat;
             if ((fabs(p) < fabs(0.5 * q * r)) && (p > q * (a - xf)) && (p < q * (b - xf))) {
                 rat = (p + 0.0) / q;
-                x = xf + rat;
-                if (((x - a) < tol2) || ((b - x) < tol2)) {
+                double xt = xf + rat;
+                if (((xt - a) < tol2) || ((b - xt) < tol2)) {
                     double d = xm - xf;
                     double si = (d > 0.0) ? 1.0 : ((d < 0.0) ? -1.0 : ((d == 0.0) ? 1.0 : d));
                     rat = tol1 * si;
@@ -53,87 +90,96 @@ __device__ __forceinline__ double brent_bounded(F&& func, double x1, double x2, 
         }
         double si = (rat > 0.0) ? 1.0 : ((rat < 0.0) ? -1.0 : ((rat == 0.0) ? 1.0 : rat));
         x = xf + si * fmax(fabs(rat), tol1);
-        double fu = func(x);
-        ++num;
-        if (fu <= fx) {
-            if (x >= xf) a = xf; else b = xf;
-            fulc = nfc; ffulc = fnfc;
-            nfc = xf; fnfc = fx;
-            xf = x; fx = fu;
-        } else {
-            if (x < xf) a = x; else b = x;
-            if ((fu <= fnfc) || (nfc == xf)) {
-                fulc = nfc; ffulc = fnfc;
-                nfc = x; fnfc = fu;
-            } else if ((fu <= ffulc) || (fulc == xf) || (fulc == nfc)) {
-                fulc = x; ffulc = fu;
-            }
-        }
-        xm = 0.5 * (a + b);
-        tol1 = sqrt_eps * fabs(xf) + xatol / 3.0;
-        tol2 = 2.0 * tol1;
-        if (num >= maxfun) break;
+        xnext = x;
+        return true;
     }
-    fval = fx;
-    nfev = num;
-    return xf;
-}
+};
 
-// c = D^T M into W.cc (column space).  D is [m][n] row-major; ms[0..m) is the signal in shared memory.
+// c = D^T M into S[W.cc..] (column space).  D is [m][n] row-major in global memory; S[oM + 0..m) is the signal.
 template <int NS>
-__device__ __forceinline__ void compute_c(const NnlsWork<NS>& W, const double* __restrict__ D, const double* ms, int m,
-                                          int n, int lane) {
-    double acc[NS];
+__device__ __forceinline__ void compute_c(const Slots<NS>& W, const double* __restrict__ D, int oM, int m, int n,
+                                          int lane) {
+    double a0[NS], a1[NS];
 #pragma unroll
-    for (int s = 0; s < NS; ++s) acc[s] = 0.0;
-    for (int e = 0; e < m; ++e) {
-        double me = ms[e];
-        const double* drow = D + e * n;
+    for (int s = 0; s < NS; ++s) a0[s] = a1[s] = 0.0;
+    int e = 0;
+    for (; e + 1 < m; e += 2) {
+        const double m0 = S[oM + e], m1 = S[oM + e + 1];
+        const double* d0 = D + e * n;
+        const double* d1 = d0 + n;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
             int col = lane + 32 * s;
-            if (col < n) acc[s] = fma(drow[col], me, acc[s]);
+            if (col < n) {
+                a0[s] = fma(__ldg(d0 + col), m0, a0[s]);
+                a1[s] = fma(__ldg(d1 + col), m1, a1[s]);
+            }
+        }
+    }
+    if (e < m) {
+        const double m0 = S[oM + e];
+        const double* d0 = D + e * n;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            int col = lane + 32 * s;
+            if (col < n) a0[s] = fma(__ldg(d0 + col), m0, a0[s]);
         }
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         int col = lane + 32 * s;
-        if (col < n) W.cc[col] = acc[s];
+        if (col < n) S[W.cc + col] = a0[s] + a1[s];
     }
     __syncwarp();
 }
 
 // fit = D x for the current positive set (lane-slot u owns echo e = lane + 32 u) and SSE = sum (fit - M)^2.
-// Dt is [n][m] row-major (the transposed dictionary).
+// Dt is [n][m] row-major (the transposed dictionary) in global memory.
 template <int NS, int ME>
-__device__ __forceinline__ double fit_and_sse(const NnlsWork<NS>& W, const double* __restrict__ Dt, const double* ms,
-                                              int m, int p, int lane, double (&fit)[ME]) {
+__device__ __forceinline__ double fit_and_sse(const Slots<NS>& W, const double* __restrict__ Dt, int oM, int m, int p,
+                                              int lane, double (&fit)[ME]) {
+    double f1[ME];
 #pragma unroll
-    for (int u = 0; u < ME; ++u) fit[u] = 0.0;
-    for (int k = 0; k < p; ++k) {
-        const double* drow = Dt + W.idx[k] * m;
-        double xk = W.xs[k];
+    for (int u = 0; u < ME; ++u) fit[u] = f1[u] = 0.0;
+    int k = 0;
+    for (; k + 1 < p; k += 2) {
+        const double* d0 = Dt + SI(W.ix, k) * m;
+        const double* d1 = Dt + SI(W.ix, k + 1) * m;
+        const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
 #pragma unroll
         for (int u = 0; u < ME; ++u) {
             int e = lane + 32 * u;
-            if (e < m) fit[u] = fma(drow[e], xk, fit[u]);
+            if (e < m) {
+                fit[u] = fma(__ldg(d0 + e), x0, fit[u]);
+                f1[u] = fma(__ldg(d1 + e), x1, f1[u]);
+            }
+        }
+    }
+    if (k < p) {
+        const double* d0 = Dt + SI(W.ix, k) * m;
+        const double x0 = S[W.xs + k];
+#pragma unroll
+        for (int u = 0; u < ME; ++u) {
+            int e = lane + 32 * u;
+            if (e < m) fit[u] = fma(__ldg(d0 + e), x0, fit[u]);
         }
     }
     double s = 0.0;
 #pragma unroll
     for (int u = 0; u < ME; ++u) {
         int e = lane + 32 * u;
+        fit[u] += f1[u];
         if (e < m) {
-            double d = fit[u] - ms[e];
+            double d = fit[u] - S[oM + e];
             s = fma(d, d, s);
         }
     }
     return warp_sum(s);
 }
 
-// sum_r ((L x)_r)^2 with L in 5-band row form lb[d*n + r] = L[r][r+d-2]; x in column space (W.xc).
+// sum_r ((L x)_r)^2 with L in 5-band row form S[oLb + d*n + r] = L[r][r+d-2]; x in column space (S[W.xc..]).
 template <int NS>
-__device__ __forceinline__ double reg_norm2(const NnlsWork<NS>& W, const double* __restrict__ lb, int n, int lane) {
+__device__ __forceinline__ double reg_norm2(const Slots<NS>& W, int oLb, int n, int lane) {
     double s = 0.0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
@@ -143,12 +189,36 @@ __device__ __forceinline__ double reg_norm2(const NnlsWork<NS>& W, const double*
 #pragma unroll
             for (int d = 0; d < 5; ++d) {
                 int c2 = r + d - 2;
-                if (c2 >= 0 && c2 < n) acc = fma(lb[d * n + r], W.xc[c2], acc);
+                if (c2 >= 0 && c2 < n) acc = fma(S[oLb + d * n + r], S[W.xc + c2], acc);
             }
             s = fma(acc, acc, s);
         }
     }
     return warp_sum(s);
+}
+
+// Load the raw signal of voxel v into S[oM..]; returns 0 if it is to be fitted, else the status bits
+// (fa_estimation.py:100 / motor...:124: mask > 0 and sum(M) > 0; NaN/Inf: algorithms.py:56 raises).
+template <int ME>
+__device__ __forceinline__ unsigned load_signal(const double* __restrict__ sig, long long v, int m, int oM, int lane) {
+    double s = 0.0;
+    bool bad = false;
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        int e = lane + 32 * u;
+        if (e < m) {
+            double xv = sig[v * m + e];
+            S[oM + e] = xv;
+            s += xv;
+            if (!isfinite(xv)) bad = true;
+        }
+    }
+    s = warp_sum(s);
+    bad = __any_sync(FULL_MASK, bad);
+    __syncwarp();
+    if (bad) return 2u | 1u;       // MET2_ST_NONFINITE | MET2_ST_SKIPPED
+    if (!(s > 0.0)) return 1u;     // MET2_ST_SKIPPED
+    return 0u;
 }
 
 }  // namespace met2

@@ -34,45 +34,20 @@ struct FaArgs {
 
 constexpr int FA_WARPS = 8;
 
+// per-warp shared memory in doubles: NNLS slots + signal ms[64]
 template <int NS>
-__device__ __forceinline__ size_t fa_warp_bytes(int pmax) {
-    return align_up256(NnlsWork<NS>::bytes(pmax) + sizeof(double) * 64);
-}
-
-// Load the raw signal of voxel v into ms; returns 0 if it is to be fitted, else the status bits.
-template <int ME>
-__device__ __forceinline__ unsigned load_signal(const double* __restrict__ sig, long long v, int m, double* ms, int lane,
-                                                bool need_m0) {
-    double s = 0.0;
-    bool bad = false;
-#pragma unroll
-    for (int u = 0; u < ME; ++u) {
-        int e = lane + 32 * u;
-        if (e < m) {
-            double x = sig[v * m + e];
-            ms[e] = x;
-            s += x;
-            if (!isfinite(x)) bad = true;
-        }
-    }
-    s = warp_sum(s);
-    bad = __any_sync(FULL_MASK, bad);
-    __syncwarp();
-    if (bad) return MET2_ST_NONFINITE | MET2_ST_SKIPPED;
-    if (!(s > 0.0)) return MET2_ST_SKIPPED;
-    if (need_m0 && !(ms[0] > 0.0)) return MET2_ST_SKIPPED;
-    return 0u;
+__host__ __device__ __forceinline__ int fa_warp_doubles(int pmax) {
+    return (Slots<NS>::doubles(pmax) + 64 + 31) & ~31;
 }
 
 template <int NS, int ME>
 __global__ void __launch_bounds__(FA_WARPS * 32) fa_search_kernel(FaArgs A) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
-    NnlsWork<NS> W;
-    unsigned char* base = smem + (size_t)warp * fa_warp_bytes<NS>(A.pmax);
-    W.carve(base, A.pmax);
-    double* ms = reinterpret_cast<double*>(base + NnlsWork<NS>::bytes(A.pmax));
+    Slots<NS> W;
+    const int wbase = warp * fa_warp_doubles<NS>(A.pmax);
+    W.carve(wbase, A.pmax);
+    const int oM = wbase + Slots<NS>::doubles(A.pmax);
     const long long chunk = (A.V + gridDim.x - 1) / gridDim.x;
     const long long v0 = (long long)blockIdx.x * chunk;
     const long long v1 = (v0 + chunk < A.V) ? v0 + chunk : A.V;
@@ -82,13 +57,13 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_search_kernel(FaArgs A) {
         const double* Dt = A.dicT_s + (size_t)a * n * m;
         const double* G = A.G_s + (size_t)a * n * n;
         for (long long v = v0 + warp; v < v1; v += FA_WARPS) {
-            unsigned st = load_signal<ME>(A.sig, v, m, ms, lane, false);
+            unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             if (st) continue;
-            compute_c<NS>(W, D, ms, m, n, lane);
+            compute_c<NS>(W, D, oM, m, n, lane);
             int nst = 0;
-            int p = nnls_gram<NS, false>(W, G, nullptr, 0.0, n, m, lane, nst);
+            int p = nnls_gram<NS, false>(W, 0, G, 0, false, 0.0, n, m, lane, nst);
             double fit[ME];
-            double sse = fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
+            double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
             double rnorm = sqrt(sse);
             if (lane == 0) {
                 if (brute) {
@@ -158,24 +133,25 @@ __global__ void spline_weights_kernel(const double* __restrict__ knots, int K, d
         for (int j = 0; j < K; ++j) wsp[i * K + j] = Aug[i][K + j];
 }
 
-__device__ __forceinline__ double spline_eval(const double* xk, const double* yk, const double* mk, int K, double x) {
+// knots at S[oX..], values at S[oY..], second derivatives at S[oM2..]
+__device__ __forceinline__ double spline_eval(int oX, int oY, int oM2, int K, double x) {
     int i = 0;
-    while (i + 2 < K && x >= xk[i + 1]) ++i;
-    double h = xk[i + 1] - xk[i];
-    double a = (xk[i + 1] - x) / h;
-    double b = (x - xk[i]) / h;
-    return a * yk[i] + b * yk[i + 1] + ((a * a * a - a) * mk[i] + (b * b * b - b) * mk[i + 1]) * (h * h) / 6.0;
+    while (i + 2 < K && x >= S[oX + i + 1]) ++i;
+    double h = S[oX + i + 1] - S[oX + i];
+    double a = (S[oX + i + 1] - x) / h;
+    double b = (x - S[oX + i]) / h;
+    return a * S[oY + i] + b * S[oY + i + 1] +
+           ((a * a * a - a) * S[oM2 + i] + (b * b * b - b) * S[oM2 + i + 1]) * (h * h) / 6.0;
 }
 
 template <int NS, int ME>
 __global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
-    extern __shared__ __align__(16) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE, nA = A.cfg.nA;
-    NnlsWork<NS> W;
-    unsigned char* base = smem + (size_t)warp * fa_warp_bytes<NS>(A.pmax);
-    W.carve(base, A.pmax);
-    double* ms = reinterpret_cast<double*>(base + NnlsWork<NS>::bytes(A.pmax));
+    Slots<NS> W;
+    const int wbase = warp * fa_warp_doubles<NS>(A.pmax);
+    W.carve(wbase, A.pmax);
+    const int oM = wbase + Slots<NS>::doubles(A.pmax);
     const bool brute = (A.cfg.method == MET2_FA_BRUTE_FORCE);
     const int K = A.cfg.nKnots;
     double fs[NS];
@@ -184,7 +160,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
     const long long gw = (long long)blockIdx.x * FA_WARPS + warp;
     const long long nw = (long long)gridDim.x * FA_WARPS;
     for (long long v = gw; v < A.V; v += nw) {
-        unsigned st = load_signal<ME>(A.sig, v, m, ms, lane, false);
+        unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
         if (st) {
             if (lane == 0) {
                 A.fa_index[v] = 0;
@@ -200,23 +176,21 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
         } else {
             // knot values and second derivatives into shared scratch: gs = y, rs = Msec, xs = knots
             if (lane < K) {
-                W.gs[lane] = A.resid[v * K + lane];
-                W.xs[lane] = A.knots[lane];
+                S[W.gs + lane] = A.resid[v * K + lane];
+                S[W.xs + lane] = A.knots[lane];
             }
             __syncwarp();
             if (lane < K) {
                 double acc = 0.0;
-                for (int j = 0; j < K; ++j) acc += A.wsp[lane * K + j] * W.gs[j];
-                W.rs[lane] = acc;
+                for (int j = 0; j < K; ++j) acc += A.wsp[lane * K + j] * S[W.gs + j];
+                S[W.rs + lane] = acc;
             }
             __syncwarp();
-            double fval;
-            int nfev;
-            const double* xk = W.xs;
-            const double* yk = W.gs;
-            const double* mk = W.rs;
-            double xmin = brent_bounded([&](double x) { return spline_eval(xk, yk, mk, K, x); }, A.cfg.brent_lo,
-                                        A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.brent_maxfun, fval, nfev);
+            Brent B;
+            double xq = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.brent_maxfun);
+            while (B.feed(spline_eval(W.xs, W.gs, W.rs, K, xq), xq)) {
+            }
+            const double xmin = B.xf;
             // indexFA = argmin |alpha_values - res.x| (first minimum; fa_estimation.py:57)
             double bd = 1.0e300;
             int bi = -1;
@@ -236,24 +210,16 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
         if (A.cfg.final_solve) {
             const double* D = A.dic + (size_t)index * m * n;
             const double* G = A.G + (size_t)index * n * n;
-            compute_c<NS>(W, D, ms, m, n, lane);
+            compute_c<NS>(W, D, oM, m, n, lane);
             int nst = 0;
-            int p = nnls_gram<NS, false>(W, G, nullptr, 0.0, n, m, lane, nst);
+            (void)nnls_gram<NS, false>(W, 0, G, 0, false, 0.0, n, m, lane, nst);
             if (nst && lane == 0) A.status[v] |= MET2_ST_ITMAX;
-            // scatter to column space, km = sum(f)
-#pragma unroll
-            for (int s = 0; s < NS; ++s) W.xc[lane + 32 * s] = 0.0;
-            __syncwarp();
-#pragma unroll
-            for (int t = 0; t < NS; ++t) {
-                int i = lane + 32 * t;
-                if (i < p) W.xc[W.idx[i]] = W.xs[i];
-            }
-            __syncwarp();
+            // nnls_gram leaves the solution in column space in S[W.xc..]; km = sum(f)
             double part = 0.0;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                double xv = W.xc[lane + 32 * s];
+                int col = lane + 32 * s;
+                double xv = (col < n) ? S[W.xc + col] : 0.0;
                 fs[s] += xv;
                 part += xv;
             }
@@ -294,8 +260,7 @@ template <int NS>
 static FaGeom fa_geometry(const met2_fa_cfg* cfg) {
     FaGeom g;
     g.pmax = cfg->nT2 < cfg->nTE ? cfg->nT2 : cfg->nTE;
-    size_t per_warp = align_up256(NnlsWork<NS>::bytes(g.pmax) + sizeof(double) * 64);
-    g.smem = per_warp * FA_WARPS;
+    g.smem = sizeof(double) * (size_t)fa_warp_doubles<NS>(g.pmax) * FA_WARPS;
     int per_sm = (int)((size_t)(200 * 1024) / (g.smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;

@@ -12,16 +12,22 @@
 //   remove position k: Givens rotations on column pairs of T that empty row k (parameters from a prefix sum of squares)
 //   solve            : z = T y   with y = T^T c_P
 // Every step is a (triangular) matrix-vector product spread over the 32 lanes; no serial substitution chains.
-// Measured against SciPy on the design-prototype (tools/proto_gram_nnls2.py): identical supports, <= 1e-9 relative.
+// Measured against SciPy on the design prototype (tools/proto_gram_nnls2.py): identical supports, <= 1e-9 relative.
+//
+// Memory: all per-warp state lives in the kernel's dynamic shared memory and is addressed as S[offset] (32-bit
+// shared-window addressing, LDS/STS); round-1 profiling of a pointer-based version showed generic LD.E + R2UR and
+// local-memory reloads dominating the issue slots (profiles/r01_t2_fit_v1_ncu_summary.txt).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace met2 {
 
+extern __shared__ __align__(16) double S[];   // the dynamic shared memory of every met2 kernel
+
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
-__device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__host__ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
 __host__ __device__ __forceinline__ size_t align_up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -43,16 +49,14 @@ __device__ __forceinline__ void warp_sum2(double& a, double& b) {
 
 // Index of the largest strictly positive value over the warp (lowest index on ties); -1 if no lane has v > 0.
 // Positive doubles order like their bit patterns, so two 32-bit REDUX max passes find the maximum.
-__device__ __forceinline__ int warp_argmax_pos(double v, int index, double& vmax) {
+__device__ __forceinline__ int warp_argmax_pos(double v, int index) {
     unsigned long long key = (v > 0.0) ? (unsigned long long)__double_as_longlong(v) : 0ull;
     unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
     unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
     unsigned mlo = __reduce_max_sync(FULL_MASK, (hi == mhi) ? lo : 0u);
     if ((mhi | mlo) == 0u) return -1;
     bool win = (key != 0ull) && (hi == mhi) && (lo == mlo);
-    unsigned best = __reduce_min_sync(FULL_MASK, win ? (unsigned)index : 0xffffffffu);
-    vmax = __longlong_as_double((long long)(((unsigned long long)mhi << 32) | mlo));
-    return (int)best;
+    return (int)__reduce_min_sync(FULL_MASK, win ? (unsigned)index : 0xffffffffu);
 }
 
 // Index of the smallest value among lanes with index >= 0 and v >= 0 (lowest index on ties); -1 if none.
@@ -69,66 +73,110 @@ __device__ __forceinline__ int warp_argmin_nonneg(double v, int index, double& v
     return (int)best;
 }
 
-// Per-warp shared-memory workspace.  NS = slots per lane; all vectors have 32*NS entries.
+// Per-warp workspace as offsets (in doubles) into S.  NS = slots per lane; vectors have LEN = 32*NS entries.
+//   T  : packed upper triangular, column-major: T(k, i) at S[T + tri(i) + k], k <= i < pmax
+//   gs : position-space scratch (gathered Gram column / c_P / rotation cosines)
+//   rs : position-space scratch (r, y / rotation sines)
+//   xs : current feasible x in position space
+//   cc : c = A^T b in column space
+//   xc : x in column space (zeros outside P)
+//   ix : position -> column (ints, stored in the space of LEN/2 doubles)
 template <int NS>
-struct NnlsWork {
-    double* T;    // packed upper triangular, column-major: T(k, i) at T[tri(i) + k], k <= i < pmax
-    double* gs;   // position-space scratch (gathered Gram column / c_P / rotation cosines)
-    double* rs;   // position-space scratch (r, y / rotation sines)
-    double* xs;   // current feasible x in position space
-    double* cc;   // c = A^T b in column space
-    double* xc;   // x in column space (zeros outside P); kept current only when the Tikhonov term is present
-    int* idx;     // position -> column
+struct Slots {
+    int T, gs, rs, xs, cc, xc, ix;
     static constexpr int LEN = 32 * NS;
-    __host__ __device__ static size_t bytes(int pmax) {
-        return sizeof(double) * (size_t)((pmax * (pmax + 1)) / 2 + 5 * LEN) + sizeof(int) * (size_t)LEN;
-    }
-    __device__ void carve(unsigned char* base, int pmax) {
-        T = reinterpret_cast<double*>(base);
-        gs = T + (pmax * (pmax + 1)) / 2;
+    __host__ __device__ static int doubles(int pmax) { return tri(pmax) + 5 * LEN + LEN / 2; }
+    __device__ __forceinline__ void carve(int base, int pmax) {
+        T = base;
+        gs = T + tri(pmax);
         rs = gs + LEN;
         xs = rs + LEN;
         cc = xs + LEN;
         xc = cc + LEN;
-        idx = reinterpret_cast<int*>(xc + LEN);
+        ix = xc + LEN;
     }
 };
 
-// out[t] (position i = lane + 32 t) = sum_{k <= i} T(k, i) * v[k]   — column dot products, T^T v
+__device__ __forceinline__ int& SI(int off, int k) { return reinterpret_cast<int*>(S + off)[k]; }
+
+// out[t] (position i = lane + 32 t) = sum_{k <= i, k < p} T(k, i) * v[k]   — column dot products, T^T v.
+// Segment `seg` of k (32 wide) only touches slots t >= seg; two accumulators per slot for ILP.
 template <int NS>
-__device__ __forceinline__ void tmul_transposed(const double* __restrict__ T, const double* __restrict__ v, int p,
-                                                int lane, double (&out)[NS]) {
+__device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane, double (&out)[NS]) {
+    double a0[NS], a1[NS];
     int base[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        out[t] = 0.0;
-        base[t] = tri(lane + 32 * t);
+        a0[t] = a1[t] = 0.0;
+        base[t] = oT + tri(lane + 32 * t);
     }
-    for (int k = 0; k < p; ++k) {
-        double vk = v[k];
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            int i = lane + 32 * t;
-            if (i < p && k <= i) out[t] = fma(T[base[t] + k], vk, out[t]);
+    for (int seg = 0; seg < NS; ++seg) {
+        const int k0 = 32 * seg;
+        if (k0 < p) {
+            const int k1 = (p < k0 + 32) ? p : k0 + 32;
+            int k = k0;
+            for (; k + 1 < k1; k += 2) {
+                const double v0 = S[oV + k], v1 = S[oV + k + 1];
+#pragma unroll
+                for (int t = seg; t < NS; ++t) {
+                    const int i = lane + 32 * t;
+                    if (i < p) {
+                        if (k <= i) a0[t] = fma(S[base[t] + k], v0, a0[t]);
+                        if (k + 1 <= i) a1[t] = fma(S[base[t] + k + 1], v1, a1[t]);
+                    }
+                }
+            }
+            if (k < k1) {
+                const double v0 = S[oV + k];
+#pragma unroll
+                for (int t = seg; t < NS; ++t) {
+                    const int i = lane + 32 * t;
+                    if (i < p && k <= i) a0[t] = fma(S[base[t] + k], v0, a0[t]);
+                }
+            }
         }
     }
+#pragma unroll
+    for (int t = 0; t < NS; ++t) out[t] = a0[t] + a1[t];
 }
 
-// out[t] (position k = lane + 32 t) = sum_{i >= k, i < p} T(k, i) * v[i]   — row dot products, T v
+// out[t] (position k = lane + 32 t) = sum_{i >= k, i < p} T(k, i) * v[i]   — row dot products, T v.
+// Segment `seg` of i only touches slots t <= seg.
 template <int NS>
-__device__ __forceinline__ void tmul(const double* __restrict__ T, const double* __restrict__ v, int p, int lane,
-                                     double (&out)[NS]) {
+__device__ __forceinline__ void tmul(int oT, int oV, int p, int lane, double (&out)[NS]) {
+    double a0[NS], a1[NS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) out[t] = 0.0;
-    for (int i = 0; i < p; ++i) {
-        double vi = v[i];
-        int ti = tri(i);
+    for (int t = 0; t < NS; ++t) a0[t] = a1[t] = 0.0;
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            int k = lane + 32 * t;
-            if (k <= i) out[t] = fma(T[ti + k], vi, out[t]);
+    for (int seg = 0; seg < NS; ++seg) {
+        const int i0 = 32 * seg;
+        if (i0 < p) {
+            const int i1 = (p < i0 + 32) ? p : i0 + 32;
+            int i = i0;
+            for (; i + 1 < i1; i += 2) {
+                const double v0 = S[oV + i], v1 = S[oV + i + 1];
+                const int t0 = oT + tri(i), t1 = oT + tri(i + 1);
+#pragma unroll
+                for (int t = 0; t <= seg; ++t) {
+                    const int k = lane + 32 * t;
+                    if (k <= i) a0[t] = fma(S[t0 + k], v0, a0[t]);
+                    if (k <= i + 1) a1[t] = fma(S[t1 + k], v1, a1[t]);
+                }
+            }
+            if (i < i1) {
+                const double v0 = S[oV + i];
+                const int t0 = oT + tri(i);
+#pragma unroll
+                for (int t = 0; t <= seg; ++t) {
+                    const int k = lane + 32 * t;
+                    if (k <= i) a0[t] = fma(S[t0 + k], v0, a0[t]);
+                }
+            }
         }
     }
+#pragma unroll
+    for (int t = 0; t < NS; ++t) out[t] = a0[t] + a1[t];
 }
 
 // Inclusive prefix sum over positions (lane + 32 t ordering).
@@ -151,25 +199,24 @@ __device__ __forceinline__ void warp_scan_positions(double (&v)[NS], int lane) {
 
 // Delete position k of the positive set (p -> p-1): re-triangularise T, shift idx and x.
 template <int NS>
-__device__ __forceinline__ void remove_position(const NnlsWork<NS>& W, int k, int& p, int lane, double (&x)[NS]) {
-    double* T = W.T;
+__device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& p, int lane, double (&x)[NS]) {
+    const int oT = W.T;
     // rotation parameters from the prefix sums of squares of row k
-    double tau[NS], S[NS];
+    double tau[NS], Sq[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         int q = lane + 32 * t;
-        tau[t] = (q >= k && q < p) ? T[tri(q) + k] : 0.0;
-        S[t] = tau[t] * tau[t];
+        tau[t] = (q >= k && q < p) ? S[oT + tri(q) + k] : 0.0;
+        Sq[t] = tau[t] * tau[t];
     }
-    warp_scan_positions<NS>(S, lane);
+    warp_scan_positions<NS>(Sq, lane);
     // nu_q = sqrt(S_q); step q (k <= q <= p-2) needs c_q = tau_{q+1}/nu_{q+1}, s_q = nu_q/nu_{q+1}
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         int q = lane + 32 * t;
         if (q >= k && q < p) {
-            double nu = sqrt(S[t]);
-            W.rs[q] = nu;          // nu_q
-            W.gs[q] = tau[t];      // tau_q
+            S[W.rs + q] = sqrt(Sq[t]);   // nu_q
+            S[W.gs + q] = tau[t];        // tau_q
         }
     }
     __syncwarp();
@@ -180,10 +227,9 @@ __device__ __forceinline__ void remove_position(const NnlsWork<NS>& W, int k, in
         cq[t] = 0.0;
         sq[t] = 1.0;
         if (q >= k && q + 1 < p) {
-            double nu1 = W.rs[q + 1];
-            double inv = 1.0 / nu1;
-            cq[t] = W.gs[q + 1] * inv;
-            sq[t] = W.rs[q] * inv;
+            double inv = 1.0 / S[W.rs + q + 1];
+            cq[t] = S[W.gs + q + 1] * inv;
+            sq[t] = S[W.rs + q] * inv;
         }
     }
     __syncwarp();
@@ -191,39 +237,34 @@ __device__ __forceinline__ void remove_position(const NnlsWork<NS>& W, int k, in
     for (int t = 0; t < NS; ++t) {
         int q = lane + 32 * t;
         if (q >= k && q + 1 < p) {
-            W.gs[q] = cq[t];
-            W.rs[q] = sq[t];
+            S[W.gs + q] = cq[t];
+            S[W.rs + q] = sq[t];
         }
-    }
-    // shift x through xs (xs is rewritten with the shifted vector below)
-#pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        int i = lane + 32 * t;
-        if (i < p) W.xs[i] = x[t];
+        if (q < p) S[W.xs + q] = x[t];   // x is shifted through xs below
     }
     __syncwarp();
     int idx_next[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         int i = lane + 32 * t;
-        idx_next[t] = (i >= k && i + 1 < p) ? W.idx[i + 1] : -1;
-        if (i >= k) x[t] = (i + 1 < p) ? W.xs[i + 1] : 0.0;
+        idx_next[t] = (i >= k && i + 1 < p) ? SI(W.ix, i + 1) : -1;
+        if (i >= k) x[t] = (i + 1 < p) ? S[W.xs + i + 1] : 0.0;
     }
     // row sweep: lane-slot owns old row rr (rr != k); carry starts as T(rr, k)
     double carry[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         int rr = lane + 32 * t;
-        carry[t] = (rr < k) ? T[tri(k) + rr] : 0.0;
+        carry[t] = (rr < k) ? S[oT + tri(k) + rr] : 0.0;
     }
     for (int q = k; q + 1 < p; ++q) {
-        double c = W.gs[q], s = W.rs[q];
-        int tq1 = tri(q + 1), tq = tri(q);
+        const double c = S[W.gs + q], s = S[W.rs + q];
+        const int tq1 = oT + tri(q + 1), tq = oT + tri(q);
         double nv[NS];
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             int rr = lane + 32 * t;
-            double b = (rr <= q + 1 && rr != k) ? T[tq1 + rr] : 0.0;
+            double b = (rr <= q + 1 && rr != k) ? S[tq1 + rr] : 0.0;
             nv[t] = s * b - c * carry[t];
             carry[t] = fma(s, carry[t], c * b);
         }
@@ -231,42 +272,40 @@ __device__ __forceinline__ void remove_position(const NnlsWork<NS>& W, int k, in
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             int rr = lane + 32 * t;
-            if (rr != k && rr <= q + 1) {
-                int rn = rr - (rr > k ? 1 : 0);
-                T[tq + rn] = nv[t];
-            }
+            if (rr != k && rr <= q + 1) S[tq + rr - (rr > k ? 1 : 0)] = nv[t];
         }
     }
     __syncwarp();
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         int i = lane + 32 * t;
-        if (idx_next[t] >= 0) W.idx[i] = idx_next[t];
+        if (idx_next[t] >= 0) SI(W.ix, i) = idx_next[t];
     }
     --p;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         int i = lane + 32 * t;
-        if (i < p) W.xs[i] = x[t];
+        if (i < p) S[W.xs + i] = x[t];
     }
     __syncwarp();
 }
 
-// Gram-domain Lawson-Hanson.  On entry W.cc[0..n) holds c = A^T b (visible to the whole warp).
-// G: n x n row-major Gram matrix of the unregularised dictionary (shared or global memory).
-// REG: add lam * K, K given in 5-band form kb[d*n + c] = K[c+d-2][c].
-// On exit W.idx[0..p) / W.xs[0..p) hold the positive set and its coefficients; returns p.  status gets bit 0 on itmax.
-template <int NS, bool REG>
-__device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __restrict__ G,
-                                      const double* __restrict__ kb, double lam, int n, int mrows, int lane,
-                                      int& status) {
+// Gram-domain Lawson-Hanson.  On entry S[W.cc + 0..n) holds c = A^T b (visible to the whole warp).
+// G: n x n row-major Gram matrix of the unregularised dictionary — in shared memory at offset oG (GSH) or in global
+// memory at Gg.  reg: add lam * K, K given in 5-band form at S[oKb + d*n + c] = K[c+d-2][c].
+// On exit S[W.ix..] / S[W.xs..] hold the positive set and its coefficients, S[W.xc..] the solution in column space;
+// returns p.  status gets bit 0 on itmax.
+template <int NS, bool GSH>
+__device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int oKb, bool reg,
+                                         double lam, int n, int mrows, int lane, int& status) {
     const int itmax = 3 * n;
+    auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * n + c] : __ldg(Gg + r * n + c); };
     double creg[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         int col = lane + 32 * s;
-        creg[s] = (col < n) ? W.cc[col] : 0.0;
-        if (REG && col < n) W.xc[col] = 0.0;
+        creg[s] = (col < n) ? S[W.cc + col] : 0.0;
+        if (col < n) S[W.xc + col] = 0.0;
     }
     unsigned inP = 0u;
     double x[NS], y[NS], z[NS];
@@ -278,19 +317,38 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
         if (p >= n || p >= mrows) break;
         // ---- dual vector w = c - (G + lam K) x on the zero set
         double w[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) w[s] = creg[s];
         if (p > 0) {
-            for (int k = 0; k < p; ++k) {
-                const double* grow = G + W.idx[k] * n;
-                double xk = W.xs[k];
+            double w1[NS];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                w[s] = creg[s];
+                w1[s] = 0.0;
+            }
+            int k = 0;
+            for (; k + 1 < p; k += 2) {
+                const int r0 = SI(W.ix, k) * n, r1 = SI(W.ix, k + 1) * n;
+                const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     int col = lane + 32 * s;
-                    if (col < n) w[s] = fma(-xk, grow[col], w[s]);
+                    if (col < n) {
+                        w[s] = fma(-x0, GSH ? S[oG + r0 + col] : __ldg(Gg + r0 + col), w[s]);
+                        w1[s] = fma(-x1, GSH ? S[oG + r1 + col] : __ldg(Gg + r1 + col), w1[s]);
+                    }
                 }
             }
-            if (REG) {
+            if (k < p) {
+                const int r0 = SI(W.ix, k) * n;
+                const double x0 = S[W.xs + k];
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    int col = lane + 32 * s;
+                    if (col < n) w[s] = fma(-x0, GSH ? S[oG + r0 + col] : __ldg(Gg + r0 + col), w[s]);
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) w[s] += w1[s];
+            if (reg) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
                     int col = lane + 32 * s;
@@ -299,12 +357,15 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
 #pragma unroll
                         for (int d = 0; d < 5; ++d) {
                             int c2 = col + d - 2;
-                            if (c2 >= 0 && c2 < n) acc = fma(kb[d * n + col], W.xc[c2], acc);
+                            if (c2 >= 0 && c2 < n) acc = fma(S[oKb + d * n + col], S[W.xc + c2], acc);
                         }
                         w[s] = fma(-lam, acc, w[s]);
                     }
                 }
             }
+        } else {
+#pragma unroll
+            for (int s = 0; s < NS; ++s) w[s] = creg[s];
         }
         // ---- pick the entering column
         unsigned rejected = 0u;
@@ -320,23 +381,21 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
                     bj = col;
                 }
             }
-            double wmax;
-            int j = warp_argmax_pos(bv, bj, wmax);
+            const int j = warp_argmax_pos(bv, bj);
             if (j < 0) break;
-            double gjj = G[j * n + j];
-            if (REG) gjj = fma(lam, kb[2 * n + j], gjj);
-            const double* gcol = G + j * n;   // G is symmetric: column j == row j
+            double gjj = Gat(j, j);
+            if (reg) gjj = fma(lam, S[oKb + 2 * n + j], gjj);
 #pragma unroll
             for (int t = 0; t < NS; ++t) {
                 int i = lane + 32 * t;
                 if (i < p) {
-                    int r = W.idx[i];
-                    double gv = gcol[r];
-                    if (REG) {
+                    int r = SI(W.ix, i);
+                    double gv = Gat(j, r);   // G is symmetric: column j == row j
+                    if (reg) {
                         int d = r - j + 2;
-                        if (d >= 0 && d <= 4) gv = fma(lam, kb[d * n + j], gv);
+                        if (d >= 0 && d <= 4) gv = fma(lam, S[oKb + d * n + j], gv);
                     }
-                    W.gs[i] = gv;
+                    S[W.gs + i] = gv;
                 }
             }
             __syncwarp();
@@ -349,43 +408,39 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
                 if (i < p) {
                     s1 = fma(r[t], r[t], s1);
                     s2 = fma(r[t], y[t], s2);
+                    S[W.rs + i] = r[t];
                 }
             }
             warp_sum2(s1, s2);
-            double rho2 = gjj - s1;
-            double cj = W.cc[j];
-            double rho = sqrt(rho2);
-            double rinv = 1.0 / rho;
-            double ynew = (cj - s2) * rinv;
-            // dependence test of nnls.f (unorm + |a_new|*0.01 > unorm) and its "ztest > 0" in Gram-domain form
-            bool ok = (rho2 > 0.0) && (sqrt(s1) + rho * 0.01 > sqrt(s1)) && (ynew > 0.0);
+            const double rho2 = gjj - s1;
+            const double cj = S[W.cc + j];
+            const double rinv = rsqrt(rho2);
+            const double ynew = (cj - s2) * rinv;
+            // nnls.f: reject if the column is numerically dependent on P (unorm + |a_new|*0.01 == unorm, i.e.
+            // rho < ~1e-14 unorm) or if its new coefficient ("ztest") is not positive
+            const bool ok = (rho2 > 0.0) && (rho2 > 1.2e-28 * s1) && (ynew > 0.0);
             if (!ok) {
                 if ((j & 31) == lane) rejected |= 1u << (j >> 5);
                 __syncwarp();
                 continue;
             }
-#pragma unroll
-            for (int t = 0; t < NS; ++t) {
-                int i = lane + 32 * t;
-                if (i < p) W.rs[i] = r[t];
-            }
             __syncwarp();
             double acc[NS];
             tmul<NS>(W.T, W.rs, p, lane, acc);
-            const int tp = tri(p);
+            const int tp = W.T + tri(p);
 #pragma unroll
             for (int t = 0; t < NS; ++t) {
                 int k = lane + 32 * t;
                 if (k < p) {
                     double tk = -acc[t] * rinv;
-                    W.T[tp + k] = tk;
+                    S[tp + k] = tk;
                     z[t] = fma(ynew, tk, z[t]);
                 } else if (k == p) {
-                    W.T[tp + p] = rinv;
+                    S[tp + p] = rinv;
                     z[t] = ynew * rinv;
                     y[t] = ynew;
-                    W.idx[p] = j;
-                    W.xs[p] = 0.0;   // x of the entering column is 0 until the solve is accepted
+                    SI(W.ix, p) = j;
+                    S[W.xs + p] = 0.0;   // x of the entering column is 0 until the solve is accepted
                 }
             }
             if ((j & 31) == lane) inP |= 1u << (j >> 5);
@@ -434,9 +489,9 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
             }
             int k = jb;
             while (true) {
-                int colk = W.idx[k];
+                int colk = SI(W.ix, k);
                 if ((colk & 31) == lane) inP &= ~(1u << (colk >> 5));
-                if (REG && lane == 0) W.xc[colk] = 0.0;
+                if (lane == 0) S[W.xc + colk] = 0.0;
                 __syncwarp();
                 remove_position<NS>(W, k, p, lane, x);
                 int q = 0x7fffffff;
@@ -453,14 +508,14 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
 #pragma unroll
             for (int t = 0; t < NS; ++t) {
                 int i = lane + 32 * t;
-                if (i < p) W.gs[i] = W.cc[W.idx[i]];
+                if (i < p) S[W.gs + i] = S[W.cc + SI(W.ix, i)];
             }
             __syncwarp();
             tmul_transposed<NS>(W.T, W.gs, p, lane, y);
 #pragma unroll
             for (int t = 0; t < NS; ++t) {
                 int i = lane + 32 * t;
-                if (i < p) W.rs[i] = y[t];
+                if (i < p) S[W.rs + i] = y[t];
                 else y[t] = 0.0;
             }
             __syncwarp();
@@ -473,20 +528,17 @@ __device__ __noinline__ int nnls_gram(const NnlsWork<NS>& W, const double* __res
             int i = lane + 32 * t;
             if (i < p) {
                 x[t] = z[t];
-                W.xs[i] = z[t];
-                if (REG) W.xc[W.idx[i]] = z[t];
+                S[W.xs + i] = z[t];
+                if (reg) S[W.xc + SI(W.ix, i)] = z[t];
             }
         }
         __syncwarp();
     }
-    // xs mirrors x on every path: after an accepted solve it was just written, after an itmax stop
-    // remove_position left the interpolated x there.
-    if (REG) {
+    // xs mirrors x on every path; make the column-space copy current for the caller
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            int i = lane + 32 * t;
-            if (i < p) W.xc[W.idx[i]] = x[t];
-        }
+    for (int t = 0; t < NS; ++t) {
+        int i = lane + 32 * t;
+        if (i < p) S[W.xc + SI(W.ix, i)] = x[t];
     }
     __syncwarp();
     return p;

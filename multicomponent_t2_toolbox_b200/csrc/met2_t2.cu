@@ -16,7 +16,7 @@
 
 namespace met2 {
 
-constexpr int T2_TILE = 64;
+constexpr int T2_TILE = 256;
 
 struct T2Args {
     const double* sig;
@@ -82,15 +82,15 @@ __global__ void t2_scatter_kernel(const int* __restrict__ fa_index, long long V,
 }
 
 // ---------------------------------------------------------------------------------------------- L-curve corner
-// Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves lx/ly of length nl in shared memory.
-__device__ __forceinline__ int select_corner_warp(double* lx, double* ly, int nl, int lane) {
+// Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves of length nl at S[oLx..], S[oLy..].
+__device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int lane) {
     // scale both curves to [-10, 10]: ((u-l)/(vmax-vmin)) * (a - (u*vmin - l*vmax)/(u-l))
     for (int c = 0; c < 2; ++c) {
-        double* a = c ? ly : lx;
+        const int oA = c ? oLy : oLx;
         double vmin = INFINITY, vmax = -INFINITY;
         bool has_nan = false;
         for (int i = lane; i < nl; i += 32) {
-            double v = a[i];
+            double v = S[oA + i];
             if (v != v) has_nan = true;
             vmin = fmin(vmin, v);
             vmax = fmax(vmax, v);
@@ -104,17 +104,17 @@ __device__ __forceinline__ int select_corner_warp(double* lx, double* ly, int nl
         double scale = 20.0 / (vmax - vmin);
         double shift = (10.0 * vmin - (-10.0) * vmax) / 20.0;
         __syncwarp();
-        for (int i = lane; i < nl; i += 32) a[i] = scale * (a[i] - shift);
+        for (int i = lane; i < nl; i += 32) S[oA + i] = scale * (S[oA + i] - shift);
         __syncwarp();
     }
     const double cte = 7.0 * 3.141592653589793 / 8.0;
-    const double cx = lx[nl - 1], cy = ly[nl - 1];
+    const double cx = S[oLx + nl - 1], cy = S[oLy + nl - 1];
     double best_ang = INFINITY;
     int best_ord = -1;
     for (int k = lane; k < nl - 2; k += 32) {
-        double bx = lx[k], by = ly[k];
+        double bx = S[oLx + k], by = S[oLy + k];
         for (int j = k + 1; j < nl - 1; ++j) {
-            double ax = lx[j], ay = ly[j];
+            double ax = S[oLx + j], ay = S[oLy + j];
             double dx1 = ax - bx, dy1 = ay - by;
             double ab = sqrt(dx1 * dx1 + dy1 * dy1);
             double dx2 = ax - cx, dy2 = ay - cy;
@@ -145,44 +145,44 @@ __device__ __forceinline__ int select_corner_warp(double* lx, double* ly, int nl
 }
 
 // ---------------------------------------------------------------------------------------------- fit kernel
-template <int NS>
-__host__ __device__ __forceinline__ size_t t2_warp_bytes(int pmax) {
-    // NnlsWork + signal ms[64] + L-curve curves 2 x 64
-    return align_up256(NnlsWork<NS>::bytes(pmax) + sizeof(double) * (64 + 128));
+// shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
+// then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64]
+__host__ __device__ __forceinline__ int t2_table_doubles(int n) {
+    return (n * n + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
 }
 
-__host__ __device__ __forceinline__ size_t t2_cta_table_bytes(int n) {
-    // G n*n, kband 10*n, logT2 n, lambdas 64, comp n bytes
-    return align_up256(sizeof(double) * (size_t)(n * n + 10 * n + n + MET2_MAX_LAMBDAS) + (size_t)n);
+template <int NS>
+__host__ __device__ __forceinline__ int t2_warp_doubles(int pmax) {
+    return (Slots<NS>::doubles(pmax) + 64 + 128 + 31) & ~31;
 }
+
+constexpr int T2_MAX_THREADS = 512;
 
 template <int NS, int ME>
-__global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
-    extern __shared__ __align__(16) unsigned char smem[];
+__global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
     __shared__ int s_tile, s_next;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
     const int method = A.cfg.method;
-    double* sG = reinterpret_cast<double*>(smem);
-    double* skb = sG + n * n;           // K band rows 0..4
-    double* slb = skb + 5 * n;          // L band rows 0..4
-    double* slogT2 = slb + 5 * n;
-    double* slam = slogT2 + n;
-    unsigned char* scomp = reinterpret_cast<unsigned char*>(slam + MET2_MAX_LAMBDAS);
-    unsigned char* wbase = smem + t2_cta_table_bytes(n) + (size_t)warp * t2_warp_bytes<NS>(A.pmax);
-    NnlsWork<NS> W;
+    const int oG = 0;
+    const int oKb = oG + n * n;          // K band rows 0..4
+    const int oLb = oKb + 5 * n;         // L band rows 0..4
+    const int oLogT2 = oLb + 5 * n;
+    const int oLam = oLogT2 + n;
+    unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLam + MET2_MAX_LAMBDAS);
+    const int wbase = t2_table_doubles(n) + warp * t2_warp_doubles<NS>(A.pmax);
+    Slots<NS> W;
     W.carve(wbase, A.pmax);
-    double* ms = reinterpret_cast<double*>(wbase + NnlsWork<NS>::bytes(A.pmax));
-    double* lcx = ms + 64;
-    double* lcy = lcx + 64;
+    const int oM = wbase + Slots<NS>::doubles(A.pmax);
+    const int oLx = oM + 64, oLy = oLx + 64;
 
-    for (int i = threadIdx.x; i < 10 * n; i += blockDim.x) skb[i] = A.kband ? A.kband[i] : 0.0;
+    for (int i = threadIdx.x; i < 10 * n; i += blockDim.x) S[oKb + i] = A.kband ? A.kband[i] : 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        slogT2[i] = A.logT2[i];
+        S[oLogT2 + i] = A.logT2[i];
         scomp[i] = A.comp[i];
     }
     for (int i = threadIdx.x; i < MET2_MAX_LAMBDAS; i += blockDim.x)
-        slam[i] = (A.lambdas && i < A.cfg.nLambda) ? A.lambdas[i] : 0.0;
+        S[oLam + i] = (A.lambdas && i < A.cfg.nLambda) ? A.lambdas[i] : 0.0;
     const int ntiles = A.counters[0];
 
     while (true) {
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
         const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
         {
             const double* Gg = A.G + (size_t)fa * n * n;
-            for (int i = threadIdx.x; i < n * n; i += blockDim.x) sG[i] = Gg[i];
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) S[oG + i] = __ldg(Gg + i);
         }
         __syncthreads();
         const double* D = A.dic + (size_t)fa * m * n;
@@ -210,27 +210,11 @@ __global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
             it = __shfl_sync(FULL_MASK, it, 0);
             if (it >= tcnt) break;
             const long long v = A.perm[tstart + it];
-            unsigned st = 0u;
             // ---- load, validity (motor...:124-131), normalise by km = M[0]
-            double s = 0.0;
-            bool bad = false;
-#pragma unroll
-            for (int u = 0; u < ME; ++u) {
-                int e = lane + 32 * u;
-                if (e < m) {
-                    double xv = A.sig[v * m + e];
-                    ms[e] = xv;
-                    s += xv;
-                    if (!isfinite(xv)) bad = true;
-                }
-            }
-            s = warp_sum(s);
-            bad = __any_sync(FULL_MASK, bad);
-            __syncwarp();
+            unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             const int fav = A.fa_index[v];
-            const double km = ms[0];
-            if (bad) st = MET2_ST_NONFINITE | MET2_ST_SKIPPED;
-            else if (!(s > 0.0) || !(km > 0.0) || fav < 0 || fav >= A.cfg.nA) st = MET2_ST_SKIPPED;
+            const double km = S[oM];
+            if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
             double regv = 0.0;
             int p = 0;
             double fit[ME];
@@ -241,67 +225,72 @@ __global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
 #pragma unroll
                 for (int u = 0; u < ME; ++u) {
                     int e = lane + 32 * u;
-                    if (e < m) ms[e] = ms[e] / km;
+                    if (e < m) S[oM + e] = S[oM + e] / km;
                 }
                 __syncwarp();
-                compute_c<NS>(W, D, ms, m, n, lane);
-                int nst = 0;
+                compute_c<NS>(W, D, oM, m, n, lane);
+                // ---- lambda-search driver: a small state machine around ONE inlined NNLS call site.
+                //   NNLS     : plain solve                                                    (algorithms.py:55)
+                //   T2SPARC  : one Tikhonov solve at lambda_fixed                             (algorithms.py:262)
+                //   X2       : plain solve -> SSE; Brent on |SSE(lam) - factor*SSE|/SSE; final (algorithms.py:211-233)
+                //   L_curve  : grid of nLambda solves -> curves -> corner; final               (algorithms.py:88-113)
+                enum { ST_PLAIN0 = 0, ST_SEARCH = 1, ST_FINAL = 2 };
+                int stage;
+                bool reg;
+                double lam = 0.0, SSE = 0.0;
+                int gi = 0;
+                Brent B;
                 if (method == MET2_REG_NNLS) {
-                    p = nnls_gram<NS, false>(W, sG, nullptr, 0.0, n, m, lane, nst);
-                    regv = 0.0;
+                    stage = ST_FINAL; reg = false;
                 } else if (method == MET2_REG_T2SPARC) {
-                    regv = A.cfg.lambda_fixed;
-                    p = nnls_gram<NS, true>(W, sG, skb, regv, n, m + n, lane, nst);
+                    stage = ST_FINAL; reg = true; lam = A.cfg.lambda_fixed;
                 } else if (method == MET2_REG_X2) {
-                    // algorithms.py:211-233
-                    p = nnls_gram<NS, false>(W, sG, nullptr, 0.0, n, m, lane, nst);
-                    const double SSE = fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
-                    if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
-                    const double factor = A.cfg.factor;
-                    double fval;
-                    int nfev;
-                    double reg_opt = brent_bounded(
-                        [&](double lamx) {
-                            int pp = nnls_gram<NS, true>(W, sG, skb, lamx, n, m + n, lane, nst);
-                            double sser = fit_and_sse<NS, ME>(W, Dt, ms, m, pp, lane, fit);
-                            return fabs(sser - factor * SSE) / SSE;
-                        },
-                        A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun, fval, nfev);
-                    p = nnls_gram<NS, true>(W, sG, skb, reg_opt, n, m + n, lane, nst);
-                    double sser = fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
-                    regv = sser / SSE;   // the orchestrator stores k_est, not lambda (motor...:141-143)
-                } else if (method == MET2_REG_LCURVE) {
-                    // algorithms.py:88-113 on the 50-point grid, then nnls_tik at the corner (motor...:145-146)
-                    const int nl = A.cfg.nLambda;
-                    for (int i = 0; i < nl; ++i) {
-                        int pp = nnls_gram<NS, true>(W, sG, skb, slam[i], n, m + n, lane, nst);
-                        double sse = fit_and_sse<NS, ME>(W, Dt, ms, m, pp, lane, fit);
-                        double nrm = reg_norm2<NS>(W, slb, n, lane);
+                    stage = ST_PLAIN0; reg = false;
+                } else {   // MET2_REG_LCURVE
+                    stage = ST_SEARCH; reg = true; lam = S[oLam];
+                }
+                int nst = 0;
+                while (true) {
+                    p = nnls_gram<NS, true>(W, oG, nullptr, oKb, reg, lam, n, reg ? m + n : m, lane, nst);
+                    const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
+                    if (stage == ST_FINAL) {
+                        if (method == MET2_REG_X2) regv = sse / SSE;   // k_est is what the orchestrator stores
+                        else regv = lam;                               // (motor...:141-143); NNLS -> 0
+                        break;
+                    }
+                    if (method == MET2_REG_X2) {
+                        if (stage == ST_PLAIN0) {
+                            SSE = sse;
+                            if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
+                            lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
+                            reg = true;
+                            stage = ST_SEARCH;
+                        } else {
+                            const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
+                            if (!B.feed(cost, lam)) {
+                                lam = B.xf;
+                                stage = ST_FINAL;
+                            }
+                        }
+                    } else {   // L-curve grid
+                        const double nrm = reg_norm2<NS>(W, oLb, n, lane);
                         if (lane == 0) {
-                            lcx[i] = log(sse + 1e-200);
-                            lcy[i] = log(nrm + 1e-200);
+                            S[oLx + gi] = log(sse + 1e-200);
+                            S[oLy + gi] = log(nrm + 1e-200);
                         }
                         __syncwarp();
+                        ++gi;
+                        if (gi < A.cfg.nLambda) {
+                            lam = S[oLam + gi];
+                        } else {
+                            lam = S[oLam + select_corner_warp(oLx, oLy, A.cfg.nLambda, lane)];
+                            stage = ST_FINAL;
+                        }
                     }
-                    int corner = select_corner_warp(lcx, lcy, nl, lane);
-                    regv = slam[corner];
-                    p = nnls_gram<NS, true>(W, sG, skb, regv, n, m + n, lane, nst);
                 }
                 if (nst) st |= MET2_ST_ITMAX;
-                (void)fit_and_sse<NS, ME>(W, Dt, ms, m, p, lane, fit);
             }
             // ---- outputs: fsol = x*km, Est_Signal = (D x)*km, reg, maps (motor...:153-155, 443-472)
-#pragma unroll
-            for (int sidx = 0; sidx < NS; ++sidx) W.xc[lane + 32 * sidx] = 0.0;
-            __syncwarp();
-            if (!(st & MET2_ST_SKIPPED)) {
-#pragma unroll
-                for (int t = 0; t < NS; ++t) {
-                    int i = lane + 32 * t;
-                    if (i < p) W.xc[W.idx[i]] = W.xs[i];
-                }
-            }
-            __syncwarp();
             const bool fitted = !(st & MET2_ST_SKIPPED);
             const double kmo = fitted ? km : 0.0;
             double xk[NS];
@@ -309,7 +298,7 @@ __global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
 #pragma unroll
             for (int sidx = 0; sidx < NS; ++sidx) {
                 int col = lane + 32 * sidx;
-                xk[sidx] = (col < n && fitted) ? W.xc[col] * kmo : 0.0;
+                xk[sidx] = (col < n && fitted) ? S[W.xc + col] * kmo : 0.0;
                 vt += xk[sidx];
                 if (col < n) A.fsol[v * n + col] = xk[sidx];
             }
@@ -328,11 +317,11 @@ __global__ void __launch_bounds__(512) t2_fit_kernel(T2Args A) {
                     unsigned char cm = scomp[col];
                     if (cm & 1) {
                         sm += xn;
-                        lm += xn * slogT2[col];
+                        lm += xn * S[oLogT2 + col];
                     }
                     if (cm & 2) {
                         stt += xn;
-                        lt += xn * slogT2[col];
+                        lt += xn * S[oLogT2 + col];
                     }
                     if (cm & 4) sc += xn;
                 }
@@ -369,11 +358,11 @@ static T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
     const int n = cfg->nT2, m = cfg->nTE;
     const bool plain = (cfg->method == MET2_REG_NNLS);
     g.pmax = plain ? (n < m ? n : m) : n;
-    size_t tables = t2_cta_table_bytes(n);
-    size_t per_warp = t2_warp_bytes<NS>(g.pmax);
-    size_t budget = 227 * 1024 - 2048;
+    size_t tables = sizeof(double) * (size_t)t2_table_doubles(n);
+    size_t per_warp = sizeof(double) * (size_t)t2_warp_doubles<NS>(g.pmax);
+    size_t budget = 227 * 1024 - 1024;
     int warps = (int)((budget - tables) / per_warp);
-    if (warps > 16) warps = 16;
+    if (warps > T2_MAX_THREADS / 32) warps = T2_MAX_THREADS / 32;
     if (warps < 1) warps = 1;
     g.warps = warps;
     g.smem = tables + per_warp * warps;
