@@ -102,32 +102,33 @@ __device__ __forceinline__ void compute_c(const Slots<NS>& W, const double* __re
     double a0[NS], a1[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) a0[s] = a1[s] = 0.0;
+    const int col0 = NS * lane;
+    const int nvalid = n - col0;
+    const bool vec = ((n & 1) == 0);
     int e = 0;
-    for (; e + 1 < m; e += 2) {
-        const double m0 = S[oM + e], m1 = S[oM + e + 1];
-        const double* d0 = D + e * n;
-        const double* d1 = d0 + n;
+    if (nvalid > 0) {
+        for (; e + 1 < m; e += 2) {
+            const double m0 = S[oM + e], m1 = S[oM + e + 1];
+            double v0[NS], v1[NS];
+            ldg_vec<NS>(D + e * n + col0, vec, nvalid, v0);
+            ldg_vec<NS>(D + (e + 1) * n + col0, vec, nvalid, v1);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            int col = lane + 32 * s;
-            if (col < n) {
-                a0[s] = fma(__ldg(d0 + col), m0, a0[s]);
-                a1[s] = fma(__ldg(d1 + col), m1, a1[s]);
+            for (int s = 0; s < NS; ++s) {
+                a0[s] = fma(v0[s], m0, a0[s]);
+                a1[s] = fma(v1[s], m1, a1[s]);
             }
         }
-    }
-    if (e < m) {
-        const double m0 = S[oM + e];
-        const double* d0 = D + e * n;
+        if (e < m) {
+            const double m0 = S[oM + e];
+            double v0[NS];
+            ldg_vec<NS>(D + e * n + col0, vec, nvalid, v0);
 #pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            int col = lane + 32 * s;
-            if (col < n) a0[s] = fma(__ldg(d0 + col), m0, a0[s]);
+            for (int s = 0; s < NS; ++s) a0[s] = fma(v0[s], m0, a0[s]);
         }
     }
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        int col = lane + 32 * s;
+        int col = NS * lane + s;
         if (col < n) S[W.cc + col] = a0[s] + a1[s];
     }
     __syncwarp();
@@ -183,7 +184,7 @@ __device__ __forceinline__ double reg_norm2(const Slots<NS>& W, int oLb, int n, 
     double s = 0.0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
-        int r = lane + 32 * t;
+        int r = NS * lane + t;
         if (r < n) {
             double acc = 0.0;
 #pragma unroll

@@ -41,7 +41,7 @@ __host__ __device__ __forceinline__ int fa_warp_doubles(int pmax) {
 }
 
 template <int NS, int ME>
-__global__ void __launch_bounds__(FA_WARPS * 32) fa_search_kernel(FaArgs A) {
+__global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_search_kernel(FaArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
     Slots<NS> W;
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_search_kernel(FaArgs A) {
             if (st) continue;
             compute_c<NS>(W, D, oM, m, n, lane);
             int nst = 0;
-            int p = nnls_gram<NS, false>(W, 0, G, 0, false, 0.0, n, m, lane, nst);
+            int p = nnls_gram<NS, false>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst);
             double fit[ME];
             double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
             double rnorm = sqrt(sse);
@@ -145,7 +145,7 @@ __device__ __forceinline__ double spline_eval(int oX, int oY, int oM2, int K, do
 }
 
 template <int NS, int ME>
-__global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
+__global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_select_kernel(FaArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE, nA = A.cfg.nA;
     Slots<NS> W;
@@ -212,13 +212,13 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
             const double* G = A.G + (size_t)index * n * n;
             compute_c<NS>(W, D, oM, m, n, lane);
             int nst = 0;
-            (void)nnls_gram<NS, false>(W, 0, G, 0, false, 0.0, n, m, lane, nst);
+            (void)nnls_gram<NS, false>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst);
             if (nst && lane == 0) A.status[v] |= MET2_ST_ITMAX;
             // nnls_gram leaves the solution in column space in S[W.xc..]; km = sum(f)
             double part = 0.0;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                int col = lane + 32 * s;
+                int col = NS * lane + s;
                 double xv = (col < n) ? S[W.xc + col] : 0.0;
                 fs[s] += xv;
                 part += xv;
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32) fa_select_kernel(FaArgs A) {
     if (A.partial) {
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            int col = lane + 32 * s;
+            int col = NS * lane + s;
             if (col < n) A.partial[gw * n + col] = fs[s];
         }
     }

@@ -99,16 +99,56 @@ struct Slots {
 
 __device__ __forceinline__ int& SI(int off, int k) { return reinterpret_cast<int*>(S + off)[k]; }
 
+// Column space: lane owns columns NS*lane + s (s < NS) so that its NS values are contiguous (128-bit LDS for NS = 2, 4).
+// Position space: lane owns positions lane + 32 t, so that sets with p <= 32 only touch slot 0.
+template <int NS>
+__device__ __forceinline__ int colof(int lane, int s) { return NS * lane + s; }
+
+// NS contiguous doubles from shared memory at S[off .. off+NS); off must be even when NS is even.
+template <int NS>
+__device__ __forceinline__ void lds_vec(int off, double (&v)[NS]) {
+    if constexpr (NS == 2) {
+        double2 t = *reinterpret_cast<const double2*>(S + off);
+        v[0] = t.x; v[1] = t.y;
+    } else if constexpr (NS == 4) {
+        double2 t = *reinterpret_cast<const double2*>(S + off);
+        double2 u = *reinterpret_cast<const double2*>(S + off + 2);
+        v[0] = t.x; v[1] = t.y; v[2] = u.x; v[3] = u.y;
+    } else {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) v[s] = S[off + s];
+    }
+}
+
+// NS contiguous doubles from global memory (read-only path); p must be 16-byte aligned when `vec` is set.
+template <int NS>
+__device__ __forceinline__ void ldg_vec(const double* __restrict__ p, bool vec, int nvalid, double (&v)[NS]) {
+    if ((NS == 2 || NS == 4) && vec && nvalid >= NS) {
+#pragma unroll
+        for (int s = 0; s < NS; s += 2) {
+            double2 t = __ldg(reinterpret_cast<const double2*>(p + s));
+            v[s] = t.x;
+            v[s + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) v[s] = (s < nvalid) ? __ldg(p + s) : 0.0;
+    }
+}
+
 // out[t] (position i = lane + 32 t) = sum_{k <= i, k < p} T(k, i) * v[k]   — column dot products, T^T v.
-// Segment `seg` of k (32 wide) only touches slots t >= seg; two accumulators per slot for ILP.
+// Segment `seg` of k (32 wide) only touches slots t >= seg; two accumulators per slot for ILP; the triangle
+// predicate is a single compare against kmax[t] (= i for live positions, -1 otherwise) so it compiles to predication.
 template <int NS>
 __device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane, double (&out)[NS]) {
     double a0[NS], a1[NS];
-    int base[NS];
+    int base[NS], kmax[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
         a0[t] = a1[t] = 0.0;
-        base[t] = oT + tri(lane + 32 * t);
+        base[t] = oT + tri(i);
+        kmax[t] = (i < p) ? i : -1;
     }
 #pragma unroll
     for (int seg = 0; seg < NS; ++seg) {
@@ -116,23 +156,23 @@ __device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane,
         if (k0 < p) {
             const int k1 = (p < k0 + 32) ? p : k0 + 32;
             int k = k0;
+#pragma unroll 2
             for (; k + 1 < k1; k += 2) {
                 const double v0 = S[oV + k], v1 = S[oV + k + 1];
 #pragma unroll
                 for (int t = seg; t < NS; ++t) {
-                    const int i = lane + 32 * t;
-                    if (i < p) {
-                        if (k <= i) a0[t] = fma(S[base[t] + k], v0, a0[t]);
-                        if (k + 1 <= i) a1[t] = fma(S[base[t] + k + 1], v1, a1[t]);
-                    }
+                    const double t0 = (k <= kmax[t]) ? S[base[t] + k] : 0.0;
+                    const double t1 = (k + 1 <= kmax[t]) ? S[base[t] + k + 1] : 0.0;
+                    a0[t] = fma(t0, v0, a0[t]);
+                    a1[t] = fma(t1, v1, a1[t]);
                 }
             }
             if (k < k1) {
                 const double v0 = S[oV + k];
 #pragma unroll
                 for (int t = seg; t < NS; ++t) {
-                    const int i = lane + 32 * t;
-                    if (i < p && k <= i) a0[t] = fma(S[base[t] + k], v0, a0[t]);
+                    const double t0 = (k <= kmax[t]) ? S[base[t] + k] : 0.0;
+                    a0[t] = fma(t0, v0, a0[t]);
                 }
             }
         }
@@ -154,23 +194,28 @@ __device__ __forceinline__ void tmul(int oT, int oV, int p, int lane, double (&o
         if (i0 < p) {
             const int i1 = (p < i0 + 32) ? p : i0 + 32;
             int i = i0;
+            int t0 = oT + tri(i);
+#pragma unroll 2
             for (; i + 1 < i1; i += 2) {
                 const double v0 = S[oV + i], v1 = S[oV + i + 1];
-                const int t0 = oT + tri(i), t1 = oT + tri(i + 1);
+                const int t1 = t0 + i + 1;
 #pragma unroll
                 for (int t = 0; t <= seg; ++t) {
                     const int k = lane + 32 * t;
-                    if (k <= i) a0[t] = fma(S[t0 + k], v0, a0[t]);
-                    if (k <= i + 1) a1[t] = fma(S[t1 + k], v1, a1[t]);
+                    const double e0 = (k <= i) ? S[t0 + k] : 0.0;
+                    const double e1 = (k <= i + 1) ? S[t1 + k] : 0.0;
+                    a0[t] = fma(e0, v0, a0[t]);
+                    a1[t] = fma(e1, v1, a1[t]);
                 }
+                t0 = t1 + i + 2;
             }
             if (i < i1) {
                 const double v0 = S[oV + i];
-                const int t0 = oT + tri(i);
 #pragma unroll
                 for (int t = 0; t <= seg; ++t) {
                     const int k = lane + 32 * t;
-                    if (k <= i) a0[t] = fma(S[t0 + k], v0, a0[t]);
+                    const double e0 = (k <= i) ? S[t0 + k] : 0.0;
+                    a0[t] = fma(e0, v0, a0[t]);
                 }
             }
         }
@@ -295,15 +340,17 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
 // memory at Gg.  reg: add lam * K, K given in 5-band form at S[oKb + d*n + c] = K[c+d-2][c].
 // On exit S[W.ix..] / S[W.xs..] hold the positive set and its coefficients, S[W.xc..] the solution in column space;
 // returns p.  status gets bit 0 on itmax.
+// ldg: row stride of G (shared: n rounded up to even so that rows stay 16-byte aligned; global: n).
 template <int NS, bool GSH>
-__device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int oKb, bool reg,
-                                         double lam, int n, int mrows, int lane, int& status) {
+__device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
+                                         bool reg, double lam, int n, int mrows, int lane, int& status) {
     const int itmax = 3 * n;
-    auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * n + c] : __ldg(Gg + r * n + c); };
+    auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * ldg + c] : __ldg(Gg + r * ldg + c); };
+    const int col0 = NS * lane;
     double creg[NS];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        int col = lane + 32 * s;
+        int col = col0 + s;
         creg[s] = (col < n) ? S[W.cc + col] : 0.0;
         if (col < n) S[W.xc + col] = 0.0;
     }
@@ -325,25 +372,60 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
                 w1[s] = 0.0;
             }
             int k = 0;
-            for (; k + 1 < p; k += 2) {
-                const int r0 = SI(W.ix, k) * n, r1 = SI(W.ix, k + 1) * n;
-                const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
+            if (GSH) {
+                // rows of G in shared memory: one vector LDS per row and lane (columns NS*lane .. NS*lane+NS-1)
+                const bool live = col0 < n;
+                for (; k + 1 < p; k += 2) {
+                    const int r0 = oG + SI(W.ix, k) * ldg + col0, r1 = oG + SI(W.ix, k + 1) * ldg + col0;
+                    const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
+                    if (live) {
+                        double g0[NS], g1[NS];
+                        lds_vec<NS>(r0, g0);
+                        lds_vec<NS>(r1, g1);
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    int col = lane + 32 * s;
-                    if (col < n) {
-                        w[s] = fma(-x0, GSH ? S[oG + r0 + col] : __ldg(Gg + r0 + col), w[s]);
-                        w1[s] = fma(-x1, GSH ? S[oG + r1 + col] : __ldg(Gg + r1 + col), w1[s]);
+                        for (int s = 0; s < NS; ++s) {
+                            w[s] = fma(-x0, g0[s], w[s]);
+                            w1[s] = fma(-x1, g1[s], w1[s]);
+                        }
                     }
                 }
-            }
-            if (k < p) {
-                const int r0 = SI(W.ix, k) * n;
-                const double x0 = S[W.xs + k];
+                if (k < p) {
+                    const int r0 = oG + SI(W.ix, k) * ldg + col0;
+                    const double x0 = S[W.xs + k];
+                    if (live) {
+                        double g0[NS];
+                        lds_vec<NS>(r0, g0);
 #pragma unroll
-                for (int s = 0; s < NS; ++s) {
-                    int col = lane + 32 * s;
-                    if (col < n) w[s] = fma(-x0, GSH ? S[oG + r0 + col] : __ldg(Gg + r0 + col), w[s]);
+                        for (int s = 0; s < NS; ++s) w[s] = fma(-x0, g0[s], w[s]);
+                    }
+                }
+            } else {
+                const bool vec = ((ldg & 1) == 0);
+                const int nvalid = n - col0;   // columns this lane really owns (<= 0: none)
+                for (; k + 1 < p; k += 2) {
+                    const double* g0 = Gg + SI(W.ix, k) * ldg + col0;
+                    const double* g1 = Gg + SI(W.ix, k + 1) * ldg + col0;
+                    const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
+                    if (nvalid > 0) {
+                        double v0[NS], v1[NS];
+                        ldg_vec<NS>(g0, vec, nvalid, v0);
+                        ldg_vec<NS>(g1, vec, nvalid, v1);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) {
+                            w[s] = fma(-x0, v0[s], w[s]);
+                            w1[s] = fma(-x1, v1[s], w1[s]);
+                        }
+                    }
+                }
+                if (k < p) {
+                    const double* g0 = Gg + SI(W.ix, k) * ldg + col0;
+                    const double x0 = S[W.xs + k];
+                    if (nvalid > 0) {
+                        double v0[NS];
+                        ldg_vec<NS>(g0, vec, nvalid, v0);
+#pragma unroll
+                        for (int s = 0; s < NS; ++s) w[s] = fma(-x0, v0[s], w[s]);
+                    }
                 }
             }
 #pragma unroll
@@ -351,7 +433,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             if (reg) {
 #pragma unroll
                 for (int s = 0; s < NS; ++s) {
-                    int col = lane + 32 * s;
+                    int col = col0 + s;
                     if (col < n) {
                         double acc = 0.0;
 #pragma unroll
@@ -375,7 +457,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             int bj = -1;
 #pragma unroll
             for (int s = 0; s < NS; ++s) {
-                int col = lane + 32 * s;
+                int col = col0 + s;
                 if (col < n && !((inP >> s) & 1u) && !((rejected >> s) & 1u) && w[s] > bv) {
                     bv = w[s];
                     bj = col;
@@ -420,7 +502,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             // rho < ~1e-14 unorm) or if its new coefficient ("ztest") is not positive
             const bool ok = (rho2 > 0.0) && (rho2 > 1.2e-28 * s1) && (ynew > 0.0);
             if (!ok) {
-                if ((j & 31) == lane) rejected |= 1u << (j >> 5);
+                if (j / NS == lane) rejected |= 1u << (j % NS);
                 __syncwarp();
                 continue;
             }
@@ -443,7 +525,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
                     S[W.xs + p] = 0.0;   // x of the entering column is 0 until the solve is accepted
                 }
             }
-            if ((j & 31) == lane) inP |= 1u << (j >> 5);
+            if (j / NS == lane) inP |= 1u << (j % NS);
             ++p;
             accepted = true;
             __syncwarp();
@@ -490,7 +572,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             int k = jb;
             while (true) {
                 int colk = SI(W.ix, k);
-                if ((colk & 31) == lane) inP &= ~(1u << (colk >> 5));
+                if (colk / NS == lane) inP &= ~(1u << (colk % NS));
                 if (lane == 0) S[W.xc + colk] = 0.0;
                 __syncwarp();
                 remove_position<NS>(W, k, p, lane, x);

@@ -147,8 +147,9 @@ __device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int 
 // ---------------------------------------------------------------------------------------------- fit kernel
 // shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
 // then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64]
+__host__ __device__ __forceinline__ int t2_ldg(int n) { return (n + 1) & ~1; }   // even row stride: 16-byte aligned rows
 __host__ __device__ __forceinline__ int t2_table_doubles(int n) {
-    return (n * n + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
+    return (n * t2_ldg(n) + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
 }
 
 template <int NS>
@@ -156,7 +157,7 @@ __host__ __device__ __forceinline__ int t2_warp_doubles(int pmax) {
     return (Slots<NS>::doubles(pmax) + 64 + 128 + 31) & ~31;
 }
 
-constexpr int T2_MAX_THREADS = 512;
+constexpr int T2_MAX_THREADS = 384;
 
 template <int NS, int ME>
 __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
     const int n = A.cfg.nT2, m = A.cfg.nTE;
     const int method = A.cfg.method;
     const int oG = 0;
-    const int oKb = oG + n * n;          // K band rows 0..4
+    const int ldg = t2_ldg(n);
+    const int oKb = oG + n * ldg;        // K band rows 0..4
     const int oLb = oKb + 5 * n;         // L band rows 0..4
     const int oLogT2 = oLb + 5 * n;
     const int oLam = oLogT2 + n;
@@ -198,7 +200,10 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
         const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
         {
             const double* Gg = A.G + (size_t)fa * n * n;
-            for (int i = threadIdx.x; i < n * n; i += blockDim.x) S[oG + i] = __ldg(Gg + i);
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+                const int r = i / n;
+                S[oG + r * ldg + (i - r * n)] = __ldg(Gg + i);
+            }
         }
         __syncthreads();
         const double* D = A.dic + (size_t)fa * m * n;
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 }
                 int nst = 0;
                 while (true) {
-                    p = nnls_gram<NS, true>(W, oG, nullptr, oKb, reg, lam, n, reg ? m + n : m, lane, nst);
+                    p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                     if (stage == ST_FINAL) {
                         if (method == MET2_REG_X2) regv = sse / SSE;   // k_est is what the orchestrator stores
@@ -297,7 +302,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
             double vt = 0.0;
 #pragma unroll
             for (int sidx = 0; sidx < NS; ++sidx) {
-                int col = lane + 32 * sidx;
+                int col = NS * lane + sidx;
                 xk[sidx] = (col < n && fitted) ? S[W.xc + col] * kmo : 0.0;
                 vt += xk[sidx];
                 if (col < n) A.fsol[v * n + col] = xk[sidx];
@@ -311,7 +316,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
             double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
 #pragma unroll
             for (int sidx = 0; sidx < NS; ++sidx) {
-                int col = lane + 32 * sidx;
+                int col = NS * lane + sidx;
                 if (col < n) {
                     double xn = xk[sidx] / vt;
                     unsigned char cm = scomp[col];
