@@ -144,6 +144,89 @@ __device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int 
     return (int)(ord % (unsigned)nl);
 }
 
+// ---------------------------------------------------------------------------------------------- BayesReg objective
+// -log evidence of bayesian_interpolation.py:107-126 for one lambda (= x), given the Tikhonov-NNLS solution f in
+// column space (S[W.xc..]):  A = beta*B + (beta*x)*K, U = chol(A) (upper), and
+//   cost = beta*ED + beta*x*EW + log(prod diag U) - (n/2) log(pi/2) - sum log(1 + erf(U f / sqrt 2))
+//        + (m/2) log(2 pi) - (m/2) log(beta) + (n/2) log(pi) - (n/2) log(2 beta x) - log(det L).
+// The n x n factor is built in place in the warp's T region (packed upper triangle, free between NNLS solves) by a
+// right-looking Cholesky: row k is scaled, then every lane updates the trailing part of the columns it owns.
+template <int NS>
+__device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg, int oKb, int n, int m, int lane,
+                                             double x, double beta, double sse, double nrm, double log_det_L,
+                                             unsigned& st) {
+    const int oT = W.T;
+    const double bx = beta * x;
+    // A[j][i], j <= i, packed column-major at oT + tri(i) + j
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < n) {
+            const int ti = oT + tri(i);
+            for (int j = 0; j <= i; ++j) {
+                double a = beta * S[oG + j * ldg + i];
+                const int d = j - i + 2;   // K[j][i] = kband[d][i], d = j - i + 2 in 0..4
+                if (d >= 0) a = a + bx * S[oKb + d * n + i];
+                S[ti + j] = a;
+            }
+        }
+    }
+    __syncwarp();
+    bool notpd = false;
+    for (int k = 0; k < n; ++k) {
+        const int tk = oT + tri(k);
+        const double akk = S[tk + k];
+        if (!(akk > 0.0)) notpd = true;
+        const double dk = sqrt(akk);
+        const double dinv = 1.0 / dk;
+        double uk[NS];
+        __syncwarp();
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int i = lane + 32 * t;
+            uk[t] = 0.0;
+            if (i > k && i < n) {
+                uk[t] = S[oT + tri(i) + k] * dinv;
+                S[oT + tri(i) + k] = uk[t];
+            } else if (i == k) {
+                S[tk + k] = dk;
+            }
+        }
+        __syncwarp();
+        for (int j = k + 1; j < n; ++j) {
+            const double ukj = S[oT + tri(j) + k];
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                const int i = lane + 32 * t;
+                if (i >= j && i < n) {
+                    const int a = oT + tri(i) + j;
+                    S[a] = fma(-ukj, uk[t], S[a]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (notpd) st |= MET2_ST_NOT_PD;
+    // det_U = prod(diag(U)) (np.prod order), U f (rows), series
+    double det_u = 1.0;
+    for (int k = 0; k < n; ++k) det_u *= S[oT + tri(k) + k];
+    double uf[NS];
+    tmul<NS>(oT, W.xc, n, lane, uf);
+    double series = 0.0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < n) series += log(1.0 + erf(0.7071067811865475 * uf[t]));
+    }
+    series = warp_sum(series);
+    const double ED = 0.5 * sse, EW = 0.5 * nrm;
+    const double PI = 3.141592653589793;
+    const double hn = n / 2.0, hm = m / 2.0;
+    const double cost1 = beta * ED + beta * x * EW + log(det_u) - hn * log(PI / 2.0) - series;
+    const double cost2 = hm * log(2.0 * PI) - hm * log(beta) + hn * log(PI) - hn * log(2.0 * beta * x) - log_det_L;
+    return notpd ? INFINITY : (cost1 + cost2);
+}
+
 // ---------------------------------------------------------------------------------------------- fit kernel
 // shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
 // then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64]
@@ -159,7 +242,8 @@ __host__ __device__ __forceinline__ int t2_warp_doubles(int pmax) {
 
 constexpr int T2_MAX_THREADS = 384;
 
-template <int NS, int ME>
+// GROUP 0: NNLS / T2SPARC / X2 / L_curve;  GROUP 1: BayesReg  (separate instantiations keep the common path lean)
+template <int NS, int ME, int GROUP>
 __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
     __shared__ int s_tile, s_next;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,12 +333,13 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     stage = ST_FINAL; reg = false;
                 } else if (method == MET2_REG_T2SPARC) {
                     stage = ST_FINAL; reg = true; lam = A.cfg.lambda_fixed;
-                } else if (method == MET2_REG_X2) {
+                } else if (method == MET2_REG_X2 || (GROUP == 1 && method == MET2_REG_BAYESREG)) {
                     stage = ST_PLAIN0; reg = false;
                 } else {   // MET2_REG_LCURVE
                     stage = ST_SEARCH; reg = true; lam = S[oLam];
                 }
                 int nst = 0;
+                double beta = 0.0;
                 while (true) {
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
@@ -263,7 +348,32 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                         else regv = lam;                               // (motor...:141-143); NNLS -> 0
                         break;
                     }
-                    if (method == MET2_REG_X2) {
+                    if (GROUP == 1 && method == MET2_REG_BAYESREG) {
+                        // bayesian_interpolation.py:84-105
+                        if (stage == ST_PLAIN0) {
+                            int nnz = 0;
+#pragma unroll
+                            for (int tt = 0; tt < NS; ++tt) {
+                                int i = lane + 32 * tt;
+                                if (i < p && S[W.xs + i] > 0.0) ++nnz;
+                            }
+                            nnz = __reduce_add_sync(FULL_MASK, nnz);
+                            const double dof = fmax((double)(m - nnz), 1.0);
+                            const double sigma = sqrt(sse / dof);
+                            beta = 1.0 / (sigma * sigma);
+                            lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
+                            reg = true;
+                            stage = ST_SEARCH;
+                        } else {
+                            const double nrm = reg_norm2<NS>(W, oLb, n, lane);
+                            const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
+                                                               A.cfg.log_det_L, st);
+                            if (!B.feed(cost, lam)) {
+                                lam = B.xf;
+                                stage = ST_FINAL;
+                            }
+                        }
+                    } else if (method == MET2_REG_X2) {
                         if (stage == ST_PLAIN0) {
                             SSE = sse;
                             if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
@@ -387,14 +497,20 @@ static T2Geom t2_geometry_any(long long V, const met2_t2_cfg* cfg) {
     return t2_geometry<4>(V, cfg);
 }
 
-template <int NS, int ME>
-static int t2_launch(const T2Args& A, const T2Geom& g, cudaStream_t st) {
-    cudaError_t e =
-        cudaFuncSetAttribute(t2_fit_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+template <int NS, int ME, int GROUP>
+static int t2_launch_group(const T2Args& A, const T2Geom& g, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(t2_fit_kernel<NS, ME, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)g.smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_fit attr (%zu B): %s", g.smem, cudaGetErrorString(e));
-    t2_fit_kernel<NS, ME><<<g.grid, g.warps * 32, g.smem, st>>>(A);
+    t2_fit_kernel<NS, ME, GROUP><<<g.grid, g.warps * 32, g.smem, st>>>(A);
     count_launch();
     return check_launch("t2_fit_kernel");
+}
+
+template <int NS, int ME>
+static int t2_launch(const T2Args& A, const T2Geom& g, cudaStream_t st) {
+    if (A.cfg.method == MET2_REG_BAYESREG) return t2_launch_group<NS, ME, 1>(A, g, st);
+    return t2_launch_group<NS, ME, 0>(A, g, st);
 }
 
 }  // namespace met2
@@ -407,8 +523,8 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
         return set_error(MET2_ERR_ARG, "met2_t2: unsupported sizes nT2=%d nTE=%d nA=%d", cfg->nT2, cfg->nTE, cfg->nA);
     if (cfg->method < MET2_REG_NNLS || cfg->method > MET2_REG_BAYESREG)
         return set_error(MET2_ERR_ARG, "met2_t2: unknown method %d", cfg->method);
-    if (cfg->method == MET2_REG_GCV || cfg->method == MET2_REG_BAYESREG)
-        return set_error(MET2_ERR_UNSUPPORTED, "met2_t2: method %d not implemented yet", cfg->method);
+    if (cfg->method == MET2_REG_GCV)
+        return set_error(MET2_ERR_UNSUPPORTED, "met2_t2: method %d (GCV) not implemented yet", cfg->method);
     if (cfg->method == MET2_REG_LCURVE && (cfg->nLambda < 3 || cfg->nLambda > MET2_MAX_LAMBDAS))
         return set_error(MET2_ERR_ARG, "met2_t2: L-curve needs 3..%d lambdas", MET2_MAX_LAMBDAS);
     return MET2_OK;

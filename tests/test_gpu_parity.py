@@ -13,6 +13,11 @@ pytestmark = pytest.mark.gpu
 
 REL_SPECTRUM = 1e-6
 ABS_MAPS = 1e-4
+# BayesReg with reg_matrix=InvT2: the reference does not reproduce ITSELF to 1e-6 — a 1e-13 relative perturbation of
+# the signal moves lambda by up to 2e-5 and the spectrum by up to 8e-6 in 13 of 48 voxels (flat evidence curve, Brent
+# xtol = 1e-5 absolute; measured with the oracle, DESIGN.md "Parity").  Like GCV it is held to active-set
+# equality, maps within 1e-4 and a looser spectrum/lambda tolerance.
+LOOSE = {("BayesReg", "InvT2"): dict(rel_spectrum=1e-3, rel_reg=1e-3, abs_t2=5e-3)}
 
 
 def _plan(**kw):
@@ -73,7 +78,8 @@ def test_config1_brute_force_nnls_all_voxels(phantom_sig):
 
 @pytest.mark.parametrize("method,rm", [("X2", "I"), ("X2", "L1"), ("X2", "L2"), ("X2", "InvT2"), ("L_curve", "I"),
                                        ("L_curve", "L2"), ("L_curve", "InvT2"), ("T2SPARC", "InvT2"),
-                                       ("T2SPARC", "I")])
+                                       ("T2SPARC", "I"), ("BayesReg", "I"), ("BayesReg", "L1"), ("BayesReg", "L2"),
+                                       ("BayesReg", "InvT2")])
 def test_spline_fa_plus_regularised_fit_vs_oracle(phantom_sig, method, rm):
     plan = _plan(reg_method=method, reg_matrix=rm, FA_method="spline", npc=60)
     sig = phantom_sig[:160]
@@ -86,9 +92,12 @@ def test_spline_fa_plus_regularised_fit_vs_oracle(phantom_sig, method, rm):
     f_ref, s_ref, reg_ref = O.fitting_slice_T2(ok, sig, idx, V, Dic, plan.lambda_reg, 60, 32, method, plan.Laplac)
     f = t2["fsol"].cpu().numpy()
     assert np.array_equal(f > 0, f_ref > 0), "active sets differ in %d voxels" % np.any((f > 0) != (f_ref > 0), 1).sum()
-    assert _rel_err(f, f_ref).max() < REL_SPECTRUM
-    assert np.allclose(t2["reg"].cpu().numpy(), reg_ref, rtol=1e-6, atol=0)
-    assert np.abs(t2["maps"].cpu().numpy()[:, :5] - _metrics(f_ref, plan)[:, :5]).max() < ABS_MAPS
+    tol = LOOSE.get((method, rm), dict(rel_spectrum=REL_SPECTRUM, rel_reg=1e-6))
+    assert _rel_err(f, f_ref).max() < tol["rel_spectrum"]
+    assert np.allclose(t2["reg"].cpu().numpy(), reg_ref, rtol=tol["rel_reg"], atol=0)
+    dm = np.abs(t2["maps"].cpu().numpy()[:, :5] - _metrics(f_ref, plan)[:, :5]).max(axis=0)
+    assert dm[:3].max() < ABS_MAPS                       # MWF, IEWF, FWF
+    assert dm[3:].max() < tol.get("abs_t2", ABS_MAPS)    # T2_M, T2_IE (ms)
     assert not t2["status"].cpu().numpy().any()
 
 
@@ -105,15 +114,18 @@ def test_golden_vectors_from_reference(golden_voxels):
     planb = _plan(reg_method="NNLS", reg_matrix="I", FA_method="brute-force")
     fab = planb.fa_fit(sig[keep])
     assert np.array_equal(fab["fa_index"].cpu().numpy(), g["fa_brute_idx"][keep].astype(np.int64))
-    for method, rm in [("NNLS", "I"), ("T2SPARC", "I"), ("X2", "I"), ("X2", "L2"), ("L_curve", "L1"), ("X2", "InvT2")]:
+    for method, rm in [("NNLS", "I"), ("T2SPARC", "I"), ("X2", "I"), ("X2", "L2"), ("L_curve", "L1"), ("X2", "InvT2"),
+                       ("BayesReg", "I"), ("BayesReg", "InvT2"), ("BayesReg", "L2")]:
         pl = _plan(reg_method=method, reg_matrix=rm, FA_method="spline", npc=60)
         t2 = pl.t2_fit(sig[keep], g["fa_spline_idx"][keep].astype(np.int32))
         f = t2["fsol"].cpu().numpy()
         gf = g["t2_%s_%s_f" % (method, rm)][keep]
         assert np.array_equal(f > 0, gf > 0), (method, rm)
-        assert _rel_err(f, gf).max() < REL_SPECTRUM, (method, rm)
-        assert np.allclose(t2["reg"].cpu().numpy(), g["t2_%s_%s_reg" % (method, rm)][keep], rtol=1e-6, atol=0)
-        assert np.abs(t2["est_signal"].cpu().numpy() - g["t2_%s_%s_s" % (method, rm)][keep]).max() < 1e-6 * gf.max()
+        tol = LOOSE.get((method, rm), dict(rel_spectrum=REL_SPECTRUM, rel_reg=1e-6))
+        assert _rel_err(f, gf).max() < tol["rel_spectrum"], (method, rm)
+        assert np.allclose(t2["reg"].cpu().numpy(), g["t2_%s_%s_reg" % (method, rm)][keep], rtol=tol["rel_reg"], atol=0)
+        assert np.abs(t2["est_signal"].cpu().numpy() - g["t2_%s_%s_s" % (method, rm)][keep]).max() < \
+            tol["rel_spectrum"] * gf.max()
         st = t2["status"].cpu().numpy()
         assert st[np.nonzero(keep)[0].tolist().index(3)] & batched.ST_SKIPPED      # empty voxel
         assert st[np.nonzero(keep)[0].tolist().index(9)] & batched.ST_SKIPPED      # M[0] == 0
