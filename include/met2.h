@@ -69,6 +69,11 @@ typedef struct met2_fa_cfg {
     int32_t reserved;
 } met2_fa_cfg;
 
+/* met2_t2_cfg.flags */
+#define MET2_T2_FLAG_REG_IS_LAMBDA 1 /* reg[v] = the selected lambda for every method (default: what the orchestrator
+                                        stores, motor...:134-155: 0 | 1.8 | k_est for X2 | lambda) */
+#define MET2_T2_FLAG_NO_NORMALISE 2  /* fit M as given instead of M / M[0] (per-voxel API of algorithms.py) */
+
 typedef struct met2_t2_cfg {
     int32_t method;   /* MET2_REG_* */
     int32_t nTE, nT2, nA;
@@ -78,7 +83,7 @@ typedef struct met2_t2_cfg {
     double lambda_fixed; /* T2SPARC 1.8 (motor...:138) */
     double brent_lo, brent_hi, brent_xatol; /* X2 [0,10]; GCV [1e-8,10]; BayesReg [1e-8,2]; xtol 1e-5 */
     double log_det_L;    /* BayesReg: log(det(L)) (bayesian_interpolation.py:100,123); -inf for L2 */
-    int32_t regularised; /* 0: lambda*K term absent (plain NNLS) */
+    int32_t flags;       /* MET2_T2_FLAG_* */
     int32_t reserved;
 } met2_t2_cfg;
 
@@ -94,7 +99,7 @@ int met2_epg_signals(const double* alphas_deg, const double* T2s, const double* 
                      double* sig, void* stream);
 
 /* Gram tables of the dictionary, G[a] = D_a^T D_a  ([nA][nT2][nT2]), and the 5-band form of K = L^T L
- * (kband[5][nT2], kband[d][c] = K[c+d-2][c]) for the Tikhonov term of algorithms.py:262-269 (A = [D; sqrt(lambda) L]).
+ * (kband[10][nT2]: rows 0..4 kband[d][c] = K[c+d-2][c], rows 5..9 the row-band form of L itself, kband[5+d][r] = L[r][r+d-2]) for the Tikhonov term of algorithms.py:262-269 (A = [D; sqrt(lambda) L]).
  * L is the dense [nT2][nT2] matrix of motor...:86-111,254-273; *band_err (device int, may be NULL) is set to 1 if
  * L^T L has an entry outside the five central diagonals (not the case for I, L1, L2, InvT2).  L/kband may be NULL. */
 int met2_gram_tables(const double* dic, int nA, int nTE, int nT2, const double* L, double* G, double* kband,

@@ -22,7 +22,7 @@ class T2Cfg(ctypes.Structure):
                 ("nLambda", ctypes.c_int32), ("maxfun", ctypes.c_int32),
                 ("factor", ctypes.c_double), ("lambda_fixed", ctypes.c_double),
                 ("brent_lo", ctypes.c_double), ("brent_hi", ctypes.c_double), ("brent_xatol", ctypes.c_double),
-                ("log_det_L", ctypes.c_double), ("regularised", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("log_det_L", ctypes.c_double), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 # every symbol include/met2.h declares, with its ctypes signature

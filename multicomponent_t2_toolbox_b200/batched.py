@@ -63,6 +63,25 @@ class Dictionary:
             _lib.check(lib.met2_gram_tables(_ptr(self.dic), self.nA, self.nTE, self.nT2, None, _ptr(self.G), None, None,
                                             _stream()), "met2_gram_tables")
 
+    @classmethod
+    def from_reference_layout(cls, Dic_3D, alphas, dev):
+        """Device tables for a dictionary given on the host as Dic_3D[nTE, nT2, nA] (any forward model)."""
+        lib = _lib.load()
+        self = cls.__new__(cls)
+        Dic_3D = np.asarray(Dic_3D, dtype=np.float64)
+        if Dic_3D.ndim == 2:
+            Dic_3D = Dic_3D[:, :, None]
+        self.nTE, self.nT2, self.nA = Dic_3D.shape
+        self.alphas_host = np.ascontiguousarray(alphas if alphas is not None else np.zeros(self.nA), dtype=np.float64)
+        self.alphas = _dev_f64(self.alphas_host, dev)
+        self.dic = _dev_f64(np.transpose(Dic_3D, (2, 0, 1)), dev)
+        self.dicT = _dev_f64(np.transpose(Dic_3D, (2, 1, 0)), dev)
+        self.G = torch.empty((self.nA, self.nT2, self.nT2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.met2_gram_tables(_ptr(self.dic), self.nA, self.nTE, self.nT2, None, _ptr(self.G), None, None,
+                                            _stream()), "met2_gram_tables")
+        return self
+
     def to_reference_layout(self):
         """Host copy in the reference's layout Dic_3D[nTE, nT2, nA] (epg/epg.py:155-162)."""
         return np.ascontiguousarray(self.dic.permute(1, 2, 0).cpu().numpy())
@@ -70,7 +89,11 @@ class Dictionary:
 
 class Met2Plan:
     def __init__(self, n_echoes, tau, TR, reg_method="X2", reg_matrix="I", FA_method="spline", myelin_T2=40.0,
-                 npc=None, n_alphas=None, T1=1000.0, device=None, lambda_reg=None, Laplac=None):
+                 npc=None, n_alphas=None, T1=1000.0, device=None, lambda_reg=None, Laplac=None, Dic_3D=None,
+                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None):
+        """Tables for one reconstruction set-up.  By default everything is built like motor...:204-277 (EPG dictionary
+        on the GPU); `Dic_3D` (+ `Dic_3D_LR`, `alpha_values`, `alpha_values_spline`, `T2s`, `Laplac`) lets a caller bring
+        its own dictionary in the reference layout [nTE, nT2, nA] — used by the drop-in row workers and per-voxel API."""
         if reg_method not in REG_METHOD_CODE:
             raise ValueError("unknown reg_method %r" % (reg_method,))
         if FA_method not in FA_METHOD_CODE:
@@ -79,11 +102,30 @@ class Met2Plan:
         self.lib = _lib.load()
         self.reg_method, self.reg_matrix, self.FA_method = reg_method, reg_matrix, FA_method
         self.nTE, self.tau, self.TR = int(n_echoes), float(tau), float(TR)
+        if Dic_3D is not None:
+            Dic_3D = np.asarray(Dic_3D, dtype=np.float64)
+            if Dic_3D.ndim == 2:
+                Dic_3D = Dic_3D[:, :, None]
+            npc = Dic_3D.shape[1]
+            if Dic_3D.shape[0] != self.nTE:
+                raise ValueError("Dic_3D has %d echoes, expected %d" % (Dic_3D.shape[0], self.nTE))
         self.npc = grids.default_npc(reg_method) if npc is None else int(npc)
-        self.T2s = grids.t2_grid(self.npc)
+        self.T2s = grids.t2_grid(self.npc) if T2s is None else np.asarray(T2s, dtype=np.float64)
         self.T1s = float(T1) * np.ones_like(self.T2s)
         self.ind_m, self.ind_t, self.ind_csf = grids.compartment_masks(self.T2s, myelin_T2)
         self.alpha_values, self.alpha_spline = grids.fa_grids(FA_method, n_alphas)
+        if Dic_3D is not None:
+            self.alpha_values = (np.asarray(alpha_values, dtype=np.float64) if alpha_values is not None
+                                 else np.zeros(Dic_3D.shape[2]))
+            if len(self.alpha_values) != Dic_3D.shape[2]:
+                raise ValueError("alpha_values does not match Dic_3D")
+            if FA_method == "spline":
+                if Dic_3D_LR is None or alpha_values_spline is None:
+                    if alpha_values is not None:
+                        raise ValueError("spline FA with a caller dictionary needs Dic_3D_LR and alpha_values_spline")
+                    self.alpha_spline = None
+                else:
+                    self.alpha_spline = np.asarray(alpha_values_spline, dtype=np.float64)
         self.lambda_reg = grids.lambda_grid() if lambda_reg is None else np.asarray(lambda_reg, dtype=np.float64)
         self.Laplac = grids.reg_matrix(reg_matrix, self.T2s) if Laplac is None else np.asarray(Laplac, np.float64)
         K = self.Laplac.T @ self.Laplac
@@ -91,11 +133,17 @@ class Met2Plan:
         if np.any(K[off] != 0.0) or np.any(self.Laplac[off] != 0.0):
             raise ValueError("regularisation matrix must be banded (|i-j| <= 2), like I, L1, L2, InvT2")
         with torch.cuda.device(self.dev):
-            self.dict_hr = Dictionary(self.alpha_values, self.T2s, self.T1s, self.nTE, tau, TR, self.dev)
             self.dict_lr = None
-            if FA_method == "spline":
-                self.dict_lr = Dictionary(self.alpha_spline, self.T2s, self.T1s, self.nTE, tau, TR, self.dev)
-                self.knots = _dev_f64(self.alpha_spline, self.dev)
+            if Dic_3D is not None:
+                self.dict_hr = Dictionary.from_reference_layout(Dic_3D, self.alpha_values, self.dev)
+                if FA_method == "spline" and self.alpha_spline is not None:
+                    self.dict_lr = Dictionary.from_reference_layout(Dic_3D_LR, self.alpha_spline, self.dev)
+                    self.knots = _dev_f64(self.alpha_spline, self.dev)
+            else:
+                self.dict_hr = Dictionary(self.alpha_values, self.T2s, self.T1s, self.nTE, tau, TR, self.dev)
+                if FA_method == "spline":
+                    self.dict_lr = Dictionary(self.alpha_spline, self.T2s, self.T1s, self.nTE, tau, TR, self.dev)
+                    self.knots = _dev_f64(self.alpha_spline, self.dev)
             self.L_dev = _dev_f64(self.Laplac, self.dev)
             self.kband = torch.zeros((10, self.npc), dtype=torch.float64, device=self.dev)
             self.band_err = torch.zeros(1, dtype=torch.int32, device=self.dev)
@@ -114,17 +162,19 @@ class Met2Plan:
                           final_solve=int(final_solve), brent_lo=90.0, brent_hi=180.0, brent_xatol=1e-5,
                           brent_maxfun=500, reserved=0)
 
-    def t2_cfg(self, reg_method=None):
+    def t2_cfg(self, reg_method=None, flags=0, **overrides):
         method = self.reg_method if reg_method is None else reg_method
         cfg = _lib.T2Cfg(method=REG_METHOD_CODE[method], nTE=self.nTE, nT2=self.npc, nA=len(self.alpha_values),
                          nLambda=len(self.lambda_reg), maxfun=300, factor=1.02, lambda_fixed=1.8, brent_lo=0.0,
-                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, regularised=int(method != "NNLS"), reserved=0)
+                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=int(flags), reserved=0)
         if method == "GCV":
             cfg.brent_lo = 1e-8
         if method == "BayesReg":
             cfg.brent_lo, cfg.brent_hi, cfg.maxfun = 1e-8, 2.0, 200
             with np.errstate(divide="ignore"):
                 cfg.log_det_L = float(np.log(np.linalg.det(self.Laplac)))
+        for k, v in overrides.items():   # e.g. factor=..., lambda_fixed=..., maxfun=...
+            setattr(cfg, k, v)
         return cfg
 
     def _workspace(self, key, nbytes):
@@ -156,6 +206,8 @@ class Met2Plan:
                        status=torch.empty(V, dtype=torch.int32, device=dev))
         if V == 0:
             return out
+        if self.FA_method == "spline" and self.dict_lr is None:
+            raise ValueError("this plan was built without a coarse (spline) dictionary")
         cfg = self.fa_cfg(final_solve)
         with torch.cuda.device(dev):
             nbytes = self.lib.met2_fa_workspace_bytes(V, ctypes.byref(cfg))
@@ -171,7 +223,7 @@ class Met2Plan:
         return out
 
     # ------------------------------------------------------------------ Steps 3 + 4
-    def t2_fit(self, sig, fa_index, reg_method=None, out=None):
+    def t2_fit(self, sig, fa_index, reg_method=None, out=None, flags=0, **cfg_overrides):
         """Spectrum fit + metrics.  Returns dict(fsol[V,nT2], est_signal[V,nTE], reg[V], maps[V,6], status[V])."""
         sig = self._signals(sig)
         V = sig.shape[0]
@@ -189,7 +241,7 @@ class Met2Plan:
                        status=torch.empty(V, dtype=torch.int32, device=dev))
         if V == 0:
             return out
-        cfg = self.t2_cfg(reg_method)
+        cfg = self.t2_cfg(reg_method, flags, **cfg_overrides)
         with torch.cuda.device(dev):
             nbytes = self.lib.met2_t2_workspace_bytes(V, ctypes.byref(cfg))
             if nbytes < 0:

@@ -302,7 +302,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
             // ---- load, validity (motor...:124-131), normalise by km = M[0]
             unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             const int fav = A.fa_index[v];
-            const double km = S[oM];
+            const bool normalise = !(A.cfg.flags & MET2_T2_FLAG_NO_NORMALISE);
+            const double km = normalise ? S[oM] : 1.0;
             if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
             double regv = 0.0;
             int p = 0;
@@ -344,8 +345,10 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                     if (stage == ST_FINAL) {
-                        if (method == MET2_REG_X2) regv = sse / SSE;   // k_est is what the orchestrator stores
-                        else regv = lam;                               // (motor...:141-143); NNLS -> 0
+                        if (method == MET2_REG_X2 && !(A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA))
+                            regv = sse / SSE;   // k_est is what the orchestrator stores (motor...:141-143)
+                        else
+                            regv = lam;         // NNLS -> 0
                         break;
                     }
                     if (GROUP == 1 && method == MET2_REG_BAYESREG) {

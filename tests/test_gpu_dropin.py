@@ -1,0 +1,111 @@
+"""Drop-in surface on the GPU: the reference's row workers / per-voxel functions / motor_recon_met2 under their own
+names, checked against the golden vectors of the unmodified reference and the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import met2_oracle as O
+from multicomponent_t2_toolbox_b200 import nifti_io
+from multicomponent_t2_toolbox_b200.epg.epg import create_Dic_3D
+from multicomponent_t2_toolbox_b200.flip_angle_algorithms.fa_estimation import (
+    compute_optimal_FA, fitting_slice_FA_brute_force, fitting_slice_FA_spline_method)
+from multicomponent_t2_toolbox_b200.intravoxel_algorithms.algorithms import nnls, nnls_lcurve_wrapper, nnls_tik, nnls_x2
+from multicomponent_t2_toolbox_b200.intravoxel_algorithms.bayesian_interpolation import BayesReg_nnls
+from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data import fitting_slice_T2, motor_recon_met2
+from multicomponent_t2_toolbox_b200.phantom import make_phantom
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dics(golden_voxels):
+    T2s = golden_voxels["T2s"]
+    T1s = 1000.0 * np.ones(60)
+    a273, a15, a91 = np.linspace(90, 180, 273), np.linspace(90, 180, 15), np.linspace(90, 180, 91)
+    mk = lambda a: create_Dic_3D(60, T2s, T1s, 32, 10.0, a, 1000.0)
+    return dict(a273=a273, a15=a15, a91=a91, d273=mk(a273), d15=mk(a15), d91=mk(a91))
+
+
+def test_create_Dic_3D_layout(golden_dictionary):
+    g = golden_dictionary
+    D = create_Dic_3D(60, g["T2s"], g["T1s"], int(g["nte"]), float(g["tau"]), g["alphas"], float(g["TR"]))
+    assert D.shape == g["dic"].shape and np.abs(D - g["dic"]).max() <= 1e-13
+
+
+def test_row_workers_against_reference_golden(golden_voxels, dics):
+    g = golden_voxels
+    nx = len(g["mask"])
+    FA, idx, KM, fs = fitting_slice_FA_brute_force(g["mask"], g["sig"], nx, dics["d91"], dics["a91"])
+    assert np.array_equal(idx, g["fa_brute_idx"]) and np.array_equal(FA, g["fa_brute_deg"])
+    assert np.allclose(KM, g["fa_brute_km"], rtol=1e-7) and np.allclose(fs, g["fa_brute_fsum"], rtol=1e-6, atol=1e-6)
+    FA, idx, KM, fs = fitting_slice_FA_spline_method(dics["d15"], dics["d273"], g["sig"], g["mask"], dics["a15"], nx,
+                                                     dics["a273"])
+    assert np.array_equal(idx, g["fa_spline_idx"]) and np.allclose(KM, g["fa_spline_km"], rtol=1e-7)
+    for method, rm in [("X2", "L1"), ("L_curve", "I"), ("NNLS", "I")]:
+        L = O._grids(method, rm, "spline", 40.0, 32, 10.0, 1000.0, npc=60)["L"]
+        f, s, reg = fitting_slice_T2(g["mask"], g["sig"], g["fa_spline_idx"], nx, dics["d273"], g["lambda_reg"], 60, 32,
+                                     method, L, None)
+        gf = g["t2_%s_%s_f" % (method, rm)]
+        assert np.array_equal(f > 0, gf > 0)
+        assert np.abs(f - gf).max() < 1e-6 * np.abs(gf).max()
+        assert np.allclose(reg, g["t2_%s_%s_reg" % (method, rm)], rtol=1e-6)
+        assert np.abs(s - g["t2_%s_%s_s" % (method, rm)]).max() < 1e-6 * np.abs(gf).max()
+
+
+def test_per_voxel_api(golden_voxels, dics):
+    g = golden_voxels
+    D = np.ascontiguousarray(dics["d273"][:, :, int(g["nnls_D_index"])])
+    M = g["sig"][0] / g["sig"][0, 0]
+    x, rn = nnls(D, M)
+    assert np.array_equal(x > 0, g["nnls_x"] > 0) and np.allclose(x, g["nnls_x"], rtol=1e-6, atol=1e-9)
+    assert abs(rn - float(g["nnls_rnorm"])) < 1e-8
+    L = np.eye(60)
+    for fun_g, fun_o in [(lambda: nnls_tik(D, M, L, 0.01), lambda: O.nnls_tik(D, M, L, 0.01))]:
+        assert np.allclose(fun_g(), fun_o(), rtol=1e-6, atol=1e-9)
+    f, lam, k = nnls_x2(D, M, L, 1.02)
+    fo, lamo, ko = O.nnls_x2(D, M, L, 1.02)
+    assert np.allclose(f, fo, rtol=1e-6, atol=1e-9) and abs(lam - lamo) < 1e-6 * lamo and abs(k - ko) < 1e-6
+    assert nnls_lcurve_wrapper(D, M, L, g["lambda_reg"]) == O.nnls_lcurve_wrapper(D, M, L, g["lambda_reg"])
+    fb, lb = BayesReg_nnls(D, M, L)
+    fbo, lbo = O.BayesReg_nnls(D, M, L)
+    assert np.allclose(fb, fbo, rtol=1e-6, atol=1e-9) and abs(lb - lbo) < 1e-6 * lbo
+    idx, alpha, km, sse, fsol = compute_optimal_FA(g["sig"][0], dics["d91"], dics["a91"])
+    io, ao, kmo, sseo, fo = O.compute_optimal_FA(g["sig"][0], dics["d91"], dics["a91"])
+    assert idx == io and alpha == ao and abs(km - kmo) < 1e-6 * kmo and abs(sse - sseo) < 1e-6 * sseo
+    with pytest.raises(ValueError):
+        nnls(D, np.full(32, np.nan))           # asarray_chkfinite, like algorithms.py:56
+
+
+def test_motor_recon_met2_files(tmp_path):
+    """Entry point with NIfTI in/out, config-1-like phantom with an ellipsoidal mask, FA_smooth both ways."""
+    ph = make_phantom((12, 10, 3), seed=6, mask_mode="ellipsoid")
+    aff = np.diag([2.0, 2.0, 3.0, 1.0])
+    nifti_io.save(ph["data"], str(tmp_path / "Data.nii.gz"), affine=aff)
+    nifti_io.save(ph["mask"].astype(np.int16), str(tmp_path / "Mask.nii.gz"), affine=aff)
+    out = str(tmp_path / "recon_all_X2-I") + "/"
+    os.mkdir(out)
+    TE = 10.0 * np.arange(1, 33)
+    motor_recon_met2(TE, str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"), out, 1000.0, "X2", "I", "None",
+                     "brute-force", "no", 40.0, -1)
+    ref = O.recon_volume(ph["data"], ph["mask"], TE, 1000.0, "X2", "I", "brute-force", num_cores=1)
+    names = {"MWF": "MWF", "IEWF": "IEWF", "FWF": "FWF", "T2_M": "T2_M", "T2_IE": "T2_IE", "TWC": "TWC", "FA": "FA",
+             "fsol_4D": "fsol_4D", "Est_Signal": "Est_Signal", "reg_param": "reg_param"}
+    for fname, key in names.items():
+        im = nifti_io.load(out + fname + ".nii.gz")
+        assert np.allclose(im.affine, aff)
+        got = im.get_fdata()
+        assert got.shape == ref[key].shape
+        if key in ("FA",):
+            assert np.array_equal(got, ref[key])
+        elif key in ("MWF", "IEWF", "FWF", "T2_M", "T2_IE"):
+            assert np.abs(got - ref[key]).max() < 1e-4, key
+        else:
+            assert np.abs(got - ref[key]).max() <= 1e-6 * np.abs(ref[key]).max(), key
+    # FA_smooth=yes only changes the FA-stage input (motor...:336-346)
+    vol = motor_recon_met2(TE, str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"), out, 1000.0, "NNLS", "I",
+                           "None", "spline", "yes", 40.0, -1)
+    assert vol["FA"][ph["mask"] > 0].min() >= 90.0 and not vol["FA"][ph["mask"] == 0].any()
+    with pytest.raises(NotImplementedError):
+        motor_recon_met2(TE, str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"), out, 1000.0, "NNLS", "I",
+                         "TV", "spline", "no", 40.0, -1)
