@@ -33,8 +33,9 @@ WORKLOAD = "config2: synthetic brain 96x96x60 (552960 voxels), nTE=32, 60 T2, FA
 
 # Algorithmic (reference-formulation) flops per voxel, SURVEY.md §8(d): Lawson-Hanson QR on [D; sqrt(lambda) L]
 # counted by oracle/flop_model.py (instrumented lh_nnls) on this workload; see DESIGN.md "Roofline".
-F_ALG_T2_X2_I = 18.8e6      # Step 3 (X2-I: 1 plain + ~29 augmented NNLS)       [flop / voxel]
-F_ALG_FA_SPLINE = 1.6e6     # Step 2 (16 plain NNLS)                             [flop / voxel]
+F_ALG_T2_X2_I = 19.35e6     # Step 3 (X2-I: 1 plain + ~28 augmented NNLS, 892 LH outer iterations) [flop / voxel]
+F_ALG_FA_SPLINE = 1.73e6    # Step 2 (16 plain NNLS)                                               [flop / voxel]
+                            # (oracle/F_ALG.json, 12 voxels of this workload; range of the X2 figure 15.2-22.4 MFLOP)
 FP64_PEAK_TFLOPS = 34.16    # own DFMA micro-benchmark on this pool's B200 (profiles/r01_fp64_peak_microbench.json);
                             # MEASURED_PEAKS.json has no FP64 entry
 HBM_BYTES_PER_VOXEL = 32 * 8 + 4 + 60 * 8 + 32 * 8 + 8 + 6 * 8 + 4   # T2 kernel: read signal+index, write outputs
