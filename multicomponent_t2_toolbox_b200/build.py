@@ -6,7 +6,8 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libmet2.so")
-SOURCES = ["met2_api.cu", "met2_epg.cu", "met2_fa.cu", "met2_t2.cu"]
+SOURCES = ["met2_api.cu", "met2_epg.cu", "met2_fa.cu", "met2_t2.cu", "met2_t2_m_nnls.cu", "met2_t2_m_t2sparc.cu",
+           "met2_t2_m_x2.cu", "met2_t2_m_lcurve.cu", "met2_t2_m_bayesreg.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     # no implicit FMA contraction: Brent / corner-selection comparisons must round like the reference's separate
@@ -36,16 +37,20 @@ def build_library(force=False, verbose=False):
     if not force and not needs_build():
         return LIB_PATH
     nvcc = _nvcc()
-    objs = []
-    logs = []
-    for src in SOURCES:
+    from concurrent.futures import ThreadPoolExecutor
+
+    def compile_one(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
-        logs.append(r.stderr)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s" % (src, r.stderr[-8000:]))
-        objs.append(obj)
+        return obj, r.stderr
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, SOURCES))
+    objs = [o for o, _ in results]
+    logs = [l for _, l in results]
     cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

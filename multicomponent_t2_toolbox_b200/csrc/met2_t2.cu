@@ -9,36 +9,9 @@
 // A persistent CTA takes a tile, stages that angle's Gram matrix G (n x n) and the band forms of K = L^T L and L in
 // shared memory, and its warps pull voxels of the tile one at a time.  One warp owns one voxel from its signal load to
 // its outputs: the whole lambda search (Brent / grid) runs in that warp, nothing per-voxel leaves the SM in between.
-#include <cmath>
-
-#include "met2_device.cuh"
-#include "met2_host.h"
+#include "met2_t2_impl.cuh"
 
 namespace met2 {
-
-constexpr int T2_TILE = 256;
-
-struct T2Args {
-    const double* sig;
-    const int* fa_index;
-    long long V;
-    met2_t2_cfg cfg;
-    const double *dic, *dicT, *G, *kband, *lambdas, *logT2;
-    const unsigned char* comp;
-    double *fsol, *est, *reg, *maps;
-    unsigned* status;
-    // workspace
-    int* hist;        // [nA]
-    int* cursor;      // [nA]
-    int* bin_start;   // [nA + 1]
-    int* perm;        // [V]
-    int* tile_fa;     // [max tiles]
-    int* tile_start;
-    int* tile_cnt;
-    int* counters;    // [0] = number of tiles, [1] = next tile
-    int pmax;
-    int warps;
-};
 
 // ---------------------------------------------------------------------------------------------- sort by FA index
 __global__ void t2_hist_kernel(const int* __restrict__ fa_index, long long V, int nA, int* __restrict__ hist) {
@@ -79,441 +52,6 @@ __global__ void t2_scatter_kernel(const int* __restrict__ fa_index, long long V,
     if (f < 0 || f >= nA) f = 0;
     int pos = bin_start[f] + atomicAdd(&cursor[f], 1);
     perm[pos] = (int)v;
-}
-
-// ---------------------------------------------------------------------------------------------- L-curve corner
-// Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves of length nl at S[oLx..], S[oLy..].
-__device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int lane) {
-    // scale both curves to [-10, 10]: ((u-l)/(vmax-vmin)) * (a - (u*vmin - l*vmax)/(u-l))
-    for (int c = 0; c < 2; ++c) {
-        const int oA = c ? oLy : oLx;
-        double vmin = INFINITY, vmax = -INFINITY;
-        bool has_nan = false;
-        for (int i = lane; i < nl; i += 32) {
-            double v = S[oA + i];
-            if (v != v) has_nan = true;
-            vmin = fmin(vmin, v);
-            vmax = fmax(vmax, v);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            vmin = fmin(vmin, __shfl_xor_sync(FULL_MASK, vmin, o));
-            vmax = fmax(vmax, __shfl_xor_sync(FULL_MASK, vmax, o));
-        }
-        if (__any_sync(FULL_MASK, has_nan)) vmin = vmax = NAN;   // numpy min/max propagate NaN
-        double scale = 20.0 / (vmax - vmin);
-        double shift = (10.0 * vmin - (-10.0) * vmax) / 20.0;
-        __syncwarp();
-        for (int i = lane; i < nl; i += 32) S[oA + i] = scale * (S[oA + i] - shift);
-        __syncwarp();
-    }
-    const double cte = 7.0 * 3.141592653589793 / 8.0;
-    const double cx = S[oLx + nl - 1], cy = S[oLy + nl - 1];
-    double best_ang = INFINITY;
-    int best_ord = -1;
-    for (int k = lane; k < nl - 2; k += 32) {
-        double bx = S[oLx + k], by = S[oLy + k];
-        for (int j = k + 1; j < nl - 1; ++j) {
-            double ax = S[oLx + j], ay = S[oLy + j];
-            double dx1 = ax - bx, dy1 = ay - by;
-            double ab = sqrt(dx1 * dx1 + dy1 * dy1);
-            double dx2 = ax - cx, dy2 = ay - cy;
-            double ac = sqrt(dx2 * dx2 + dy2 * dy2);
-            double dx3 = bx - cx, dy3 = by - cy;
-            double bc = sqrt(dx3 * dx3 + dy3 * dy3);
-            double cosa = (ab * ab + ac * ac - bc * bc) / (2.0 * ab * ac);
-            // Python: max(-1.0, min(cosa, 1.0)) -> NaN becomes -1.0
-            if (cosa != cosa) cosa = -1.0;
-            else cosa = fmax(-1.0, fmin(cosa, 1.0));
-            double ang = acos(cosa);
-            double area = 0.5 * ((bx - ax) * (ay - cy) - (ax - cx) * (by - ay));
-            if (area > 0.0 && ang < cte && ang < best_ang) {
-                best_ang = ang;
-                best_ord = k * nl + j;
-            }
-        }
-    }
-    // global minimum angle; ties -> earliest (k, j) in the reference's loop order
-    unsigned long long key = (best_ord >= 0) ? (unsigned long long)__double_as_longlong(best_ang + 0.0) : ~0ull;
-    unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-    unsigned mhi = __reduce_min_sync(FULL_MASK, hi);
-    unsigned mlo = __reduce_min_sync(FULL_MASK, (hi == mhi) ? lo : 0xffffffffu);
-    if (mhi == 0xffffffffu && mlo == 0xffffffffu) return nl - 1;
-    bool win = (best_ord >= 0) && hi == mhi && lo == mlo;
-    unsigned ord = __reduce_min_sync(FULL_MASK, win ? (unsigned)best_ord : 0xffffffffu);
-    return (int)(ord % (unsigned)nl);
-}
-
-// ---------------------------------------------------------------------------------------------- BayesReg objective
-// -log evidence of bayesian_interpolation.py:107-126 for one lambda (= x), given the Tikhonov-NNLS solution f in
-// column space (S[W.xc..]):  A = beta*B + (beta*x)*K, U = chol(A) (upper), and
-//   cost = beta*ED + beta*x*EW + log(prod diag U) - (n/2) log(pi/2) - sum log(1 + erf(U f / sqrt 2))
-//        + (m/2) log(2 pi) - (m/2) log(beta) + (n/2) log(pi) - (n/2) log(2 beta x) - log(det L).
-// The n x n factor is built in place in the warp's T region (packed upper triangle, free between NNLS solves) by a
-// right-looking Cholesky: row k is scaled, then every lane updates the trailing part of the columns it owns.
-template <int NS>
-__device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg, int oKb, int n, int m, int lane,
-                                             double x, double beta, double sse, double nrm, double log_det_L,
-                                             unsigned& st) {
-    const int oT = W.T;
-    const double bx = beta * x;
-    // A[j][i], j <= i, packed column-major at oT + tri(i) + j
-#pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        const int i = lane + 32 * t;
-        if (i < n) {
-            const int ti = oT + tri(i);
-            for (int j = 0; j <= i; ++j) {
-                double a = beta * S[oG + j * ldg + i];
-                const int d = j - i + 2;   // K[j][i] = kband[d][i], d = j - i + 2 in 0..4
-                if (d >= 0) a = a + bx * S[oKb + d * n + i];
-                S[ti + j] = a;
-            }
-        }
-    }
-    __syncwarp();
-    bool notpd = false;
-    for (int k = 0; k < n; ++k) {
-        const int tk = oT + tri(k);
-        const double akk = S[tk + k];
-        if (!(akk > 0.0)) notpd = true;
-        const double dk = sqrt(akk);
-        const double dinv = 1.0 / dk;
-        double uk[NS];
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            const int i = lane + 32 * t;
-            uk[t] = 0.0;
-            if (i > k && i < n) {
-                uk[t] = S[oT + tri(i) + k] * dinv;
-                S[oT + tri(i) + k] = uk[t];
-            } else if (i == k) {
-                S[tk + k] = dk;
-            }
-        }
-        __syncwarp();
-        for (int j = k + 1; j < n; ++j) {
-            const double ukj = S[oT + tri(j) + k];
-#pragma unroll
-            for (int t = 0; t < NS; ++t) {
-                const int i = lane + 32 * t;
-                if (i >= j && i < n) {
-                    const int a = oT + tri(i) + j;
-                    S[a] = fma(-ukj, uk[t], S[a]);
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (notpd) st |= MET2_ST_NOT_PD;
-    // det_U = prod(diag(U)) (np.prod order), U f (rows), series
-    double det_u = 1.0;
-    for (int k = 0; k < n; ++k) det_u *= S[oT + tri(k) + k];
-    double uf[NS];
-    tmul<NS>(oT, W.xc, n, lane, uf);
-    double series = 0.0;
-#pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        const int i = lane + 32 * t;
-        if (i < n) series += log(1.0 + erf(0.7071067811865475 * uf[t]));
-    }
-    series = warp_sum(series);
-    const double ED = 0.5 * sse, EW = 0.5 * nrm;
-    const double PI = 3.141592653589793;
-    const double hn = n / 2.0, hm = m / 2.0;
-    const double cost1 = beta * ED + beta * x * EW + log(det_u) - hn * log(PI / 2.0) - series;
-    const double cost2 = hm * log(2.0 * PI) - hm * log(beta) + hn * log(PI) - hn * log(2.0 * beta * x) - log_det_L;
-    return notpd ? INFINITY : (cost1 + cost2);
-}
-
-// ---------------------------------------------------------------------------------------------- fit kernel
-// shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
-// then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64]
-__host__ __device__ __forceinline__ int t2_ldg(int n) { return (n + 1) & ~1; }   // even row stride: 16-byte aligned rows
-__host__ __device__ __forceinline__ int t2_table_doubles(int n) {
-    return (n * t2_ldg(n) + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
-}
-
-template <int NS>
-__host__ __device__ __forceinline__ int t2_warp_doubles(int pmax) {
-    return (Slots<NS>::doubles(pmax) + 64 + 128 + 31) & ~31;
-}
-
-constexpr int T2_MAX_THREADS = 384;
-
-// GROUP 0: NNLS / T2SPARC / X2 / L_curve;  GROUP 1: BayesReg  (separate instantiations keep the common path lean)
-template <int NS, int ME, int GROUP>
-__global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
-    __shared__ int s_tile, s_next;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = A.cfg.nT2, m = A.cfg.nTE;
-    const int method = A.cfg.method;
-    const int oG = 0;
-    const int ldg = t2_ldg(n);
-    const int oKb = oG + n * ldg;        // K band rows 0..4
-    const int oLb = oKb + 5 * n;         // L band rows 0..4
-    const int oLogT2 = oLb + 5 * n;
-    const int oLam = oLogT2 + n;
-    unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLam + MET2_MAX_LAMBDAS);
-    const int wbase = t2_table_doubles(n) + warp * t2_warp_doubles<NS>(A.pmax);
-    Slots<NS> W;
-    W.carve(wbase, A.pmax);
-    const int oM = wbase + Slots<NS>::doubles(A.pmax);
-    const int oLx = oM + 64, oLy = oLx + 64;
-
-    for (int i = threadIdx.x; i < 10 * n; i += blockDim.x) S[oKb + i] = A.kband ? A.kband[i] : 0.0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        S[oLogT2 + i] = A.logT2[i];
-        scomp[i] = A.comp[i];
-    }
-    for (int i = threadIdx.x; i < MET2_MAX_LAMBDAS; i += blockDim.x)
-        S[oLam + i] = (A.lambdas && i < A.cfg.nLambda) ? A.lambdas[i] : 0.0;
-    const int ntiles = A.counters[0];
-
-    while (true) {
-        __syncthreads();   // previous tile fully consumed (G, s_next) before they are overwritten
-        if (threadIdx.x == 0) {
-            s_tile = atomicAdd(&A.counters[1], 1);
-            s_next = 0;
-        }
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= ntiles) break;
-        const int fa = A.tile_fa[tile];
-        const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
-        {
-            const double* Gg = A.G + (size_t)fa * n * n;
-            for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
-                const int r = i / n;
-                S[oG + r * ldg + (i - r * n)] = __ldg(Gg + i);
-            }
-        }
-        __syncthreads();
-        const double* D = A.dic + (size_t)fa * m * n;
-        const double* Dt = A.dicT + (size_t)fa * n * m;
-
-        while (true) {
-            int it = 0;
-            if (lane == 0) it = atomicAdd(&s_next, 1);
-            it = __shfl_sync(FULL_MASK, it, 0);
-            if (it >= tcnt) break;
-            const long long v = A.perm[tstart + it];
-            // ---- load, validity (motor...:124-131), normalise by km = M[0]
-            unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
-            const int fav = A.fa_index[v];
-            const bool normalise = !(A.cfg.flags & MET2_T2_FLAG_NO_NORMALISE);
-            const double km = normalise ? S[oM] : 1.0;
-            if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
-            double regv = 0.0;
-            int p = 0;
-            double fit[ME];
-#pragma unroll
-            for (int u = 0; u < ME; ++u) fit[u] = 0.0;
-            if (!st) {
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < ME; ++u) {
-                    int e = lane + 32 * u;
-                    if (e < m) S[oM + e] = S[oM + e] / km;
-                }
-                __syncwarp();
-                compute_c<NS>(W, D, oM, m, n, lane);
-                // ---- lambda-search driver: a small state machine around ONE inlined NNLS call site.
-                //   NNLS     : plain solve                                                    (algorithms.py:55)
-                //   T2SPARC  : one Tikhonov solve at lambda_fixed                             (algorithms.py:262)
-                //   X2       : plain solve -> SSE; Brent on |SSE(lam) - factor*SSE|/SSE; final (algorithms.py:211-233)
-                //   L_curve  : grid of nLambda solves -> curves -> corner; final               (algorithms.py:88-113)
-                enum { ST_PLAIN0 = 0, ST_SEARCH = 1, ST_FINAL = 2 };
-                int stage;
-                bool reg;
-                double lam = 0.0, SSE = 0.0;
-                int gi = 0;
-                Brent B;
-                if (method == MET2_REG_NNLS) {
-                    stage = ST_FINAL; reg = false;
-                } else if (method == MET2_REG_T2SPARC) {
-                    stage = ST_FINAL; reg = true; lam = A.cfg.lambda_fixed;
-                } else if (method == MET2_REG_X2 || (GROUP == 1 && method == MET2_REG_BAYESREG)) {
-                    stage = ST_PLAIN0; reg = false;
-                } else {   // MET2_REG_LCURVE
-                    stage = ST_SEARCH; reg = true; lam = S[oLam];
-                }
-                int nst = 0;
-                double beta = 0.0;
-                while (true) {
-                    p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst);
-                    const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
-                    if (stage == ST_FINAL) {
-                        if (method == MET2_REG_X2 && !(A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA))
-                            regv = sse / SSE;   // k_est is what the orchestrator stores (motor...:141-143)
-                        else
-                            regv = lam;         // NNLS -> 0
-                        break;
-                    }
-                    if (GROUP == 1 && method == MET2_REG_BAYESREG) {
-                        // bayesian_interpolation.py:84-105
-                        if (stage == ST_PLAIN0) {
-                            int nnz = 0;
-#pragma unroll
-                            for (int tt = 0; tt < NS; ++tt) {
-                                int i = lane + 32 * tt;
-                                if (i < p && S[W.xs + i] > 0.0) ++nnz;
-                            }
-                            nnz = __reduce_add_sync(FULL_MASK, nnz);
-                            const double dof = fmax((double)(m - nnz), 1.0);
-                            const double sigma = sqrt(sse / dof);
-                            beta = 1.0 / (sigma * sigma);
-                            lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
-                            reg = true;
-                            stage = ST_SEARCH;
-                        } else {
-                            const double nrm = reg_norm2<NS>(W, oLb, n, lane);
-                            const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
-                                                               A.cfg.log_det_L, st);
-                            if (!B.feed(cost, lam)) {
-                                lam = B.xf;
-                                stage = ST_FINAL;
-                            }
-                        }
-                    } else if (method == MET2_REG_X2) {
-                        if (stage == ST_PLAIN0) {
-                            SSE = sse;
-                            if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
-                            lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
-                            reg = true;
-                            stage = ST_SEARCH;
-                        } else {
-                            const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
-                            if (!B.feed(cost, lam)) {
-                                lam = B.xf;
-                                stage = ST_FINAL;
-                            }
-                        }
-                    } else {   // L-curve grid
-                        const double nrm = reg_norm2<NS>(W, oLb, n, lane);
-                        if (lane == 0) {
-                            S[oLx + gi] = log(sse + 1e-200);
-                            S[oLy + gi] = log(nrm + 1e-200);
-                        }
-                        __syncwarp();
-                        ++gi;
-                        if (gi < A.cfg.nLambda) {
-                            lam = S[oLam + gi];
-                        } else {
-                            lam = S[oLam + select_corner_warp(oLx, oLy, A.cfg.nLambda, lane)];
-                            stage = ST_FINAL;
-                        }
-                    }
-                }
-                if (nst) st |= MET2_ST_ITMAX;
-            }
-            // ---- outputs: fsol = x*km, Est_Signal = (D x)*km, reg, maps (motor...:153-155, 443-472)
-            const bool fitted = !(st & MET2_ST_SKIPPED);
-            const double kmo = fitted ? km : 0.0;
-            double xk[NS];
-            double vt = 0.0;
-#pragma unroll
-            for (int sidx = 0; sidx < NS; ++sidx) {
-                int col = NS * lane + sidx;
-                xk[sidx] = (col < n && fitted) ? S[W.xc + col] * kmo : 0.0;
-                vt += xk[sidx];
-                if (col < n) A.fsol[v * n + col] = xk[sidx];
-            }
-#pragma unroll
-            for (int u = 0; u < ME; ++u) {
-                int e = lane + 32 * u;
-                if (e < m) A.est[v * m + e] = fitted ? fit[u] * kmo : 0.0;
-            }
-            vt = warp_sum(vt) + 1.0e-16;
-            double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
-#pragma unroll
-            for (int sidx = 0; sidx < NS; ++sidx) {
-                int col = NS * lane + sidx;
-                if (col < n) {
-                    double xn = xk[sidx] / vt;
-                    unsigned char cm = scomp[col];
-                    if (cm & 1) {
-                        sm += xn;
-                        lm += xn * S[oLogT2 + col];
-                    }
-                    if (cm & 2) {
-                        stt += xn;
-                        lt += xn * S[oLogT2 + col];
-                    }
-                    if (cm & 4) sc += xn;
-                }
-            }
-            sm = warp_sum(sm);
-            stt = warp_sum(stt);
-            sc = warp_sum(sc);
-            lm = warp_sum(lm);
-            lt = warp_sum(lt);
-            if (lane == 0) {
-                double* mp = A.maps + v * 6;
-                mp[0] = sm;
-                mp[1] = stt;
-                mp[2] = sc;
-                mp[3] = exp(lm / (sm + 1.0e-16));
-                mp[4] = exp(lt / (stt + 1.0e-16));
-                mp[5] = vt;
-                A.reg[v] = fitted ? regv : 0.0;
-                A.status[v] = st;
-            }
-            __syncwarp();
-        }
-    }
-}
-
-struct T2Geom {
-    int grid, warps, pmax, max_tiles;
-    size_t smem;
-};
-
-template <int NS>
-static T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
-    T2Geom g;
-    const int n = cfg->nT2, m = cfg->nTE;
-    const bool plain = (cfg->method == MET2_REG_NNLS);
-    g.pmax = plain ? (n < m ? n : m) : n;
-    size_t tables = sizeof(double) * (size_t)t2_table_doubles(n);
-    size_t per_warp = sizeof(double) * (size_t)t2_warp_doubles<NS>(g.pmax);
-    size_t budget = 227 * 1024 - 1024;
-    int warps = (int)((budget - tables) / per_warp);
-    if (warps > T2_MAX_THREADS / 32) warps = T2_MAX_THREADS / 32;
-    if (warps < 1) warps = 1;
-    g.warps = warps;
-    g.smem = tables + per_warp * warps;
-    int per_sm = (int)(budget / (g.smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    int sms = sm_count();
-    if (sms <= 0) sms = 148;
-    g.grid = sms * per_sm;
-    g.max_tiles = (int)(V / T2_TILE) + cfg->nA + 1;
-    return g;
-}
-
-static T2Geom t2_geometry_any(long long V, const met2_t2_cfg* cfg) {
-    int ns = (cfg->nT2 + 31) / 32;
-    if (ns <= 2) return t2_geometry<2>(V, cfg);
-    if (ns == 3) return t2_geometry<3>(V, cfg);
-    return t2_geometry<4>(V, cfg);
-}
-
-template <int NS, int ME, int GROUP>
-static int t2_launch_group(const T2Args& A, const T2Geom& g, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(t2_fit_kernel<NS, ME, GROUP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)g.smem);
-    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_fit attr (%zu B): %s", g.smem, cudaGetErrorString(e));
-    t2_fit_kernel<NS, ME, GROUP><<<g.grid, g.warps * 32, g.smem, st>>>(A);
-    count_launch();
-    return check_launch("t2_fit_kernel");
-}
-
-template <int NS, int ME>
-static int t2_launch(const T2Args& A, const T2Geom& g, cudaStream_t st) {
-    if (A.cfg.method == MET2_REG_BAYESREG) return t2_launch_group<NS, ME, 1>(A, g, st);
-    return t2_launch_group<NS, ME, 0>(A, g, st);
 }
 
 }  // namespace met2
@@ -591,13 +129,12 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     t2_scatter_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);
     count_launch();
     if ((rc = check_launch("t2_scatter_kernel"))) return rc;
-    int ns = (cfg->nT2 + 31) / 32;
-    int me = (cfg->nTE + 31) / 32;
-    if (ns <= 2 && me == 1) return t2_launch<2, 1>(A, g, st);
-    if (ns <= 2 && me == 2) return t2_launch<2, 2>(A, g, st);
-    if (ns == 3 && me == 1) return t2_launch<3, 1>(A, g, st);
-    if (ns == 3 && me == 2) return t2_launch<3, 2>(A, g, st);
-    if (ns == 4 && me == 1) return t2_launch<4, 1>(A, g, st);
-    if (ns == 4 && me == 2) return t2_launch<4, 2>(A, g, st);
-    return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: unsupported template sizes");
+    switch (cfg->method) {
+        case MET2_REG_NNLS: return t2_launch_nnls(A, g, st);
+        case MET2_REG_T2SPARC: return t2_launch_t2sparc(A, g, st);
+        case MET2_REG_X2: return t2_launch_x2(A, g, st);
+        case MET2_REG_LCURVE: return t2_launch_lcurve(A, g, st);
+        case MET2_REG_BAYESREG: return t2_launch_bayesreg(A, g, st);
+        default: return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: method %d not implemented", cfg->method);
+    }
 }
