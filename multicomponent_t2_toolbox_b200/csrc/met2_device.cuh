@@ -134,6 +134,92 @@ __device__ __forceinline__ void compute_c(const Slots<NS>& W, const double* __re
     __syncwarp();
 }
 
+// Shared-memory variant: D ([m][n], row stride n, n even when NS is even) staged at S[oD..].
+template <int NS>
+__device__ __forceinline__ void compute_c_sh(const Slots<NS>& W, int oD, int oM, int m, int n, int lane) {
+    double a0[NS], a1[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) a0[s] = a1[s] = 0.0;
+    const int col0 = NS * lane;
+    if (col0 < n) {
+        const bool vec = ((n & 1) == 0) && (col0 + NS <= n);
+        int e = 0;
+        for (; e + 1 < m; e += 2) {
+            const double m0 = S[oM + e], m1 = S[oM + e + 1];
+            double v0[NS], v1[NS];
+            if (vec) {
+                lds_vec<NS>(oD + e * n + col0, v0);
+                lds_vec<NS>(oD + (e + 1) * n + col0, v1);
+            } else {
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    v0[s] = (col0 + s < n) ? S[oD + e * n + col0 + s] : 0.0;
+                    v1[s] = (col0 + s < n) ? S[oD + (e + 1) * n + col0 + s] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                a0[s] = fma(v0[s], m0, a0[s]);
+                a1[s] = fma(v1[s], m1, a1[s]);
+            }
+        }
+        if (e < m) {
+            const double m0 = S[oM + e];
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (col0 + s < n) a0[s] = fma(S[oD + e * n + col0 + s], m0, a0[s]);
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        int col = NS * lane + s;
+        if (col < n) S[W.cc + col] = a0[s] + a1[s];
+    }
+    __syncwarp();
+}
+
+// Shared-memory variant of fit_and_sse: Dt ([n][m]) staged at S[oDt..].
+template <int NS, int ME>
+__device__ __forceinline__ double fit_and_sse_sh(const Slots<NS>& W, int oDt, int oM, int m, int p, int lane,
+                                                 double (&fit)[ME]) {
+    double f1[ME];
+#pragma unroll
+    for (int u = 0; u < ME; ++u) fit[u] = f1[u] = 0.0;
+    int k = 0;
+    for (; k + 1 < p; k += 2) {
+        const int d0 = oDt + SI(W.ix, k) * m, d1 = oDt + SI(W.ix, k + 1) * m;
+        const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
+#pragma unroll
+        for (int u = 0; u < ME; ++u) {
+            int e = lane + 32 * u;
+            if (e < m) {
+                fit[u] = fma(S[d0 + e], x0, fit[u]);
+                f1[u] = fma(S[d1 + e], x1, f1[u]);
+            }
+        }
+    }
+    if (k < p) {
+        const int d0 = oDt + SI(W.ix, k) * m;
+        const double x0 = S[W.xs + k];
+#pragma unroll
+        for (int u = 0; u < ME; ++u) {
+            int e = lane + 32 * u;
+            if (e < m) fit[u] = fma(S[d0 + e], x0, fit[u]);
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        int e = lane + 32 * u;
+        fit[u] += f1[u];
+        if (e < m) {
+            double dd = fit[u] - S[oM + e];
+            s = fma(dd, dd, s);
+        }
+    }
+    return warp_sum(s);
+}
+
 // fit = D x for the current positive set (lane-slot u owns echo e = lane + 32 u) and SSE = sum (fit - M)^2.
 // Dt is [n][m] row-major (the transposed dictionary) in global memory.
 template <int NS, int ME>

@@ -3,7 +3,9 @@
 // Takes over flip_angle_algorithms/fa_estimation.py: compute_optimal_FA (:74-90, brute force),
 // fitting_slice_FA_spline_method (:35-70) and the joblib loop that drives them (motor/motor_recon_met2_real_data.py:349-373).
 //   kernel 1 (fa_search_kernel): residual norm of the plain NNLS fit for every search angle and voxel.  Angles are the
-//       OUTER loop of each CTA so the ~59 KB of tables of one angle (D, D^T, G) are shared by all its warps through L1.
+//       OUTER loop of each CTA: the ~59 KB of tables of one angle (D, D^T, G) are staged in shared memory once per
+//       angle and CTA (the version that read them through L1/L2 spent its time on L2 latency), and every voxel's fit
+//       is warm-started from its fit at the previous angle.
 //   kernel 2 (fa_select_kernel): brute force -> the running arg-min of kernel 1; spline -> not-a-knot cubic through the
 //       15 knot residuals, SciPy's bounded Brent on it, snap to the fine grid; then the NNLS at the chosen angle for
 //       km = sum(f) and the per-warp partial sums of f (mean_T2_dist).
@@ -29,8 +31,13 @@ struct FaArgs {
     double* resid;      // spline: [V][nS]; brute force: best residual [V]
     double* wsp;        // [nK][nK] spline weights
     double* partial;    // [total warps][nT2]
+    int* ws_p;          // [V] size of the positive set carried from the previous search angle (0 = none)
+    int* ws_ix;         // [V][FA_CARRY] its columns
+    double* ws_x;       // [V][FA_CARRY] its coefficients
     int pmax;
 };
+
+constexpr int FA_CARRY = 16;   // supports of the plain fits have 3-8 columns; larger ones restart cold
 
 constexpr int FA_WARPS = 8;
 
@@ -40,12 +47,20 @@ __host__ __device__ __forceinline__ int fa_warp_doubles(int pmax) {
     return (Slots<NS>::doubles(pmax) + 64 + 31) & ~31;
 }
 
+constexpr int FA_SEARCH_WARPS = 16;
+
+__host__ __device__ __forceinline__ int fa_ldg(int n) { return (n + 1) & ~1; }
+// staged tables of one angle, in doubles: D [m][n], Dt [n][m], G [n][ldg]
+__host__ __device__ __forceinline__ int fa_table_doubles(int n, int m) { return (2 * m * n + n * fa_ldg(n) + 31) & ~31; }
+
 template <int NS, int ME>
-__global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_search_kernel(FaArgs A) {
+__global__ void __launch_bounds__(FA_SEARCH_WARPS * 32, 1) fa_search_kernel(FaArgs A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
+    const int ldg = fa_ldg(n);
+    const int oD = 0, oDt = m * n, oG = 2 * m * n;
     Slots<NS> W;
-    const int wbase = warp * fa_warp_doubles<NS>(A.pmax);
+    const int wbase = fa_table_doubles(n, m) + warp * fa_warp_doubles<NS>(A.pmax);
     W.carve(wbase, A.pmax);
     const int oM = wbase + Slots<NS>::doubles(A.pmax);
     const long long chunk = (A.V + gridDim.x - 1) / gridDim.x;
@@ -53,17 +68,47 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_search_kernel(FaArgs A) {
     const long long v1 = (v0 + chunk < A.V) ? v0 + chunk : A.V;
     const bool brute = (A.cfg.method == MET2_FA_BRUTE_FORCE);
     for (int a = 0; a < A.nS; ++a) {
-        const double* D = A.dic_s + (size_t)a * m * n;
-        const double* Dt = A.dicT_s + (size_t)a * n * m;
-        const double* G = A.G_s + (size_t)a * n * n;
-        for (long long v = v0 + warp; v < v1; v += FA_WARPS) {
+        {
+            const double* D = A.dic_s + (size_t)a * m * n;
+            const double* Dt = A.dicT_s + (size_t)a * n * m;
+            const double* G = A.G_s + (size_t)a * n * n;
+            for (int i = threadIdx.x; i < m * n; i += blockDim.x) {
+                S[oD + i] = __ldg(D + i);
+                S[oDt + i] = __ldg(Dt + i);
+            }
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+                const int r = i / n;
+                S[oG + r * ldg + (i - r * n)] = __ldg(G + i);
+            }
+        }
+        __syncthreads();
+        for (long long v = v0 + warp; v < v1; v += FA_SEARCH_WARPS) {
             unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             if (st) continue;
-            compute_c<NS>(W, D, oM, m, n, lane);
+            compute_c_sh<NS>(W, oD, oM, m, n, lane);
+            // warm start from the fit at the previous search angle (same voxel, neighbouring dictionary): the residual
+            // norm of the NNLS optimum does not depend on the starting point
+            int p0 = 0;
+            if (a > 0) {
+                p0 = A.ws_p[v];
+                if (lane < p0) {
+                    SI(W.ix, lane) = A.ws_ix[v * FA_CARRY + lane];
+                    S[W.xs + lane] = A.ws_x[v * FA_CARRY + lane];
+                }
+                __syncwarp();
+            }
             int nst = 0;
-            int p = nnls_gram<NS, false>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst);
+            int p = nnls_gram<NS, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, p0);
+            if (a + 1 < A.nS) {
+                const bool keep = (p <= FA_CARRY);
+                if (keep && lane < p) {
+                    A.ws_ix[v * FA_CARRY + lane] = SI(W.ix, lane);
+                    A.ws_x[v * FA_CARRY + lane] = S[W.xs + lane];
+                }
+                if (lane == 0) A.ws_p[v] = keep ? p : 0;
+            }
             double fit[ME];
-            double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
+            double sse = fit_and_sse_sh<NS, ME>(W, oDt, oM, m, p, lane, fit);
             double rnorm = sqrt(sse);
             if (lane == 0) {
                 if (brute) {
@@ -79,7 +124,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_search_kernel(FaArgs A) {
             }
             __syncwarp();
         }
-        __syncthreads();   // keep the CTA's warps on the same angle (L1 locality of the tables)
+        __syncthreads();   // all warps are done with this angle's tables
     }
 }
 
@@ -251,9 +296,11 @@ __global__ void reduce_partials_kernel(const double* __restrict__ partial, long 
 }
 
 struct FaGeom {
-    int grid;
+    int grid;          // select kernel
     size_t smem;
     int pmax;
+    int grid_search;   // search kernel: one CTA of FA_SEARCH_WARPS warps per SM, tables staged in shared memory
+    size_t smem_search;
 };
 
 template <int NS>
@@ -267,6 +314,9 @@ static FaGeom fa_geometry(const met2_fa_cfg* cfg) {
     int sms = sm_count();
     if (sms <= 0) sms = 148;
     g.grid = sms * per_sm;
+    g.grid_search = sms;
+    g.smem_search = sizeof(double) * ((size_t)fa_table_doubles(cfg->nT2, cfg->nTE) +
+                                      (size_t)fa_warp_doubles<NS>(g.pmax) * FA_SEARCH_WARPS);
     return g;
 }
 
@@ -280,11 +330,12 @@ static FaGeom fa_geometry_any(const met2_fa_cfg* cfg) {
 template <int NS, int ME>
 static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
     cudaError_t e;
-    e = cudaFuncSetAttribute(fa_search_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
+    e = cudaFuncSetAttribute(fa_search_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)g.smem_search);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_search attr: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(fa_select_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_select attr: %s", cudaGetErrorString(e));
-    fa_search_kernel<NS, ME><<<g.grid, FA_WARPS * 32, g.smem, st>>>(A);
+    fa_search_kernel<NS, ME><<<g.grid_search, FA_SEARCH_WARPS * 32, g.smem_search, st>>>(A);
     count_launch();
     int rc = check_launch("fa_search_kernel");
     if (rc) return rc;
@@ -329,6 +380,8 @@ extern "C" int64_t met2_fa_workspace_bytes(int64_t V, const met2_fa_cfg* cfg) {
     size_t b = align256(sizeof(double) * (size_t)V * nS);
     b += align256(sizeof(double) * MET2_MAX_KNOTS * MET2_MAX_KNOTS);
     b += align256(sizeof(double) * (size_t)g.grid * FA_WARPS * cfg->nT2);
+    b += align256(sizeof(int) * (size_t)V) + align256(sizeof(int) * (size_t)V * FA_CARRY) +
+         align256(sizeof(double) * (size_t)V * FA_CARRY);
     return (int64_t)b + 256;
 }
 
@@ -366,6 +419,12 @@ extern "C" int met2_fa_fit(const double* sig, int64_t V, const met2_fa_cfg* cfg,
     A.wsp = reinterpret_cast<double*>(w);
     w += align256(sizeof(double) * MET2_MAX_KNOTS * MET2_MAX_KNOTS);
     A.partial = fsol_sum ? reinterpret_cast<double*>(w) : nullptr;
+    w += align256(sizeof(double) * (size_t)g.grid * FA_WARPS * cfg->nT2);
+    A.ws_p = reinterpret_cast<int*>(w);
+    w += align256(sizeof(int) * (size_t)V);
+    A.ws_ix = reinterpret_cast<int*>(w);
+    w += align256(sizeof(int) * (size_t)V * FA_CARRY);
+    A.ws_x = reinterpret_cast<double*>(w);
     A.pmax = g.pmax;
     cudaError_t e = cudaMemsetAsync(status, 0, sizeof(uint32_t) * (size_t)V, st);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "memset status: %s", cudaGetErrorString(e));
