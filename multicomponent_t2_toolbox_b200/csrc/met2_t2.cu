@@ -64,8 +64,13 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
         return set_error(MET2_ERR_ARG, "met2_t2: unsupported sizes nT2=%d nTE=%d nA=%d", cfg->nT2, cfg->nTE, cfg->nA);
     if (cfg->method < MET2_REG_NNLS || cfg->method > MET2_REG_BAYESREG)
         return set_error(MET2_ERR_ARG, "met2_t2: unknown method %d", cfg->method);
-    if (cfg->method == MET2_REG_GCV)
-        return set_error(MET2_ERR_UNSUPPORTED, "met2_t2: method %d (GCV) not implemented yet", cfg->method);
+    if (cfg->method == MET2_REG_GCV) {
+        // the Jacobi work matrix ((min(nT2, nTE+1))^2 with odd stride) lives in the packed-T region
+        const int N = cfg->nT2 < cfg->nTE + 1 ? cfg->nT2 : cfg->nTE + 1;
+        if (N * (N | 1) > (cfg->nT2 * (cfg->nT2 + 1)) / 2)
+            return set_error(MET2_ERR_UNSUPPORTED, "met2_t2: GCV needs (nTE+1)^2 <= nT2(nT2+1)/2 (nTE=%d nT2=%d)",
+                             cfg->nTE, cfg->nT2);
+    }
     if (cfg->method == MET2_REG_LCURVE && (cfg->nLambda < 3 || cfg->nLambda > MET2_MAX_LAMBDAS))
         return set_error(MET2_ERR_ARG, "met2_t2: L-curve needs 3..%d lambdas", MET2_MAX_LAMBDAS);
     return MET2_OK;
@@ -135,6 +140,7 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
         case MET2_REG_X2: return t2_launch_x2(A, g, st);
         case MET2_REG_LCURVE: return t2_launch_lcurve(A, g, st);
         case MET2_REG_BAYESREG: return t2_launch_bayesreg(A, g, st);
+        case MET2_REG_GCV: return t2_launch_gcv(A, g, st);
         default: return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: method %d not implemented", cfg->method);
     }
 }

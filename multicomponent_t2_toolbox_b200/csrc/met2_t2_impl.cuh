@@ -180,6 +180,214 @@ __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg
     return notpd ? INFINITY : (cost1 + cost2);
 }
 
+// ---------------------------------------------------------------------------------------------- GCV objective
+// obj_nnls_gcv of algorithms.py:285-296, quirks included: with sel = {f > 0} (k columns), Dr = D[:, sel] and the SCALAR
+// s = sum_sel L_ii^2 (the reference's L[f>0, f>0] picks diagonal entries), the reference forms Mk = Dr^T Dr + x s 1 1^T
+// (x s added to EVERY entry), A = Dr lstsq(Mk, Dr^T, rcond=None) and returns log( (SSEr^2/m) / ((m - tr A)/m)^2 ) with
+// SSEr the residual norm of the STACKED system.  lstsq (gelsd) is a truncated pseudo-inverse: singular values <= eps*k*s_max
+// are dropped.  With the symmetric eigen-decomposition Mk = V diag(l) V^T:  tr A = sum_kept (1 - x s (1^T v_i)^2 / l_i).
+// When k > m+1 the same non-zero spectrum is taken from the (m+1) x (m+1) matrix Er Er^T, Er = [Dr; sqrt(x s) 1^T]:
+// tr A = sum_kept (1 - u_i[m]^2).  Either way only the eigenvalues and ONE linear functional of the eigenvectors are
+// needed; both come from a parallel (round-robin) two-sided Jacobi iteration in the warp's T region.
+// the kept/dropped decision sits at rounding level for eigenvalues near eps*k*l_max, so the reference
+// itself is not reproducible there; parity for GCV is statistical (DESIGN.md "Parity").
+template <int NS>
+__device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int N, bool mk_form, double xs_scale, int k_sel,
+                                               int lane) {
+    // matrix A: N x N row-major with stride LD at S[W.T ..]; functional e at S[W.rs ..]; (c, s) of a round at S[W.gs ..]
+    const int oA = W.T;
+    const int LD = N | 1;
+    const int Ne = N + (N & 1);
+    const int half = Ne >> 1;
+    // entries below 1e-22 of the largest diagonal entry cannot influence an eigenvalue near the eps*k*l_max cut-off
+    double dmax = 0.0;
+    for (int i = lane; i < N; i += 32) dmax = fmax(dmax, fabs(S[oA + i * LD + i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL_MASK, dmax, o));
+    const double floor_abs = 1e-22 * dmax;
+    for (int sweep = 0; sweep < 14; ++sweep) {
+        double off = 0.0;
+        for (int round = 0; round < Ne - 1; ++round) {
+            // ---- rotation of pair `lane` of this round (circle method)
+            int pp = -1, qq = -1;
+            if (lane < half) {
+                if (lane == 0) {
+                    pp = round;
+                    qq = Ne - 1;
+                } else {
+                    pp = round + lane;
+                    if (pp >= Ne - 1) pp -= Ne - 1;
+                    qq = round - lane + (Ne - 1);
+                    if (qq >= Ne - 1) qq -= Ne - 1;
+                }
+                if (pp > qq) {
+                    int tmp = pp;
+                    pp = qq;
+                    qq = tmp;
+                }
+                if (qq >= N) pp = qq = -1;
+            }
+            double c = 1.0, s = 0.0;
+            if (pp >= 0) {
+                const double apq = S[oA + pp * LD + qq];
+                const double app = S[oA + pp * LD + pp], aqq = S[oA + qq * LD + qq];
+                if (fabs(apq) > 1.1e-16 * sqrt(fabs(app * aqq)) && fabs(apq) > floor_abs) {   // relative criterion
+                    off += apq * apq;
+                    const double zeta = (aqq - app) / (2.0 * apq);
+                    const double tt = ((zeta >= 0.0) ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                    c = 1.0 / sqrt(1.0 + tt * tt);
+                    s = tt * c;
+                }
+                // the functional transforms like a row of V: e_p' = c e_p - s e_q, e_q' = s e_p + c e_q
+                const double ep = S[W.rs + pp], eq = S[W.rs + qq];
+                S[W.rs + pp] = c * ep - s * eq;
+                S[W.rs + qq] = s * ep + c * eq;
+            }
+            if (lane < half) {
+                S[W.gs + lane] = c;
+                S[W.gs + 32 + lane] = s;
+            }
+            __syncwarp();
+            // ---- columns: A <- A J   (lane = row r; rows 32.. handled by a second slot)
+            for (int i = 0; i < half; ++i) {
+                int p2, q2;
+                if (i == 0) {
+                    p2 = round;
+                    q2 = Ne - 1;
+                } else {
+                    p2 = round + i;
+                    if (p2 >= Ne - 1) p2 -= Ne - 1;
+                    q2 = round - i + (Ne - 1);
+                    if (q2 >= Ne - 1) q2 -= Ne - 1;
+                }
+                if (p2 > q2) {
+                    int tmp = p2;
+                    p2 = q2;
+                    q2 = tmp;
+                }
+                if (q2 >= N) continue;
+                const double ci = S[W.gs + i], si = S[W.gs + 32 + i];
+                for (int r = lane; r < N; r += 32) {
+                    const double xv = S[oA + r * LD + p2], yv = S[oA + r * LD + q2];
+                    S[oA + r * LD + p2] = ci * xv - si * yv;
+                    S[oA + r * LD + q2] = si * xv + ci * yv;
+                }
+            }
+            __syncwarp();
+            // ---- rows: A <- J^T A   (lane = column)
+            for (int i = 0; i < half; ++i) {
+                int p2, q2;
+                if (i == 0) {
+                    p2 = round;
+                    q2 = Ne - 1;
+                } else {
+                    p2 = round + i;
+                    if (p2 >= Ne - 1) p2 -= Ne - 1;
+                    q2 = round - i + (Ne - 1);
+                    if (q2 >= Ne - 1) q2 -= Ne - 1;
+                }
+                if (p2 > q2) {
+                    int tmp = p2;
+                    p2 = q2;
+                    q2 = tmp;
+                }
+                if (q2 >= N) continue;
+                const double ci = S[W.gs + i], si = S[W.gs + 32 + i];
+                for (int cc = lane; cc < N; cc += 32) {
+                    const double xv = S[oA + p2 * LD + cc], yv = S[oA + q2 * LD + cc];
+                    S[oA + p2 * LD + cc] = ci * xv - si * yv;
+                    S[oA + q2 * LD + cc] = si * xv + ci * yv;
+                }
+            }
+            __syncwarp();
+        }
+        off = warp_sum(off);
+        if (off == 0.0) break;
+    }
+    // eigenvalues on the diagonal; truncated-pseudo-inverse trace
+    double lmax = 0.0;
+    for (int i = lane; i < N; i += 32) lmax = fmax(lmax, S[oA + i * LD + i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(FULL_MASK, lmax, o));
+    const double tau = 2.220446049250313e-16 * (double)k_sel * lmax;
+    double tr = 0.0;
+    for (int i = lane; i < N; i += 32) {
+        const double li = S[oA + i * LD + i];
+        if (li > tau) {
+            const double ei = S[W.rs + i];
+            tr += mk_form ? (1.0 - xs_scale * ei * ei / li) : (1.0 - ei * ei);
+        }
+    }
+    return warp_sum(tr);
+}
+
+template <int NS>
+__device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, int oLb, const double* __restrict__ Dt,
+                                           int n, int m, int lane, double x, double sse, double nrm, int p) {
+    // sel = positions with a strictly positive coefficient, compacted into S[W.gs + 64-free]... kept in registers:
+    // position list is W.ix[0..p); after a converged solve every coefficient is > 0, after an itmax stop some may be 0
+    int k = 0;
+    double sdiag = 0.0;
+    for (int i = 0; i < p; ++i) {
+        if (S[W.xs + i] > 0.0) {
+            const int cidx = SI(W.ix, i);
+            const double lii = S[oLb + 2 * n + cidx];
+            sdiag = fma(lii, lii, sdiag);
+            ++k;
+        }
+    }
+    const double xs = x * sdiag;
+    const int oA = W.T;
+    double tr;
+    __syncwarp();
+    if (k <= m + 1) {
+        // Mk = G[sel, sel] + x s  (k x k)
+        const int N = k, LD = N | 1;
+        int a = 0;
+        for (int i = 0; i < p; ++i) {
+            if (!(S[W.xs + i] > 0.0)) continue;
+            const int ci = SI(W.ix, i);
+            int b = 0;
+            for (int j = 0; j < p; ++j) {
+                if (!(S[W.xs + j] > 0.0)) continue;
+                if ((b & 31) == lane) S[oA + a * LD + b] = S[oG + ci * ldg + SI(W.ix, j)] + xs;
+                ++b;
+            }
+            if (lane == 0) S[W.rs + a] = 1.0;
+            ++a;
+        }
+        __syncwarp();
+        tr = jacobi_trace<NS>(W, N, true, xs, k, lane);
+    } else {
+        // W = Er Er^T, Er = [Dr; sqrt(x s) 1^T]   ((m+1) x (m+1)); lane a owns row a (lane 0 also the last row)
+        const int N = m + 1, LD = N | 1;
+        for (int i = lane; i < N * LD; i += 32) S[oA + i] = 0.0;
+        __syncwarp();
+        const double rt = sqrt(xs);
+        for (int i = 0; i < p; ++i) {
+            if (!(S[W.xs + i] > 0.0)) continue;
+            const double* drow = Dt + SI(W.ix, i) * m;
+            for (int a = lane; a < m; a += 32) S[W.gs + a] = __ldg(drow + a);
+            __syncwarp();
+            for (int a = lane; a < m; a += 32) {
+                const double da = S[W.gs + a];
+                for (int b = 0; b < m; ++b) S[oA + a * LD + b] = fma(da, S[W.gs + b], S[oA + a * LD + b]);
+                S[oA + a * LD + m] = fma(rt, da, S[oA + a * LD + m]);
+            }
+            __syncwarp();
+        }
+        for (int a = lane; a < m; a += 32) S[oA + m * LD + a] = S[oA + a * LD + m];
+        if (lane == 0) S[oA + m * LD + m] = xs * (double)k;
+        for (int a = lane; a < N; a += 32) S[W.rs + a] = (a == m) ? 1.0 : 0.0;
+        __syncwarp();
+        tr = jacobi_trace<NS>(W, N, false, xs, k, lane);
+    }
+    const double dm = (double)m;
+    const double num = (1.0 / dm) * (sse + x * nrm);
+    const double den = (1.0 / dm) * (dm - tr);
+    return log(num / (den * den));
+}
+
 // ---------------------------------------------------------------------------------------------- fit kernel
 // shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
 // then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64]
@@ -287,8 +495,15 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     stage = ST_FINAL; reg = false;
                 } else if (method == MET2_REG_T2SPARC) {
                     stage = ST_FINAL; reg = true; lam = A.cfg.lambda_fixed;
-                } else if (method == MET2_REG_X2 || (method == MET2_REG_BAYESREG)) {
+                } else if (method == MET2_REG_X2 || method == MET2_REG_BAYESREG) {
                     stage = ST_PLAIN0; reg = false;
+                } else if (method == MET2_REG_GCV) {
+                    stage = ST_SEARCH; reg = true;
+                    lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
+                    if (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL) {   // objective-level parity hook: one solve at lambda_fixed
+                        stage = ST_FINAL;
+                        lam = A.cfg.lambda_fixed;
+                    }
                 } else {   // MET2_REG_LCURVE
                     stage = ST_SEARCH; reg = true; lam = S[oLam];
                 }
@@ -302,13 +517,26 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                                             warm ? p : 0);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                     if (stage == ST_FINAL) {
+                        if (method == MET2_REG_GCV && (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL)) {
+                            const double nrm = reg_norm2<NS>(W, oLb, n, lane);
+                            regv = gcv_cost<NS>(W, oG, ldg, oLb, Dt, n, m, lane, lam, sse, nrm, p);
+                            (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
+                        } else
                         if (method == MET2_REG_X2 && !(A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA))
                             regv = sse / SSE;   // k_est is what the orchestrator stores (motor...:141-143)
                         else
                             regv = lam;         // NNLS -> 0
                         break;
                     }
-                    if (method == MET2_REG_BAYESREG) {
+                    if (method == MET2_REG_GCV) {
+                        // algorithms.py:276-296
+                        const double nrm = reg_norm2<NS>(W, oLb, n, lane);
+                        const double cost = gcv_cost<NS>(W, oG, ldg, oLb, Dt, n, m, lane, lam, sse, nrm, p);
+                        if (!B.feed(cost, lam)) {
+                            lam = B.xf;
+                            stage = ST_FINAL;
+                        }
+                    } else if (method == MET2_REG_BAYESREG) {
                         // bayesian_interpolation.py:84-105
                         if (stage == ST_PLAIN0) {
                             int nnz = 0;
@@ -485,5 +713,6 @@ int t2_launch_t2sparc(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_x2(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_lcurve(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_bayesreg(const T2Args& A, const T2Geom& g, cudaStream_t st);
+int t2_launch_gcv(const T2Args& A, const T2Geom& g, cudaStream_t st);
 
 }  // namespace met2

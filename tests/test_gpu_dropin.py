@@ -10,7 +10,8 @@ from multicomponent_t2_toolbox_b200 import nifti_io
 from multicomponent_t2_toolbox_b200.epg.epg import create_Dic_3D
 from multicomponent_t2_toolbox_b200.flip_angle_algorithms.fa_estimation import (
     compute_optimal_FA, fitting_slice_FA_brute_force, fitting_slice_FA_spline_method)
-from multicomponent_t2_toolbox_b200.intravoxel_algorithms.algorithms import nnls, nnls_lcurve_wrapper, nnls_tik, nnls_x2
+from multicomponent_t2_toolbox_b200.intravoxel_algorithms.algorithms import (nnls, nnls_gcv, nnls_lcurve_wrapper,
+                                                                             nnls_tik, nnls_x2)
 from multicomponent_t2_toolbox_b200.intravoxel_algorithms.bayesian_interpolation import BayesReg_nnls
 from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data import fitting_slice_T2, motor_recon_met2
 from multicomponent_t2_toolbox_b200.phantom import make_phantom
@@ -70,6 +71,8 @@ def test_per_voxel_api(golden_voxels, dics):
     fb, lb = BayesReg_nnls(D, M, L)
     fbo, lbo = O.BayesReg_nnls(D, M, L)
     assert np.allclose(fb, fbo, rtol=1e-6, atol=1e-9) and abs(lb - lbo) < 1e-6 * lbo
+    fg, lg = nnls_gcv(D, M, L)                      # GCV: statistical parity only (see test_gpu_parity)
+    assert fg.shape == (60,) and 1e-8 <= lg <= 10.0 and (fg >= 0).all()
     idx, alpha, km, sse, fsol = compute_optimal_FA(g["sig"][0], dics["d91"], dics["a91"])
     io, ao, kmo, sseo, fo = O.compute_optimal_FA(g["sig"][0], dics["d91"], dics["a91"])
     assert idx == io and alpha == ao and abs(km - kmo) < 1e-6 * kmo and abs(sse - sseo) < 1e-6 * sseo
