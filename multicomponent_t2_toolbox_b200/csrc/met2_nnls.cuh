@@ -224,6 +224,18 @@ __device__ __forceinline__ void tmul(int oT, int oV, int p, int lane, double (&o
     for (int t = 0; t < NS; ++t) out[t] = a0[t] + a1[t];
 }
 
+// 1/sqrt(d) from the single-precision hardware estimate plus two Newton steps in double (relative error ~1e-16); the
+// library rsqrt() costs ~3x the instructions and sits on the serial pivot chain of every factorisation step.
+__device__ __forceinline__ double rsqrt_fast(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return rsqrt(d);
+    double r = (double)rsqrtf((float)d);
+    double e = fma(-d * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    e = fma(-d * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    return r;
+}
+
 // FP64 tensor-core MMA m8n8k4 (DMMA.8x8x4 on sm_100a): D(8x8) += A(8x4) B(4x8).  Fragments: A[lane/4][lane%4],
 // B[lane%4][lane/4], C/D[lane/4][2*(lane%4) + {0,1}] (verified on B200 by tools/dmma_probe.cu; 16 cycles issue interval,
 // 26 cycles dependent latency).
@@ -303,7 +315,7 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
         for (int k = 0; k < 8; ++k) {
             const double d = S[W.gs + k * 9];
             if (!(d > 0.0)) ok = false;
-            const double ri = rsqrt(d);
+            const double ri = rsqrt_fast(d);
             __syncwarp();
             if (lane < 8 && lane > k) S[W.gs + k * 8 + lane] *= ri;   // row k of R
             if (lane == k) S[W.gs + k * 9] = ri;                      // keep 1/R_kk on the diagonal
@@ -558,7 +570,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         warp_sum2(s1, s2);
         const double rho2 = gjj - s1;
         const double cj = S[W.cc + j];
-        const double rinv = rsqrt(rho2);
+        const double rinv = rsqrt_fast(rho2);
         const double ynew = (cj - s2) * rinv;
         // nnls.f: reject if the column is numerically dependent on P (unorm + |a_new|*0.01 == unorm, i.e.
         // rho < ~1e-14 unorm) or if its new coefficient ("ztest") is not positive

@@ -568,6 +568,22 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                             lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
                             reg = true;
                             stage = ST_SEARCH;
+                            if (warm && lam >= 1.0) {
+                                // Brent's first abscissa is large (3.82 on [0, 10]): nearly every column ends up
+                                // active, so start from the FULL set with the feasible point x_j = c_j / (G + lam K)_jj
+                                // and let the secondary loop drop the few that do not belong, instead of ~55 appends.
+#pragma unroll
+                                for (int tt = 0; tt < NS; ++tt) {
+                                    const int j = lane + 32 * tt;
+                                    if (j < n) {
+                                        const double djj = fma(lam, S[oKb + 2 * n + j], S[oG + j * ldg + j]);
+                                        SI(W.ix, j) = j;
+                                        S[W.xs + j] = fmax(S[W.cc + j] / djj, 1e-300);
+                                    }
+                                }
+                                __syncwarp();
+                                p = n;
+                            }
                         } else {
                             const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
                             if (!B.feed(cost, lam)) {
