@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(FA_SEARCH_WARPS * 32, 1) fa_search_kernel(FaAr
             }
         }
         __syncthreads();
-        for (long long v = v0 + warp; v < v1; v += FA_SEARCH_WARPS) {
+        for (long long v = v0 + warp; v < v1; v += (blockDim.x >> 5)) {
             unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             if (st) continue;
             compute_c_sh<NS>(W, oD, oM, m, n, lane);
@@ -299,8 +299,9 @@ struct FaGeom {
     int grid;          // select kernel
     size_t smem;
     int pmax;
-    int grid_search;   // search kernel: one CTA of FA_SEARCH_WARPS warps per SM, tables staged in shared memory
+    int grid_search;   // search kernel: one CTA of up to FA_SEARCH_WARPS warps per SM, tables staged in shared memory
     size_t smem_search;
+    int warps_search;
 };
 
 template <int NS>
@@ -315,8 +316,16 @@ static FaGeom fa_geometry(const met2_fa_cfg* cfg) {
     if (sms <= 0) sms = 148;
     g.grid = sms * per_sm;
     g.grid_search = sms;
-    g.smem_search = sizeof(double) * ((size_t)fa_table_doubles(cfg->nT2, cfg->nTE) +
-                                      (size_t)fa_warp_doubles<NS>(g.pmax) * FA_SEARCH_WARPS);
+    {
+        const size_t tables = sizeof(double) * (size_t)fa_table_doubles(cfg->nT2, cfg->nTE);
+        const size_t per_warp = sizeof(double) * (size_t)fa_warp_doubles<NS>(g.pmax);
+        const size_t budget = 227 * 1024 - 1024;
+        int w = tables < budget ? (int)((budget - tables) / per_warp) : 0;
+        if (w > FA_SEARCH_WARPS) w = FA_SEARCH_WARPS;
+        if (w < 1) w = 1;
+        g.warps_search = w;
+        g.smem_search = tables + per_warp * w;
+    }
     return g;
 }
 
@@ -335,7 +344,7 @@ static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_search attr: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(fa_select_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_select attr: %s", cudaGetErrorString(e));
-    fa_search_kernel<NS, ME><<<g.grid_search, FA_SEARCH_WARPS * 32, g.smem_search, st>>>(A);
+    fa_search_kernel<NS, ME><<<g.grid_search, g.warps_search * 32, g.smem_search, st>>>(A);
     count_launch();
     int rc = check_launch("fa_search_kernel");
     if (rc) return rc;
