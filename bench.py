@@ -293,7 +293,8 @@ def run_ours(args):
                 "gpu_launches": launches,
                 "roofline": {"bound": "fp64", "kernel": "t2_fit_kernel", "achieved": achieved_tf,
                              "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s", "frac": achieved_tf / FP64_PEAK_TFLOPS,
-                             "traffic": None,
+                             "traffic": _ncu_traffic() if shape == SHAPE else None,
+                             "algorithmic_bytes": HBM_BYTES_PER_VOXEL * V,
                              "note": "FP64 DFMA-issue bound, not HBM/tensor (SURVEY.md 8d); achieved = algorithmic "
                                      "(reference-formulation) flops/voxel x voxels / kernel time; peak = own DFMA "
                                      "microbench (MEASURED_PEAKS.json has no FP64 entry)",
@@ -312,6 +313,16 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one t2_fit_kernel launch on this workload, from the committed
+    ncu capture (profiles/r01_t2_fit_v7_fullsize_counters.json); None if the record is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v7_fullsize_counters.json")) as fh:
+            return json.load(fh)["traffic_bytes"]
+    except Exception:
+        return None
 
 
 def _hbm_peak():
