@@ -173,6 +173,8 @@ class Met2Plan:
             cfg.brent_lo, cfg.brent_hi, cfg.maxfun = 1e-8, 2.0, 200
             with np.errstate(divide="ignore"):
                 cfg.log_det_L = float(np.log(np.linalg.det(self.Laplac)))
+        if method == "X2" and np.array_equal(self.Laplac, np.eye(self.npc)):
+            cfg.flags |= 16   # MET2_T2_FLAG_FULL_START
         for k, v in overrides.items():   # e.g. factor=..., lambda_fixed=..., maxfun=...
             setattr(cfg, k, v)
         return cfg

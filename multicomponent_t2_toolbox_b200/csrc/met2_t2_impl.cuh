@@ -102,69 +102,61 @@ __device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int 
 // column space (S[W.xc..]):  A = beta*B + (beta*x)*K, U = chol(A) (upper), and
 //   cost = beta*ED + beta*x*EW + log(prod diag U) - (n/2) log(pi/2) - sum log(1 + erf(U f / sqrt 2))
 //        + (m/2) log(2 pi) - (m/2) log(beta) + (n/2) log(pi) - (n/2) log(2 beta x) - log(det L).
-// The n x n factor is built in place in the warp's T region (packed upper triangle, free between NNLS solves) by a
-// right-looking Cholesky: row k is scaled, then every lane updates the trailing part of the columns it owns.
+// The n x n INVERSE factor T = U^-1 is built in the warp's T region (free between NNLS solves) by the same blocked
+// FP64-tensor-core factorisation that warm starts use (rebuild_T_blocked); log det U = -sum log T_kk and
+// U f = T^T (A f), so U itself is never needed.
 template <int NS>
 __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg, int oKb, int n, int m, int lane,
                                              double x, double beta, double sse, double nrm, double log_det_L,
-                                             unsigned& st) {
+                                             unsigned& st, int p) {
     const int oT = W.T;
     const double bx = beta * x;
-    // A[j][i], j <= i, packed column-major at oT + tri(i) + j
-#pragma unroll
-    for (int t = 0; t < NS; ++t) {
-        const int i = lane + 32 * t;
-        if (i < n) {
-            const int ti = oT + tri(i);
-            for (int j = 0; j <= i; ++j) {
-                double a = beta * S[oG + j * ldg + i];
-                const int d = j - i + 2;   // K[j][i] = kband[d][i], d = j - i + 2 in 0..4
-                if (d >= 0) a = a + bx * S[oKb + d * n + i];
-                S[ti + j] = a;
-            }
-        }
-    }
-    __syncwarp();
-    bool notpd = false;
-    for (int k = 0; k < n; ++k) {
-        const int tk = oT + tri(k);
-        const double akk = S[tk + k];
-        if (!(akk > 0.0)) notpd = true;
-        const double dk = sqrt(akk);
-        const double dinv = 1.0 / dk;
-        double uk[NS];
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < NS; ++t) {
-            const int i = lane + 32 * t;
-            uk[t] = 0.0;
-            if (i > k && i < n) {
-                uk[t] = S[oT + tri(i) + k] * dinv;
-                S[oT + tri(i) + k] = uk[t];
-            } else if (i == k) {
-                S[tk + k] = dk;
-            }
-        }
-        __syncwarp();
-        for (int j = k + 1; j < n; ++j) {
-            const double ukj = S[oT + tri(j) + k];
-#pragma unroll
-            for (int t = 0; t < NS; ++t) {
-                const int i = lane + 32 * t;
-                if (i >= j && i < n) {
-                    const int a = oT + tri(i) + j;
-                    S[a] = fma(-ukj, uk[t], S[a]);
-                }
-            }
-        }
-        __syncwarp();
-    }
-    if (notpd) st |= MET2_ST_NOT_PD;
-    // det_U = prod(diag(U)) (np.prod order), U f (rows), series
+    // T = U^-1 with A = beta*B + (beta*x)*K = U^T U, all n columns in natural order, by the blocked DMMA factorisation
+    auto Aent = [&](int r, int c) -> double {
+        double a = beta * S[oG + r * ldg + c];
+        const int d = r - c + 2;   // K[r][c] = kband[d][c]
+        if (d >= 0 && d <= 4) a = a + bx * S[oKb + d * n + c];
+        return a;
+    };
+    const bool pd = rebuild_T_blocked<NS>(W, Aent, n, lane);
+    if (!pd) st |= MET2_ST_NOT_PD;
+    // det_U = prod(diag(U)) = prod 1 / T_kk  (np.prod order)
     double det_u = 1.0;
-    for (int k = 0; k < n; ++k) det_u *= S[oT + tri(k) + k];
+    for (int k = 0; k < n; ++k) det_u *= 1.0 / S[oT + tri(k) + k];
+    // U f = U^-T (U^T U f) = T^T (A f);  v = A f in column space, f = S[W.xc ..] (support W.ix / W.xs, size p)
+    {
+        const int col0 = NS * lane;
+        double v[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) v[s] = 0.0;
+        if (col0 < n) {
+            for (int k = 0; k < p; ++k) {
+                const int r0 = oG + SI(W.ix, k) * ldg + col0;
+                const double xk = S[W.xs + k];
+                double g0[NS];
+                lds_vec<NS>(r0, g0);
+#pragma unroll
+                for (int s = 0; s < NS; ++s) v[s] = fma(xk, g0[s], v[s]);
+            }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int col = col0 + s;
+            if (col < n) {
+                double kf = 0.0;
+#pragma unroll
+                for (int d = 0; d < 5; ++d) {
+                    const int c2 = col + d - 2;
+                    if (c2 >= 0 && c2 < n) kf = fma(S[oKb + d * n + col], S[W.xc + c2], kf);
+                }
+                S[W.gs + col] = beta * v[s] + bx * kf;
+            }
+        }
+        __syncwarp();
+    }
     double uf[NS];
-    tmul<NS>(oT, W.xc, n, lane, uf);
+    tmul_transposed<NS>(oT, W.gs, n, lane, uf);
     double series = 0.0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
@@ -177,7 +169,7 @@ __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg
     const double hn = n / 2.0, hm = m / 2.0;
     const double cost1 = beta * ED + beta * x * EW + log(det_u) - hn * log(PI / 2.0) - series;
     const double cost2 = hm * log(2.0 * PI) - hm * log(beta) + hn * log(PI) - hn * log(2.0 * beta * x) - log_det_L;
-    return notpd ? INFINITY : (cost1 + cost2);
+    return pd ? (cost1 + cost2) : INFINITY;
 }
 
 // ---------------------------------------------------------------------------------------------- GCV objective
@@ -511,6 +503,24 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 double beta = 0.0;
                 const bool warm = !(A.cfg.flags & MET2_T2_FLAG_COLD_START);
                 p = 0;
+                // X2 with L = I: Brent's first abscissa (3.82 on [0, 10]) gives a solution with nearly every column
+                // active, so that solve starts from the FULL set with the feasible point x_j = c_j / (G + lam K)_jj and
+                // lets the secondary loop drop the few columns that do not belong, instead of ~55 single-column appends.
+                // (Host sets MET2_T2_FLAG_FULL_START only for the identity matrix: with InvT2 the long-T2 columns are
+                // barely penalised and most of them leave again — measured 2x slower for T2SPARC.)
+                auto full_set_start = [&](double lam0) {
+#pragma unroll
+                    for (int tt = 0; tt < NS; ++tt) {
+                        const int j = lane + 32 * tt;
+                        if (j < n) {
+                            const double djj = fma(lam0, S[oKb + 2 * n + j], S[oG + j * ldg + j]);
+                            SI(W.ix, j) = j;
+                            S[W.xs + j] = fmax(S[W.cc + j] / djj, 1e-300);
+                        }
+                    }
+                    __syncwarp();
+                    p = n;
+                };
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
@@ -555,7 +565,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                         } else {
                             const double nrm = reg_norm2<NS>(W, oLb, n, lane);
                             const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
-                                                               A.cfg.log_det_L, st);
+                                                               A.cfg.log_det_L, st, p);
                             if (!B.feed(cost, lam)) {
                                 lam = B.xf;
                                 stage = ST_FINAL;
@@ -568,22 +578,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                             lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
                             reg = true;
                             stage = ST_SEARCH;
-                            if (warm && lam >= 1.0) {
-                                // Brent's first abscissa is large (3.82 on [0, 10]): nearly every column ends up
-                                // active, so start from the FULL set with the feasible point x_j = c_j / (G + lam K)_jj
-                                // and let the secondary loop drop the few that do not belong, instead of ~55 appends.
-#pragma unroll
-                                for (int tt = 0; tt < NS; ++tt) {
-                                    const int j = lane + 32 * tt;
-                                    if (j < n) {
-                                        const double djj = fma(lam, S[oKb + 2 * n + j], S[oG + j * ldg + j]);
-                                        SI(W.ix, j) = j;
-                                        S[W.xs + j] = fmax(S[W.cc + j] / djj, 1e-300);
-                                    }
-                                }
-                                __syncwarp();
-                                p = n;
-                            }
+                            if (warm && (A.cfg.flags & MET2_T2_FLAG_FULL_START) && lam >= 1.0) full_set_start(lam);
                         } else {
                             const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
                             if (!B.feed(cost, lam)) {
