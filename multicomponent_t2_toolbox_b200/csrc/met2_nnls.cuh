@@ -137,8 +137,9 @@ __device__ __forceinline__ void ldg_vec(const double* __restrict__ p, bool vec, 
 }
 
 // out[t] (position i = lane + 32 t) = sum_{k <= i, k < p} T(k, i) * v[k]   — column dot products, T^T v.
-// Segment `seg` of k (32 wide) only touches slots t >= seg; two accumulators per slot for ILP; the triangle
-// predicate is a single compare against kmax[t] (= i for live positions, -1 otherwise) so it compiles to predication.
+// Two accumulators per slot for ILP; the triangle predicate is a single compare against kmax[t] (= i for live
+// positions, -1 otherwise) so it compiles to predication.  Kept deliberately compact: this kernel is bound by
+// instruction fetch (6 KB L0 / 32 KB L1.5 instruction caches), smaller code measured faster than more unrolling.
 template <int NS>
 __device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane, double (&out)[NS]) {
     double a0[NS], a1[NS];
@@ -150,31 +151,26 @@ __device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane,
         base[t] = oT + tri(i);
         kmax[t] = (i < p) ? i : -1;
     }
+    int k = 0;
+#pragma unroll 1
+    for (; k + 1 < p; k += 2) {
+        const double v0 = S[oV + k], v1 = S[oV + k + 1];
 #pragma unroll
-    for (int seg = 0; seg < NS; ++seg) {
-        const int k0 = 32 * seg;
-        if (k0 < p) {
-            const int k1 = (p < k0 + 32) ? p : k0 + 32;
-            int k = k0;
-#pragma unroll 2
-            for (; k + 1 < k1; k += 2) {
-                const double v0 = S[oV + k], v1 = S[oV + k + 1];
-#pragma unroll
-                for (int t = seg; t < NS; ++t) {
-                    const double t0 = (k <= kmax[t]) ? S[base[t] + k] : 0.0;
-                    const double t1 = (k + 1 <= kmax[t]) ? S[base[t] + k + 1] : 0.0;
-                    a0[t] = fma(t0, v0, a0[t]);
-                    a1[t] = fma(t1, v1, a1[t]);
-                }
+        for (int t = 0; t < NS; ++t) {
+            if (32 * t + 31 >= k) {   // uniform: slot t only holds positions <= 32 t + 31
+                const double t0 = (k <= kmax[t]) ? S[base[t] + k] : 0.0;
+                const double t1 = (k + 1 <= kmax[t]) ? S[base[t] + k + 1] : 0.0;
+                a0[t] = fma(t0, v0, a0[t]);
+                a1[t] = fma(t1, v1, a1[t]);
             }
-            if (k < k1) {
-                const double v0 = S[oV + k];
+        }
+    }
+    if (k < p) {
+        const double v0 = S[oV + k];
 #pragma unroll
-                for (int t = seg; t < NS; ++t) {
-                    const double t0 = (k <= kmax[t]) ? S[base[t] + k] : 0.0;
-                    a0[t] = fma(t0, v0, a0[t]);
-                }
-            }
+        for (int t = 0; t < NS; ++t) {
+            const double t0 = (k <= kmax[t]) ? S[base[t] + k] : 0.0;
+            a0[t] = fma(t0, v0, a0[t]);
         }
     }
 #pragma unroll
@@ -182,42 +178,36 @@ __device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane,
 }
 
 // out[t] (position k = lane + 32 t) = sum_{i >= k, i < p} T(k, i) * v[i]   — row dot products, T v.
-// Segment `seg` of i only touches slots t <= seg.
 template <int NS>
 __device__ __forceinline__ void tmul(int oT, int oV, int p, int lane, double (&out)[NS]) {
     double a0[NS], a1[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) a0[t] = a1[t] = 0.0;
+    int i = 0;
+    int t0 = oT;
+#pragma unroll 1
+    for (; i + 1 < p; i += 2) {
+        const double v0 = S[oV + i], v1 = S[oV + i + 1];
+        const int t1 = t0 + i + 1;
 #pragma unroll
-    for (int seg = 0; seg < NS; ++seg) {
-        const int i0 = 32 * seg;
-        if (i0 < p) {
-            const int i1 = (p < i0 + 32) ? p : i0 + 32;
-            int i = i0;
-            int t0 = oT + tri(i);
-#pragma unroll 2
-            for (; i + 1 < i1; i += 2) {
-                const double v0 = S[oV + i], v1 = S[oV + i + 1];
-                const int t1 = t0 + i + 1;
-#pragma unroll
-                for (int t = 0; t <= seg; ++t) {
-                    const int k = lane + 32 * t;
-                    const double e0 = (k <= i) ? S[t0 + k] : 0.0;
-                    const double e1 = (k <= i + 1) ? S[t1 + k] : 0.0;
-                    a0[t] = fma(e0, v0, a0[t]);
-                    a1[t] = fma(e1, v1, a1[t]);
-                }
-                t0 = t1 + i + 2;
+        for (int t = 0; t < NS; ++t) {
+            if (32 * t <= i + 1) {   // uniform: slot t only holds rows >= 32 t
+                const int k = lane + 32 * t;
+                const double e0 = (k <= i) ? S[t0 + k] : 0.0;
+                const double e1 = (k <= i + 1) ? S[t1 + k] : 0.0;
+                a0[t] = fma(e0, v0, a0[t]);
+                a1[t] = fma(e1, v1, a1[t]);
             }
-            if (i < i1) {
-                const double v0 = S[oV + i];
+        }
+        t0 = t1 + i + 2;
+    }
+    if (i < p) {
+        const double v0 = S[oV + i];
 #pragma unroll
-                for (int t = 0; t <= seg; ++t) {
-                    const int k = lane + 32 * t;
-                    const double e0 = (k <= i) ? S[t0 + k] : 0.0;
-                    a0[t] = fma(e0, v0, a0[t]);
-                }
-            }
+        for (int t = 0; t < NS; ++t) {
+            const int k = lane + 32 * t;
+            const double e0 = (k <= i) ? S[t0 + k] : 0.0;
+            a0[t] = fma(e0, v0, a0[t]);
         }
     }
 #pragma unroll
@@ -282,7 +272,7 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
                 const int ii = 8 * it + g;
                 const int coli = oT + tri(ii);
                 double d0 = 0.0, d1 = 0.0;
-#pragma unroll 2
+#pragma unroll 1
                 for (int ks = 0; ks < 2 * it + 2; ++ks) {
                     const int kk = 4 * ks + q;
                     const double af = (kk <= ii) ? S[coli + kk] : 0.0;
@@ -302,7 +292,7 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
             s0 = (r < p && ca < p) ? Aent(r, ca) : ((r == ca) ? 1.0 : 0.0);
             s1 = (r < p && cb < p) ? Aent(r, cb) : ((r == cb) ? 1.0 : 0.0);
         }
-#pragma unroll 2
+#pragma unroll 1
         for (int is = 0; is < 2 * b; ++is) {
             const double v = jlive ? S[colg + 4 * is + q] : 0.0;
             dmma884(s0, s1, -v, v);
@@ -356,7 +346,7 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
             for (int kt = 0; kt < b; ++kt) {
                 const int kk = 8 * kt + g;
                 double d0 = 0.0, d1 = 0.0;
-#pragma unroll 2
+#pragma unroll 1
                 for (int is = 2 * kt; is < 2 * b; ++is) {
                     const int i2 = 4 * is + q;
                     const double af = (kk <= i2) ? S[oT + tri(i2) + kk] : 0.0;

@@ -4,6 +4,7 @@
 // otherwise: "no_instruction" becomes the top stall).
 #pragma once
 #include <cmath>
+#include <cstdlib>
 
 #include "met2_device.cuh"
 #include "met2_host.h"
@@ -678,6 +679,10 @@ static inline T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
     int warps = (int)((budget - tables) / per_warp);
     if (warps > T2_MAX_THREADS / 32) warps = T2_MAX_THREADS / 32;
     if (warps < 1) warps = 1;
+    if (const char* ev = getenv("MET2_T2_WARPS")) {   // tuning/diagnostic override (never raises the limit)
+        int w = atoi(ev);
+        if (w >= 1 && w < warps) warps = w;
+    }
     g.warps = warps;
     g.smem = tables + per_warp * warps;
     int per_sm = (int)(budget / (g.smem + 1024));
