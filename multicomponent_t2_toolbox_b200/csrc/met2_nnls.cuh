@@ -461,6 +461,7 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
         int rr = lane + 32 * t;
         carry[t] = (rr < k) ? S[oT + tri(k) + rr] : 0.0;
     }
+#pragma unroll 1
     for (int q = k; q + 1 < p; ++q) {
         const double c = S[W.gs + q], s = S[W.rs + q];
         const int tq1 = oT + tri(q + 1), tq = oT + tri(q);
@@ -605,6 +606,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         const bool good = rebuild_T_blocked<NS>(W, Aent, p0, lane);
         if (good) {
             p = p0;
+#pragma unroll 1
             for (int i = 0; i < p; ++i) {
                 const int col = SI(W.ix, i);
                 if (col / NS == lane) inP |= 1u << (col % NS);
@@ -636,6 +638,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             if (GSH) {
                 // rows of G in shared memory: one vector LDS per row and lane (columns NS*lane .. NS*lane+NS-1)
                 const bool live = col0 < n;
+#pragma unroll 1
                 for (; k + 1 < p; k += 2) {
                     const int r0 = oG + SI(W.ix, k) * ldg + col0, r1 = oG + SI(W.ix, k + 1) * ldg + col0;
                     const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
@@ -663,6 +666,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             } else {
                 const bool vec = ((ldg & 1) == 0);
                 const int nvalid = n - col0;   // columns this lane really owns (<= 0: none)
+#pragma unroll 1
                 for (; k + 1 < p; k += 2) {
                     const double* g0 = Gg + SI(W.ix, k) * ldg + col0;
                     const double* g1 = Gg + SI(W.ix, k + 1) * ldg + col0;
