@@ -137,6 +137,12 @@ int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met
                 const uint8_t* comp, double* fsol, double* est_signal, double* reg, double* maps, uint32_t* status,
                 void* workspace, void* stream);
 
+/* FA-stage preprocessing: replaces `filt.gaussian_filter(data[:, :, :, c], 2.0, 0)` per echo (motor...:336-346;
+ * scipy.ndimage semantics: mode 'reflect', symmetric kernel `weights[2*radius+1]`, radius = int(4 sigma + 0.5)).
+ * vol/out/tmp are [nx][ny][nz][nt] C-order device arrays; out and tmp must not alias vol. */
+int met2_gaussian_smooth(const double* vol, int nx, int ny, int nz, int nt, const double* weights, int radius,
+                         double* out, double* tmp, void* stream);
+
 /* Diagnostics */
 const char* met2_last_error(void);
 int met2_version(void);

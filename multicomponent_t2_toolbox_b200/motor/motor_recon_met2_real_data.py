@@ -3,14 +3,14 @@
 `motor_recon_met2` keeps the reference's signature and NIfTI outputs (motor/motor_recon_met2_real_data.py:165-506) but
 replaces the two joblib voxel loops (Steps 2 and 3, :349-373 and :428-441) and the Python metrics loop (Step 4,
 :443-472) by one gather -> batched GPU fit -> scatter (pipeline.recon_arrays).  Host-side preprocessing that is not on
-the accelerated path: Gaussian smoothing for the FA stage uses scipy.ndimage like the reference (:336-346); the TV and
-NESMA denoisers (:293-334) and the mean-spectrum PNG (:379-424) are out of scope.
+the accelerated path: the TV and NESMA denoisers (:293-334) and the mean-spectrum PNG (:379-424) are out of scope
+(SURVEY.md §2, §8f); the Gaussian smoothing for the FA stage (:336-346) runs on the GPU (met2_gaussian_smooth).
 """
 import os
 
 import numpy as np
 
-from .. import nifti_io, pipeline
+from .. import batched, nifti_io, pipeline
 from ..reference_api import create_Laplacian_matrix, fitting_slice_T2  # noqa: F401
 
 OUTPUTS = ("MWF", "IEWF", "FWF", "T2_M", "T2_IE", "TWC", "FA", "fsol_4D", "Est_Signal", "reg_param")
@@ -39,10 +39,8 @@ def motor_recon_met2(TE_array, path_to_data, path_to_mask, path_to_save_data, TR
     print('Step #2: Estimation of flip angles:')
     data_fa = None
     if FA_smooth == 'yes':
-        from scipy.ndimage import gaussian_filter
-        data_fa = np.zeros((nx, ny, nz, nt))
-        for c in range(nt):
-            data_fa[:, :, :, c] = gaussian_filter(data[:, :, :, c], 2.0, order=0)
+        # per-echo Gaussian smoothing, sigma = 2 (motor...:336-346) — on the GPU, bitwise equal to scipy.ndimage
+        data_fa = batched.gaussian_smooth(data, sigma=2.0)
     print('Step #3: Estimation of T2 spectra:')
     vol = pipeline.recon_arrays(data, mask, np.asarray(TE_array, dtype=np.float64), TR, reg_method, reg_matrix,
                                 FA_method, myelin_T2=myelin_T2, data_fa=data_fa)

@@ -40,7 +40,12 @@ def fit_voxels(plan, sig, sig_fa=None, pinned_out=None):
     V = sig.shape[0]
     with torch.cuda.device(dev):
         d_sig = torch.as_tensor(sig).to(dev, non_blocking=True)
-        d_sig_fa = d_sig if sig_fa is None else torch.as_tensor(sig_fa).to(dev, non_blocking=True)
+        if sig_fa is None:
+            d_sig_fa = d_sig
+        elif isinstance(sig_fa, torch.Tensor):
+            d_sig_fa = sig_fa.to(dev)
+        else:
+            d_sig_fa = torch.as_tensor(sig_fa).to(dev, non_blocking=True)
         fa = plan.fa_fit(d_sig_fa)
         t2 = plan.t2_fit(d_sig, fa["fa_index"])
         out = dict(fa_index=fa["fa_index"], fa_deg=fa["fa_deg"], km=fa["km"], fsol_sum=fa["fsol_sum"],
@@ -72,11 +77,18 @@ def recon_arrays(data, mask, TE_array, TR, reg_method, reg_matrix, FA_method, my
                                 reg_matrix=reg_matrix, FA_method=FA_method, myelin_T2=myelin_T2, npc=npc,
                                 n_alphas=n_alphas, device=device)
     flat, sig = masked_voxel_list(data, mask)
+    lo, hi = slab_bounds(len(flat), rank, world_size)
     sig_fa = None
     if data_fa is not None:
-        _, sig_fa = masked_voxel_list(np.asarray(data_fa, dtype=np.float64), mask)
-    lo, hi = slab_bounds(len(flat), rank, world_size)
-    res = fit_voxels(plan, sig[lo:hi], None if sig_fa is None else sig_fa[lo:hi])
+        if isinstance(data_fa, torch.Tensor):
+            # smoothed volume already on the GPU (batched.gaussian_smooth): gather the slab's voxels there
+            idx = torch.as_tensor(flat[lo:hi]).to(data_fa.device)
+            m = torch.as_tensor(np.asarray(mask).reshape(-1)[flat[lo:hi]].astype(np.float64)).to(data_fa.device)
+            sig_fa = (data_fa.reshape(-1, nt).index_select(0, idx) * m[:, None]).clamp_min(0.0)
+        else:
+            _, sig_fa_all = masked_voxel_list(np.asarray(data_fa, dtype=np.float64), mask)
+            sig_fa = sig_fa_all[lo:hi]
+    res = fit_voxels(plan, sig[lo:hi], sig_fa)
     sel = flat[lo:hi]
     nvox = nx * ny * nz
     vol = {}

@@ -109,6 +109,26 @@ def test_motor_recon_met2_files(tmp_path):
     vol = motor_recon_met2(TE, str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"), out, 1000.0, "NNLS", "I",
                            "None", "spline", "yes", 40.0, -1)
     assert vol["FA"][ph["mask"] > 0].min() >= 90.0 and not vol["FA"][ph["mask"] == 0].any()
+    from scipy.ndimage import gaussian_filter
+    masked = ph["data"] * ph["mask"][..., None]
+    smooth = np.stack([gaussian_filter(masked[:, :, :, c], 2.0, 0) for c in range(32)], axis=-1)
+    ref_s = O.recon_volume(ph["data"], ph["mask"], TE, 1000.0, "NNLS", "I", "spline", num_cores=1, data_fa=smooth)
+    assert np.array_equal(vol["FA"], ref_s["FA"]) and np.array_equal(vol["fsol_4D"] > 0, ref_s["fsol_4D"] > 0)
     with pytest.raises(NotImplementedError):
         motor_recon_met2(TE, str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"), out, 1000.0, "NNLS", "I",
                          "TV", "spline", "no", 40.0, -1)
+
+
+def test_gaussian_smooth_bitwise_equal_to_scipy():
+    """the FA-stage smoothing (motor...:336-346) on the GPU."""
+    from scipy.ndimage import gaussian_filter
+
+    from multicomponent_t2_toolbox_b200 import batched
+    rng = np.random.default_rng(3)
+    for shape in [(13, 9, 5, 4), (20, 17, 3, 2), (6, 6, 6, 1)]:      # includes axes shorter than the radius (8)
+        data = rng.uniform(0.0, 1000.0, shape)
+        data[rng.uniform(size=shape[:3]) < 0.3] = 0.0                # masked-out voxels are zeros in the orchestrator
+        got = batched.gaussian_smooth(data, sigma=2.0).cpu().numpy()
+        for c in range(shape[3]):
+            ref = gaussian_filter(data[:, :, :, c], 2.0, 0)
+            assert np.array_equal(got[:, :, :, c], ref), (shape, c, np.abs(got[:, :, :, c] - ref).max())
