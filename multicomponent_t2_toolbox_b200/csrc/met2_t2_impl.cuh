@@ -192,12 +192,13 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int N, bool m
     const int LD = N | 1;
     const int Ne = N + (N & 1);
     const int half = Ne >> 1;
-    // entries below 1e-22 of the largest diagonal entry cannot influence an eigenvalue near the eps*k*l_max cut-off
+    // an off-diagonal entry below 1e-18 of the largest diagonal entry moves no eigenvalue by more than that, four
+    // orders of magnitude under the eps*k*l_max cut-off; without the floor the noise-level block keeps rotating
     double dmax = 0.0;
     for (int i = lane; i < N; i += 32) dmax = fmax(dmax, fabs(S[oA + i * LD + i]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL_MASK, dmax, o));
-    const double floor_abs = 1e-22 * dmax;
+    const double floor_abs = 1e-18 * dmax;
     for (int sweep = 0; sweep < 14; ++sweep) {
         double off = 0.0;
         for (int round = 0; round < Ne - 1; ++round) {
@@ -334,21 +335,19 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
     double tr;
     __syncwarp();
     if (k <= m + 1) {
-        // Mk = G[sel, sel] + x s  (k x k)
+        // Mk = G[sel, sel] + x s  (k x k); compact list of the selected columns in S[W.gs ..] (as doubles)
         const int N = k, LD = N | 1;
-        int a = 0;
-        for (int i = 0; i < p; ++i) {
-            if (!(S[W.xs + i] > 0.0)) continue;
-            const int ci = SI(W.ix, i);
-            int b = 0;
-            for (int j = 0; j < p; ++j) {
-                if (!(S[W.xs + j] > 0.0)) continue;
-                if ((b & 31) == lane) S[oA + a * LD + b] = S[oG + ci * ldg + SI(W.ix, j)] + xs;
-                ++b;
-            }
-            if (lane == 0) S[W.rs + a] = 1.0;
-            ++a;
+        if (lane == 0) {
+            int a = 0;
+            for (int i = 0; i < p; ++i)
+                if (S[W.xs + i] > 0.0) S[W.gs + (a++)] = (double)SI(W.ix, i);
         }
+        __syncwarp();
+        for (int a = 0; a < N; ++a) {
+            const int ca = (int)S[W.gs + a];
+            for (int b = lane; b < N; b += 32) S[oA + a * LD + b] = S[oG + ca * ldg + (int)S[W.gs + b]] + xs;
+        }
+        for (int a = lane; a < N; a += 32) S[W.rs + a] = 1.0;
         __syncwarp();
         tr = jacobi_trace<NS>(W, N, true, xs, k, lane);
     } else {
