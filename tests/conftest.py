@@ -25,3 +25,15 @@ def golden_voxels():
 def golden_dictionary():
     import numpy as np
     return dict(np.load(os.path.join(GOLDEN, "dictionary.npz")))
+
+
+@pytest.fixture(scope="session")
+def golden_config2():
+    """20 480 voxels of the config-2 phantom fitted by the unmodified reference (oracle/make_golden_config2.py)."""
+    import numpy as np
+    g = dict(np.load(os.path.join(GOLDEN, "config2_subset.npz")))
+    sup = np.unpackbits(g["support"], axis=1)[:, :60].astype(bool)
+    f = np.zeros(sup.shape)
+    f[sup] = g["f_nz"]
+    g["f"] = f
+    return g

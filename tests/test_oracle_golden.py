@@ -93,3 +93,21 @@ def test_nnls_known_answer(golden_voxels, dics):
     x2, rn2, mode = O.lh_nnls(D, M)
     assert mode == 1 and np.array_equal(x2 > 0, x > 0)
     assert np.allclose(x2, x, rtol=1e-8, atol=1e-12) and abs(rn2 - rn) <= 1e-10 * rn
+
+
+def test_config2_subset_slice(golden_config2, dics):
+    """The oracle port against the reference outputs on voxels of BASELINE.json configs[1] (FA spline + X2-I)."""
+    g = golden_config2
+    sl = slice(0, 20480, 160)            # 128 voxels spread over the subset
+    sig = g["sig"][sl]
+    nx = sig.shape[0]
+    ok = np.ones(nx)
+    FA, idx, KM, _ = O.fitting_slice_FA_spline_method(dics["d15"], dics["d273"], sig, ok, dics["a15"], nx, dics["a273"])
+    assert np.array_equal(idx.astype(np.int16), g["fa_idx"][sl])
+    assert np.allclose(KM, g["km"][sl], rtol=1e-12, atol=0)
+    lam = np.zeros(50)
+    lam[1:] = np.logspace(-8, 1, 49)
+    f, s, reg = O.fitting_slice_T2(ok, sig, idx, nx, dics["d273"], lam, 60, 32, "X2", np.eye(60))
+    assert np.array_equal(f > 0, g["f"][sl] > 0)
+    assert np.allclose(f, g["f"][sl], rtol=1e-10, atol=1e-12 * g["f"][sl].max())
+    assert np.allclose(reg, g["reg"][sl], rtol=1e-10, atol=0)
