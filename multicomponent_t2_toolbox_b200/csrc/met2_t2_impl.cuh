@@ -178,17 +178,25 @@ __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg
 // s = sum_sel L_ii^2 (the reference's L[f>0, f>0] picks diagonal entries), the reference forms Mk = Dr^T Dr + x s 1 1^T
 // (x s added to EVERY entry), A = Dr lstsq(Mk, Dr^T, rcond=None) and returns log( (SSEr^2/m) / ((m - tr A)/m)^2 ) with
 // SSEr the residual norm of the STACKED system.  lstsq (gelsd) is a truncated pseudo-inverse: singular values <= eps*k*s_max
-// are dropped.  With the symmetric eigen-decomposition Mk = V diag(l) V^T:  tr A = sum_kept (1 - x s (1^T v_i)^2 / l_i).
-// When k > m+1 the same non-zero spectrum is taken from the (m+1) x (m+1) matrix Er Er^T, Er = [Dr; sqrt(x s) 1^T]:
-// tr A = sum_kept (1 - u_i[m]^2).  Either way only the eigenvalues and ONE linear functional of the eigenvectors are
-// needed; both come from a parallel (round-robin) two-sided Jacobi iteration in the warp's T region.
-// the kept/dropped decision sits at rounding level for eigenvalues near eps*k*l_max, so the reference
+// are dropped.  With the symmetric eigen-decomposition Mk = U diag(mu) U^T:  tr A = sum_kept (1 - x s (1^T u_i)^2 / mu_i).
+//
+// Mk is numerically of rank 10-17 whatever k is (the EPG dictionary's singular values fall by ~12x per index), so the
+// k x k eigenproblem is first reduced by a rank-revealing (diagonally pivoted) Cholesky factorisation Mk = C C^T + E,
+// C: k x r, stopped when the largest residual diagonal entry is below 1e-16 of the largest diagonal entry (far under the
+// eps*k*mu_max cut-off).  The non-zero spectrum of C C^T is that of the r x r matrix H = C^T C = W diag(mu) W^T, with
+// u_i = C w_i / sqrt(mu_i), hence  tr A = sum_kept (1 - x s (g^T w_i)^2 / mu_i^2),  g = C^T 1.
+// H goes through a parallel (round-robin) two-sided Jacobi iteration that carries g along as one row of W.
+// tools/proto_gcv_pivchol.py (CPU) measured the reduced form against the full k x k eigen-decomposition: identical
+// objective statistics against the reference (median |d obj| 5e-7 .. 8e-6; r <= 17 on the phantom).
+// the kept/dropped decision sits at rounding level for eigenvalues near eps*k*mu_max, so the reference
 // itself is not reproducible there; parity for GCV is statistical (DESIGN.md "Parity").
+constexpr int GCV_RCAP = 20;              // columns of C (numerical rank cap)
+constexpr int GCV_LDC = GCV_RCAP + 1;     // odd row stride: conflict-free column walks
+__host__ __device__ __forceinline__ int gcv_region_doubles(int n) { return n * GCV_LDC + GCV_RCAP * (GCV_RCAP | 1); }
+
 template <int NS>
-__device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int N, bool mk_form, double xs_scale, int k_sel,
-                                               int lane) {
-    // matrix A: N x N row-major with stride LD at S[W.T ..]; functional e at S[W.rs ..]; (c, s) of a round at S[W.gs ..]
-    const int oA = W.T;
+__device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N, double xs_scale, int k_sel, int lane) {
+    // matrix H: N x N row-major with stride LD at S[oA ..]; functional e at S[W.rs ..]; (c, s) of a round at S[W.gs ..]
     const int LD = N | 1;
     const int Ne = N + (N & 1);
     const int half = Ne >> 1;
@@ -232,65 +240,39 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int N, bool m
                     c = 1.0 / sqrt(1.0 + tt * tt);
                     s = tt * c;
                 }
-                // the functional transforms like a row of V: e_p' = c e_p - s e_q, e_q' = s e_p + c e_q
+                // the functional transforms like a row of W: e_p' = c e_p - s e_q, e_q' = s e_p + c e_q
                 const double ep = S[W.rs + pp], eq = S[W.rs + qq];
                 S[W.rs + pp] = c * ep - s * eq;
                 S[W.rs + qq] = s * ep + c * eq;
             }
             if (lane < half) {
-                S[W.gs + lane] = c;
-                S[W.gs + 32 + lane] = s;
+                S[W.gs + 3 * lane] = c;
+                S[W.gs + 3 * lane + 1] = s;
+                SI(W.gs + 3 * lane + 2, 0) = pp;
+                SI(W.gs + 3 * lane + 2, 1) = qq;
             }
             __syncwarp();
-            // ---- columns: A <- A J   (lane = row r; rows 32.. handled by a second slot)
-            for (int i = 0; i < half; ++i) {
-                int p2, q2;
-                if (i == 0) {
-                    p2 = round;
-                    q2 = Ne - 1;
-                } else {
-                    p2 = round + i;
-                    if (p2 >= Ne - 1) p2 -= Ne - 1;
-                    q2 = round - i + (Ne - 1);
-                    if (q2 >= Ne - 1) q2 -= Ne - 1;
-                }
-                if (p2 > q2) {
-                    int tmp = p2;
-                    p2 = q2;
-                    q2 = tmp;
-                }
-                if (q2 >= N) continue;
-                const double ci = S[W.gs + i], si = S[W.gs + 32 + i];
-                for (int r = lane; r < N; r += 32) {
-                    const double xv = S[oA + r * LD + p2], yv = S[oA + r * LD + q2];
-                    S[oA + r * LD + p2] = ci * xv - si * yv;
-                    S[oA + r * LD + q2] = si * xv + ci * yv;
+            // ---- columns: H <- H J   (lane = row r; N <= 32)
+            if (lane < N) {
+                for (int i = 0; i < half; ++i) {
+                    const int p2 = SI(W.gs + 3 * i + 2, 0), q2 = SI(W.gs + 3 * i + 2, 1);
+                    if (p2 < 0) continue;
+                    const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                    const double xv = S[oA + lane * LD + p2], yv = S[oA + lane * LD + q2];
+                    S[oA + lane * LD + p2] = ci * xv - si * yv;
+                    S[oA + lane * LD + q2] = si * xv + ci * yv;
                 }
             }
             __syncwarp();
-            // ---- rows: A <- J^T A   (lane = column)
-            for (int i = 0; i < half; ++i) {
-                int p2, q2;
-                if (i == 0) {
-                    p2 = round;
-                    q2 = Ne - 1;
-                } else {
-                    p2 = round + i;
-                    if (p2 >= Ne - 1) p2 -= Ne - 1;
-                    q2 = round - i + (Ne - 1);
-                    if (q2 >= Ne - 1) q2 -= Ne - 1;
-                }
-                if (p2 > q2) {
-                    int tmp = p2;
-                    p2 = q2;
-                    q2 = tmp;
-                }
-                if (q2 >= N) continue;
-                const double ci = S[W.gs + i], si = S[W.gs + 32 + i];
-                for (int cc = lane; cc < N; cc += 32) {
-                    const double xv = S[oA + p2 * LD + cc], yv = S[oA + q2 * LD + cc];
-                    S[oA + p2 * LD + cc] = ci * xv - si * yv;
-                    S[oA + q2 * LD + cc] = si * xv + ci * yv;
+            // ---- rows: H <- J^T H   (lane = column)
+            if (lane < N) {
+                for (int i = 0; i < half; ++i) {
+                    const int p2 = SI(W.gs + 3 * i + 2, 0), q2 = SI(W.gs + 3 * i + 2, 1);
+                    if (p2 < 0) continue;
+                    const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                    const double xv = S[oA + p2 * LD + lane], yv = S[oA + q2 * LD + lane];
+                    S[oA + p2 * LD + lane] = ci * xv - si * yv;
+                    S[oA + q2 * LD + lane] = si * xv + ci * yv;
                 }
             }
             __syncwarp();
@@ -309,71 +291,115 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int N, bool m
         const double li = S[oA + i * LD + i];
         if (li > tau) {
             const double ei = S[W.rs + i];
-            tr += mk_form ? (1.0 - xs_scale * ei * ei / li) : (1.0 - ei * ei);
+            tr += 1.0 - xs_scale * (ei * ei) / (li * li);
         }
     }
     return warp_sum(tr);
 }
 
 template <int NS>
-__device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, int oLb, const double* __restrict__ Dt,
-                                           int n, int m, int lane, double x, double sse, double nrm, int p) {
-    // sel = positions with a strictly positive coefficient, compacted into S[W.gs + 64-free]... kept in registers:
-    // position list is W.ix[0..p); after a converged solve every coefficient is > 0, after an itmax stop some may be 0
+__device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, int oLb, int n, int m, int lane,
+                                           double x, double sse, double nrm, int p) {
+    // ---- sel = positions with a strictly positive coefficient (after an itmax stop some may be 0), compacted as
+    //      column indices into S[W.gs ..] (ints); row i of Mk <-> lane i % 32, slot i / 32
+    __syncwarp();
     int k = 0;
     double sdiag = 0.0;
-    for (int i = 0; i < p; ++i) {
-        if (S[W.xs + i] > 0.0) {
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        const bool in = (i < p) && (S[W.xs + i] > 0.0);
+        const unsigned bal = __ballot_sync(FULL_MASK, in);
+        if (in) {
             const int cidx = SI(W.ix, i);
+            SI(W.gs, k + __popc(bal & ((1u << lane) - 1u))) = cidx;
             const double lii = S[oLb + 2 * n + cidx];
             sdiag = fma(lii, lii, sdiag);
-            ++k;
         }
+        k += __popc(bal);
     }
-    const double xs = x * sdiag;
-    const int oA = W.T;
-    double tr;
+    sdiag = warp_sum(sdiag);
     __syncwarp();
-    if (k <= m + 1) {
-        // Mk = G[sel, sel] + x s  (k x k); compact list of the selected columns in S[W.gs ..] (as doubles)
-        const int N = k, LD = N | 1;
-        if (lane == 0) {
-            int a = 0;
-            for (int i = 0; i < p; ++i)
-                if (S[W.xs + i] > 0.0) S[W.gs + (a++)] = (double)SI(W.ix, i);
+    const double xs = x * sdiag;
+    const int oC = W.T, oH = W.T + k * GCV_LDC;
+    // ---- diagonally pivoted Cholesky  Mk ~ C C^T  (residual diagonal in S[W.rs ..])
+    int col[NS];
+    unsigned done = 0u;
+    double dmax = 0.0;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        col[t] = (i < k) ? SI(W.gs, i) : 0;
+        if (i < k) {
+            const double d = S[oG + col[t] * ldg + col[t]] + xs;
+            S[W.rs + i] = d;
+            dmax = fmax(dmax, d);
+        } else {
+            done |= 1u << t;
         }
-        __syncwarp();
-        for (int a = 0; a < N; ++a) {
-            const int ca = (int)S[W.gs + a];
-            for (int b = lane; b < N; b += 32) S[oA + a * LD + b] = S[oG + ca * ldg + (int)S[W.gs + b]] + xs;
-        }
-        for (int a = lane; a < N; a += 32) S[W.rs + a] = 1.0;
-        __syncwarp();
-        tr = jacobi_trace<NS>(W, N, true, xs, k, lane);
-    } else {
-        // W = Er Er^T, Er = [Dr; sqrt(x s) 1^T]   ((m+1) x (m+1)); lane a owns row a (lane 0 also the last row)
-        const int N = m + 1, LD = N | 1;
-        for (int i = lane; i < N * LD; i += 32) S[oA + i] = 0.0;
-        __syncwarp();
-        const double rt = sqrt(xs);
-        for (int i = 0; i < p; ++i) {
-            if (!(S[W.xs + i] > 0.0)) continue;
-            const double* drow = Dt + SI(W.ix, i) * m;
-            for (int a = lane; a < m; a += 32) S[W.gs + a] = __ldg(drow + a);
-            __syncwarp();
-            for (int a = lane; a < m; a += 32) {
-                const double da = S[W.gs + a];
-                for (int b = 0; b < m; ++b) S[oA + a * LD + b] = fma(da, S[W.gs + b], S[oA + a * LD + b]);
-                S[oA + a * LD + m] = fma(rt, da, S[oA + a * LD + m]);
-            }
-            __syncwarp();
-        }
-        for (int a = lane; a < m; a += 32) S[oA + m * LD + a] = S[oA + a * LD + m];
-        if (lane == 0) S[oA + m * LD + m] = xs * (double)k;
-        for (int a = lane; a < N; a += 32) S[W.rs + a] = (a == m) ? 1.0 : 0.0;
-        __syncwarp();
-        tr = jacobi_trace<NS>(W, N, false, xs, k, lane);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax = fmax(dmax, __shfl_xor_sync(FULL_MASK, dmax, o));
+    const double thr = 1e-16 * dmax;
+    __syncwarp();
+    int r = 0;
+    for (; r < GCV_RCAP && r < k; ++r) {
+        double bv = 0.0;
+        int bj = -1;
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int i = lane + 32 * t;
+            if (!((done >> t) & 1u)) {
+                const double d = S[W.rs + i];
+                if (d > bv) {
+                    bv = d;
+                    bj = i;
+                }
+            }
+        }
+        const int piv = warp_argmax_pos(bv, bj);
+        if (piv < 0) break;
+        const double dp = S[W.rs + piv];
+        if (!(dp > thr)) break;
+        const int cp = SI(W.gs, piv);
+        const double rinv = rsqrt_fast(dp);
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int i = lane + 32 * t;
+            if (i < k) {
+                double cv = 0.0;
+                if (i == piv) {
+                    cv = dp * rinv;
+                    done |= 1u << t;
+                } else if (!((done >> t) & 1u)) {
+                    double v = S[oG + cp * ldg + col[t]] + xs;
+                    for (int l = 0; l < r; ++l) v = fma(-S[oC + i * GCV_LDC + l], S[oC + piv * GCV_LDC + l], v);
+                    cv = v * rinv;
+                    S[W.rs + i] = fma(-cv, cv, S[W.rs + i]);
+                }
+                S[oC + i * GCV_LDC + r] = cv;
+            }
+        }
+        __syncwarp();
+    }
+    // ---- H = C^T C (r x r) and g = C^T 1
+    const int LD = r | 1;
+    for (int a = 0; a < r; ++a) {
+        const int b = a + lane;
+        if (b < r) {
+            double h = 0.0;
+            for (int i = 0; i < k; ++i) h = fma(S[oC + i * GCV_LDC + a], S[oC + i * GCV_LDC + b], h);
+            S[oH + a * LD + b] = h;
+            S[oH + b * LD + a] = h;
+        }
+    }
+    if (lane < r) {
+        double g = 0.0;
+        for (int i = 0; i < k; ++i) g += S[oC + i * GCV_LDC + lane];
+        S[W.rs + lane] = g;
+    }
+    __syncwarp();
+    const double tr = (r > 0) ? jacobi_trace<NS>(W, oH, r, xs, k, lane) : 0.0;
     const double dm = (double)m;
     const double num = (1.0 / dm) * (sse + x * nrm);
     const double den = (1.0 / dm) * (dm - tr);
@@ -529,7 +555,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     if (stage == ST_FINAL) {
                         if (method == MET2_REG_GCV && (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL)) {
                             const double nrm = reg_norm2<NS>(W, oLb, n, lane);
-                            regv = gcv_cost<NS>(W, oG, ldg, oLb, Dt, n, m, lane, lam, sse, nrm, p);
+                            regv = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p);
                             (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                         } else
                         if (method == MET2_REG_X2 && !(A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA))
@@ -541,7 +567,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     if (method == MET2_REG_GCV) {
                         // algorithms.py:276-296
                         const double nrm = reg_norm2<NS>(W, oLb, n, lane);
-                        const double cost = gcv_cost<NS>(W, oG, ldg, oLb, Dt, n, m, lane, lam, sse, nrm, p);
+                        const double cost = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p);
                         if (!B.feed(cost, lam)) {
                             lam = B.xf;
                             stage = ST_FINAL;
@@ -672,6 +698,8 @@ static inline T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
     const int n = cfg->nT2, m = cfg->nTE;
     const bool plain = (cfg->method == MET2_REG_NNLS);
     g.pmax = plain ? (n < m ? n : m) : n;
+    if (cfg->method == MET2_REG_GCV)   // the T region also hosts the GCV workspace (C: n x 21, H: 20 x 21)
+        while (tri(g.pmax) < gcv_region_doubles(n)) ++g.pmax;
     size_t tables = sizeof(double) * (size_t)t2_table_doubles(n);
     size_t per_warp = sizeof(double) * (size_t)t2_warp_doubles<NS>(g.pmax);
     size_t budget = 227 * 1024 - 1024;
