@@ -143,6 +143,26 @@ int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met
 int met2_gaussian_smooth(const double* vol, int nx, int ny, int nz, int nt, const double* weights, int radius,
                          double* out, double* tmp, void* stream);
 
+/* Per-segment mean signal and mean kernel: the inputs of the reference's mean-spectrum diagnostics
+ * (motor/motor_recon_met2_real_data.py:377-403, one segment: mask == 1) and of its ROI-based estimator
+ * (motor/motor_recon_met2_real_data_ROI.py:405-445, one segment per ROI label), which both walk the whole volume in a
+ * Python triple loop:  total_signal = mean of data[v, :],  total_Kernel = mean of Dic_3D[:, :, FA_index[v]]  over the
+ * voxels of the segment.  label [V] int32 segment id in [0, nSeg) (anything else: voxel in no segment).
+ * Outputs: mean_signal [nSeg][nTE], mean_kernel [nSeg][nTE][nT2] (the layout of `dic`, usable as an nSeg-"angle"
+ * dictionary for met2_t2_fit), counts [nSeg] int32.  An empty segment gives NaN (the reference divides by nv = 0). */
+int64_t met2_segment_workspace_bytes(int nSeg, int nA);
+int met2_segment_means(const double* sig, const int32_t* fa_index, const int32_t* label, int64_t V, int nTE, int nT2,
+                       int nA, int nSeg, const double* dic, double* mean_signal, double* mean_kernel, int32_t* counts,
+                       void* workspace, void* stream);
+
+/* Optional Step-1 preprocessing: replaces the NESMA loop of motor/motor_recon_met2_real_data.py:305-333.  For every
+ * voxel with mask == 1: RE_p = 100 * sum_t |s_p(t) - s(t)| / sum_t s(t) over the window [c - hw, c + hw) per axis
+ * (clipped to the volume; hw = path_size = 6), out = mean of the s_p with RE_p < threshold_percent (2.5).  Voxels with
+ * mask != 1 get zeros.  vol/out [nx][ny][nz][nt] C-order, mask [nx][ny][nz] int32, tmp: nx*ny*nz*nt doubles of
+ * scratch (echo-major copy of vol); out and tmp must not alias vol. */
+int met2_nesma_filter(const double* vol, const int32_t* mask, int nx, int ny, int nz, int nt, int half_window,
+                      double threshold_percent, double* out, double* tmp, void* stream);
+
 /* Diagnostics */
 const char* met2_last_error(void);
 int met2_version(void);

@@ -39,6 +39,12 @@ SIGNATURES = {
     "met2_t2_fit": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [c_void_p] * 14),
     "met2_gaussian_smooth": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
                                             ctypes.c_int, c_void_p, c_void_p, c_void_p]),
+    "met2_segment_workspace_bytes": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int]),
+    "met2_segment_means": (ctypes.c_int, [c_void_p, c_void_p, c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                          c_void_p]),
+    "met2_nesma_filter": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "met2_last_error": (ctypes.c_char_p, []),
     "met2_version": (ctypes.c_int, []),
     "met2_launch_count": (ctypes.c_int64, []),

@@ -67,6 +67,56 @@ def gaussian_smooth(data, sigma=2.0, truncate=4.0, device=None):
     return out
 
 
+def nesma_filter(data, mask, half_window=6, threshold=2.5, device=None):
+    """NESMA denoiser of motor/motor_recon_met2_real_data.py:305-333 on the GPU (met2_nesma_filter): every voxel with
+    mask == 1 becomes the mean of the signals in its [-6, +6) window whose relative L1 distance to it is < 2.5 %.
+    data[nx, ny, nz, nt], mask[nx, ny, nz]; returns a CUDA tensor like data."""
+    dev = _require_cuda(device)
+    lib = _lib.load()
+    if isinstance(data, np.ndarray):
+        data = torch.as_tensor(np.ascontiguousarray(data, dtype=np.float64))
+    if isinstance(mask, np.ndarray):
+        mask = torch.as_tensor(np.ascontiguousarray(mask))
+    vol = data.to(device=dev, dtype=torch.float64).contiguous()
+    msk = mask.to(device=dev, dtype=torch.int32).contiguous()
+    if vol.dim() != 4 or tuple(msk.shape) != tuple(vol.shape[:3]):
+        raise ValueError("data must be [nx, ny, nz, nt] and mask [nx, ny, nz]")
+    out = torch.empty_like(vol)
+    tmp = torch.empty_like(vol)
+    nx, ny, nz, nt = vol.shape
+    with torch.cuda.device(dev):
+        _lib.check(lib.met2_nesma_filter(_ptr(vol), _ptr(msk), nx, ny, nz, nt, int(half_window), float(threshold),
+                                         _ptr(out), _ptr(tmp), _stream()), "met2_nesma_filter")
+    return out
+
+
+def segment_means(sig, fa_index, labels, n_seg, dictionary):
+    """Per-segment mean signal and mean kernel (met2_segment_means; motor...:377-392 and
+    motor_recon_met2_real_data_ROI.py:408-423).  sig[V, nTE], fa_index[V], labels[V] in [0, n_seg) (else: no segment).
+    Returns (mean_signal[n_seg, nTE], mean_kernel[n_seg, nTE, nT2], counts[n_seg]) as CUDA tensors."""
+    lib = _lib.load()
+    dev = dictionary.dic.device
+    if isinstance(sig, np.ndarray):
+        sig = torch.as_tensor(np.ascontiguousarray(sig, dtype=np.float64))
+    sig = sig.to(device=dev, dtype=torch.float64).contiguous()
+    as_i32 = lambda a: (torch.as_tensor(np.ascontiguousarray(a)) if isinstance(a, np.ndarray) else a).to(
+        device=dev, dtype=torch.int32).contiguous()
+    fa_index, labels = as_i32(fa_index), as_i32(labels)
+    V = sig.shape[0]
+    if sig.dim() != 2 or sig.shape[1] != dictionary.nTE or fa_index.shape != (V,) or labels.shape != (V,):
+        raise ValueError("segment_means: sig[V, nTE], fa_index[V], labels[V] expected")
+    n_seg = int(n_seg)
+    mean_signal = torch.empty((n_seg, dictionary.nTE), dtype=torch.float64, device=dev)
+    mean_kernel = torch.empty((n_seg, dictionary.nTE, dictionary.nT2), dtype=torch.float64, device=dev)
+    counts = torch.empty(n_seg, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty(int(lib.met2_segment_workspace_bytes(n_seg, dictionary.nA)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.met2_segment_means(_ptr(sig), _ptr(fa_index), _ptr(labels), V, dictionary.nTE, dictionary.nT2,
+                                          dictionary.nA, n_seg, _ptr(dictionary.dic), _ptr(mean_signal),
+                                          _ptr(mean_kernel), _ptr(counts), _ptr(ws), _stream()), "met2_segment_means")
+    return mean_signal, mean_kernel, counts
+
+
 class Dictionary:
     """Device EPG dictionary of one angle grid: dic [nA][nTE][nT2], dicT [nA][nT2][nTE], G [nA][nT2][nT2]."""
 
@@ -100,6 +150,24 @@ class Dictionary:
         self.alphas = _dev_f64(self.alphas_host, dev)
         self.dic = _dev_f64(np.transpose(Dic_3D, (2, 0, 1)), dev)
         self.dicT = _dev_f64(np.transpose(Dic_3D, (2, 1, 0)), dev)
+        self.G = torch.empty((self.nA, self.nT2, self.nT2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.met2_gram_tables(_ptr(self.dic), self.nA, self.nTE, self.nT2, None, _ptr(self.G), None, None,
+                                            _stream()), "met2_gram_tables")
+        return self
+
+    @classmethod
+    def from_device(cls, dic, alphas=None):
+        """Tables for a dictionary already on the GPU as dic[nA, nTE, nT2] (e.g. the per-segment mean kernels of
+        `segment_means`)."""
+        lib = _lib.load()
+        self = cls.__new__(cls)
+        dev = dic.device
+        self.dic = dic.to(torch.float64).contiguous()
+        self.nA, self.nTE, self.nT2 = self.dic.shape
+        self.alphas_host = np.ascontiguousarray(alphas if alphas is not None else np.zeros(self.nA), dtype=np.float64)
+        self.alphas = _dev_f64(self.alphas_host, dev)
+        self.dicT = self.dic.transpose(1, 2).contiguous()
         self.G = torch.empty((self.nA, self.nT2, self.nT2), dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             _lib.check(lib.met2_gram_tables(_ptr(self.dic), self.nA, self.nTE, self.nT2, None, _ptr(self.G), None, None,
@@ -249,8 +317,9 @@ class Met2Plan:
         return out
 
     # ------------------------------------------------------------------ Steps 3 + 4
-    def t2_fit(self, sig, fa_index, reg_method=None, out=None, flags=0, **cfg_overrides):
-        """Spectrum fit + metrics.  Returns dict(fsol[V,nT2], est_signal[V,nTE], reg[V], maps[V,6], status[V])."""
+    def t2_fit(self, sig, fa_index, reg_method=None, out=None, flags=0, dictionary=None, **cfg_overrides):
+        """Spectrum fit + metrics.  Returns dict(fsol[V,nT2], est_signal[V,nTE], reg[V], maps[V,6], status[V]).
+        `dictionary` (a `Dictionary` with this plan's nTE / nT2) replaces the plan's own kernel set for this call."""
         sig = self._signals(sig)
         V = sig.shape[0]
         dev = self.dev
@@ -268,12 +337,15 @@ class Met2Plan:
         if V == 0:
             return out
         cfg = self.t2_cfg(reg_method, flags, **cfg_overrides)
+        hr = self.dict_hr if dictionary is None else dictionary
+        if (hr.nTE, hr.nT2) != (self.nTE, self.npc):
+            raise ValueError("dictionary shape does not match the plan")
+        cfg.nA = hr.nA
         with torch.cuda.device(dev):
             nbytes = self.lib.met2_t2_workspace_bytes(V, ctypes.byref(cfg))
             if nbytes < 0:
                 _lib.check(-1, "met2_t2_workspace_bytes")
             ws = self._workspace("t2", nbytes)
-            hr = self.dict_hr
             _lib.check(self.lib.met2_t2_fit(
                 _ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(hr.dic), _ptr(hr.dicT), _ptr(hr.G),
                 _ptr(self.kband), _ptr(self.lambdas), _ptr(self.logT2), _ptr(self.comp), _ptr(out["fsol"]),

@@ -794,3 +794,93 @@ def recon_volume(data, mask, TE_array, TR, reg_method, reg_matrix, FA_method, my
     out.update(TWC=Ktotal, FA=FA, FA_index=FA_index, fsol_4D=f_sol_4D, Est_Signal=s_sol_4D, reg_param=reg_param,
                mean_T2_dist=mean_T2_dist, T2s=g["T2s"], alpha_values=g["alpha_values"])
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# Rows of SURVEY.md §8f either side of the voxel fit: NESMA denoiser, mean-spectrum diagnostics, ROI-based estimator.
+# ----------------------------------------------------------------------------------------------------------------
+
+
+def nesma_filter(data, mask, path_size=(6, 6, 6), threshold=2.5):
+    """NESMA denoiser — motor/motor_recon_met2_real_data.py:305-333 (same loops, same NumPy expressions)."""
+    data = np.asarray(data, dtype=np.float64)
+    nx, ny, nz, nt = data.shape
+    data_den = np.zeros_like(data)
+    with np.errstate(all="ignore"):
+        for voxelx in range(nx):
+            min_x = np.max([voxelx - path_size[0], 0])
+            max_x = np.min([voxelx + path_size[0], nx])
+            for voxely in range(ny):
+                min_y = np.max([voxely - path_size[1], 0])
+                max_y = np.min([voxely + path_size[1], ny])
+                for voxelz in range(nz):
+                    if mask[voxelx, voxely, voxelz] == 1:
+                        min_z = np.max([voxelz - path_size[2], 0])
+                        max_z = np.min([voxelz + path_size[2], nz])
+                        signal_path = data[min_x:max_x, min_y:max_y, min_z:max_z, :]
+                        dim = signal_path.shape
+                        signal_path2D = signal_path.reshape((np.prod(dim[0:3]), nt))
+                        signal_xyz = data[voxelx, voxely, voxelz]
+                        RE = 100 * np.sum(np.abs(signal_path2D - signal_xyz), axis=1) / np.sum(signal_xyz)
+                        ind_valid = RE < threshold
+                        if ind_valid.any():
+                            data_den[voxelx, voxely, voxelz] = np.mean(signal_path2D[ind_valid, :], axis=0)
+                        else:
+                            data_den[voxelx, voxely, voxelz] = np.nan   # np.mean of an empty selection
+    return data_den
+
+
+def segment_mean(data, FA_index, Dic_3D, selector):
+    """total_signal / total_Kernel of motor...:377-392 (selector = mask == 1) and of
+    motor_recon_met2_real_data_ROI.py:408-423 (selector = ROIs == label): sequential sums in (x, y, z) order."""
+    nx, ny, nz, nt = data.shape
+    total_signal = 0
+    total_Kernel = 0
+    nv = 0
+    for voxelx in range(nx):
+        for voxely in range(ny):
+            for voxelz in range(nz):
+                if selector[voxelx, voxely, voxelz]:
+                    total_signal = total_signal + data[voxelx, voxely, voxelz, :]
+                    ind_xyz = int(FA_index[voxelx, voxely, voxelz])
+                    total_Kernel = total_Kernel + Dic_3D[:, :, ind_xyz]
+                    nv = nv + 1.0
+    return total_signal / nv, total_Kernel / nv, nv
+
+
+def mean_spectrum_diagnostics(data, mask, FA_index, Dic_3D, mean_T2_dist, factor=1.01):
+    """The three curves of the 'Mean_spectrum_from_all_voxels' figure — motor...:375-403."""
+    npc = Dic_3D.shape[1]
+    mean_T2_dist = mean_T2_dist / np.sum(mean_T2_dist)
+    total_signal, total_Kernel, nv = segment_mean(data, FA_index, Dic_3D, np.asarray(mask) == 1)
+    fmean1, SSE = nnls(total_Kernel, total_signal)
+    fmean2, reg_opt2, k_est = nnls_x2(total_Kernel, total_signal, np.eye(npc), factor)
+    return dict(mean_T2_dist=mean_T2_dist, dist_T2_mean1=fmean1 / np.sum(fmean1), dist_T2_mean2=fmean2 / np.sum(fmean2),
+                total_signal=total_signal, total_Kernel=total_Kernel, nv=nv, reg_opt2=reg_opt2, k_est=k_est)
+
+
+def roi_estimates(data, mask, ROIs, FA_index, Dic_3D, Laplac, T2s, ind_m, ind_t, ind_csf, factor=1.01):
+    """ROI-based estimator — motor/motor_recon_met2_real_data_ROI.py:166-183 (labels) and :405-445 (per-ROI X2 fit and
+    metrics)."""
+    ROIs = np.asarray(ROIs).astype(np.int64)
+    values = np.unique(ROIs)
+    values = np.delete(values, np.where(values == 0))
+    ROIs = ROIs * np.asarray(mask).astype(np.int64)
+    logT2 = np.log(T2s)
+    out = dict(roi_values=values, fsol_ROIs=np.zeros((len(values), len(T2s))))
+    for k in ("MWF", "IEWF", "FWF", "T2M", "T2IE", "TWC", "reg_opt", "k_est"):
+        out[k] = np.zeros(len(values))
+    for i, val in enumerate(values):
+        total_signal, total_Kernel, nv = segment_mean(data, FA_index, Dic_3D, ROIs == val)
+        x_sol, reg_opt2, k_est = nnls_x2(total_Kernel, total_signal, Laplac, factor)
+        vt = np.sum(x_sol) + EPSILON
+        x_sol = x_sol / vt
+        out["fsol_ROIs"][i] = x_sol
+        out["MWF"][i] = np.sum(x_sol[ind_m])
+        out["IEWF"][i] = np.sum(x_sol[ind_t])
+        out["FWF"][i] = np.sum(x_sol[ind_csf])
+        out["T2M"][i] = np.exp(np.sum(x_sol[ind_m] * logT2[ind_m]) / (np.sum(x_sol[ind_m]) + EPSILON))
+        out["T2IE"][i] = np.exp(np.sum(x_sol[ind_t] * logT2[ind_t]) / (np.sum(x_sol[ind_t]) + EPSILON))
+        out["TWC"][i] = vt
+        out["reg_opt"][i], out["k_est"][i] = reg_opt2, k_est
+    return out

@@ -132,3 +132,107 @@ def test_gaussian_smooth_bitwise_equal_to_scipy():
         for c in range(shape[3]):
             ref = gaussian_filter(data[:, :, :, c], 2.0, 0)
             assert np.array_equal(got[:, :, :, c], ref), (shape, c, np.abs(got[:, :, :, c] - ref).max())
+
+
+# ------------------------------------------------------------------------------------------------ SURVEY.md §8f rows
+@pytest.fixture(scope="module")
+def pipeline_gold():
+    from conftest import GOLDEN
+    return dict(np.load(os.path.join(GOLDEN, "pipeline_nesma_x2.npz")))
+
+
+def test_nesma_filter_vs_numpy_restatement(pipeline_gold):
+    """NESMA denoiser (motor...:305-333) on the GPU against the oracle's loop-for-loop restatement: same summation
+    orders, so the result is bitwise equal wherever the 2.5 % similarity decisions agree (they all do here)."""
+    from multicomponent_t2_toolbox_b200 import batched
+    g = pipeline_gold
+    mask = g["mask"].astype(np.int64)
+    data = g["data"] * mask[..., None]
+    got = batched.nesma_filter(data, mask).cpu().numpy()
+    ref = O.nesma_filter(data, mask)
+    assert got.shape == ref.shape and not got[mask == 0].any()
+    assert np.array_equal(got, ref), np.abs(got - ref).max()
+    # 48 echoes (two register slots), non-cubic volume smaller than the window, a mask value that is not 1, and a voxel
+    # whose own signal is all zero (RE = NaN -> empty selection -> NaN, like np.mean of an empty array)
+    rng = np.random.default_rng(5)
+    base = rng.uniform(100.0, 1000.0, (1, 1, 1, 48)) * np.exp(-np.arange(48) / 10.0)
+    vol = base * (1.0 + 0.004 * rng.standard_normal((7, 5, 16, 48)))
+    m2 = np.ones((7, 5, 16), dtype=np.int64)
+    m2[0, 0, 0] = 2
+    m2[3, 2, 1] = 0
+    vol[3, 2, 1] = 0.0
+    vol[4, 4, 4] = 0.0
+    got2 = batched.nesma_filter(vol, m2).cpu().numpy()
+    ref2 = O.nesma_filter(vol, m2)
+    assert np.isnan(ref2[4, 4, 4]).all() and np.isnan(got2[4, 4, 4]).all()
+    assert not got2[0, 0, 0].any() and not got2[3, 2, 1].any()
+    assert np.array_equal(np.nan_to_num(got2, nan=-1.0), np.nan_to_num(ref2, nan=-1.0))
+
+
+def test_motor_recon_met2_nesma_smooth_against_reference_run(pipeline_gold, tmp_path):
+    """The whole entry point (NIfTI in -> NESMA -> smoothing -> FA spline -> X2-I -> maps -> NIfTI out) against the
+    outputs of the UNMODIFIED reference orchestrator run end to end (oracle/make_golden_pipeline.py)."""
+    g = pipeline_gold
+    nifti_io.save(g["data"], str(tmp_path / "Data.nii.gz"))
+    nifti_io.save(g["mask"].astype(np.int16), str(tmp_path / "Mask.nii.gz"))
+    out = str(tmp_path / "recon_all_X2-I") + "/"
+    os.mkdir(out)
+    vol = motor_recon_met2(g["TE"], str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"), out, 1000.0, "X2", "I",
+                           "NESMA", "spline", "yes", 40.0, -1)
+    assert np.array_equal(nifti_io.load(out + "FA.nii.gz").get_fdata(), g["FA"])            # FA index bit-exact
+    f = nifti_io.load(out + "fsol_4D.nii.gz").get_fdata()
+    assert np.array_equal(f > 0, g["fsol_4D"] > 0)                                           # active sets bit-exact
+    scale = np.abs(g["fsol_4D"]).max(axis=3, keepdims=True)
+    scale[scale == 0] = 1.0
+    assert (np.abs(f - g["fsol_4D"]) / scale).max() < 1e-6
+    for k in ("MWF", "IEWF", "FWF", "T2_M", "T2_IE"):
+        assert np.abs(nifti_io.load(out + k + ".nii.gz").get_fdata() - g[k]).max() < 1e-4, k
+    for k in ("TWC", "Est_Signal", "reg_param"):
+        got = nifti_io.load(out + k + ".nii.gz").get_fdata()
+        assert np.abs(got - g[k]).max() <= 1e-6 * np.abs(g[k]).max(), k
+    # the data behind the reference's mean-spectrum figure (motor...:375-403)
+    tab = np.loadtxt(out + "Mean_spectrum_from_all_voxels.txt")
+    for col, k in enumerate(("mean_T2_dist", "dist_T2_mean1", "dist_T2_mean2"), start=1):
+        assert np.abs(tab[:, col] - g[k]).max() < 1e-6 * g[k].max(), k
+        assert np.array_equal(tab[:, col] > 0, g[k] > 0), k
+    assert vol["diagnostics"]["nv"] == int((g["mask"] == 1).sum())
+
+
+def test_roi_estimator_against_oracle(pipeline_gold, tmp_path):
+    """ROI-based estimator (motor_recon_met2_real_data_ROI.py:405-445) through its file-level entry point."""
+    from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data_ROI import motor_recon_met2_ROIs
+    g = pipeline_gold
+    nx, ny, nz = g["mask"].shape
+    rois = (1 + (np.arange(nx)[:, None, None] // 5) + 3 * (np.arange(ny)[None, :, None] // 6)
+            + 0 * np.arange(nz)[None, None, :]).astype(np.int16)
+    rois[:, :, :2] = 0
+    rois[0, 0, 5] = 40            # a label that only exists outside the mask: empty after ROIs * mask
+    nifti_io.save(g["data"], str(tmp_path / "Data.nii.gz"))
+    nifti_io.save(g["mask"].astype(np.int16), str(tmp_path / "Mask.nii.gz"))
+    nifti_io.save(rois, str(tmp_path / "ROIs.nii.gz"))
+    out = str(tmp_path / "recon_all_X2-L2_ROI-based") + "/"
+    os.mkdir(out)
+    vol = motor_recon_met2_ROIs(g["TE"], str(tmp_path / "Data.nii.gz"), str(tmp_path / "Mask.nii.gz"),
+                                str(tmp_path / "ROIs.nii.gz"), out, 1000.0, "L2", "None", "spline", "no", 40.0, -1)
+    mask = g["mask"].astype(np.int64)
+    data = g["data"] * mask[..., None]
+    gr = O._grids("X2", "L2", "spline", 40.0, 32, 10.0, 1000.0)
+    Dic = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, gr["alpha_values"], 1000.0)
+    keep = np.unique(rois)
+    keep = keep[(keep != 0) & (keep != 40)]
+    rois_ref = np.where(np.isin(rois, keep), rois, 0)
+    ref = O.roi_estimates(data, mask, rois_ref, vol["FA_index"], Dic, gr["L"], gr["T2s"], gr["ind_m"], gr["ind_t"],
+                          gr["ind_csf"])
+    roi = vol["roi"]
+    sel = np.isin(roi["roi_values"], keep)
+    assert np.array_equal(roi["roi_values"][sel], ref["roi_values"]) and roi["roi_values"][~sel].tolist() == [40]
+    assert roi["counts"][~sel].tolist() == [0] and not np.isfinite(roi["mean_signal"][~sel]).any()
+    assert np.array_equal(roi["fsol_ROIs"][sel] > 0, ref["fsol_ROIs"] > 0)
+    assert np.abs(roi["fsol_ROIs"][sel] - ref["fsol_ROIs"]).max() < 1e-6 * ref["fsol_ROIs"].max()
+    for k in ("MWF", "IEWF", "FWF", "T2M", "T2IE"):
+        assert np.abs(roi[k + "_ROIs"][sel] - ref[k]).max() < 1e-4, k
+    assert np.allclose(roi["TWC_ROIs"][sel], ref["TWC"], rtol=1e-6)
+    assert np.allclose(roi["reg_opt"][sel], ref["reg_opt"], rtol=1e-5) and np.allclose(roi["k_est"][sel], ref["k_est"], rtol=1e-6)
+    assert np.allclose(np.loadtxt(out + "table_MWF.csv", delimiter=",")[sel], ref["MWF"], atol=1e-4)
+    assert np.loadtxt(out + "table_Spectra.csv", delimiter=",").shape == (len(roi["roi_values"]), 60)
+    assert os.path.exists(out + "ROI_%d/table_values.csv" % int(keep[0]))
