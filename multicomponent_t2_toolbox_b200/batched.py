@@ -20,6 +20,7 @@ FA_METHOD_CODE = {"brute-force": 0, "spline": 1}
 REG_METHOD_CODE = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3, "GCV": 4, "BayesReg": 5}
 
 ST_SKIPPED, ST_NONFINITE, ST_ITMAX, ST_SSE_ZERO, ST_NOT_PD = 1, 2, 4, 8, 16
+REG_IS_LAMBDA, NO_NORMALISE, COLD_START, GCV_EVAL, FULL_START, GCV_GRID = 1, 2, 4, 8, 16, 32   # MET2_T2_FLAG_*
 
 
 def _require_cuda(device):
@@ -182,7 +183,7 @@ class Dictionary:
 class Met2Plan:
     def __init__(self, n_echoes, tau, TR, reg_method="X2", reg_matrix="I", FA_method="spline", myelin_T2=40.0,
                  npc=None, n_alphas=None, T1=1000.0, device=None, lambda_reg=None, Laplac=None, Dic_3D=None,
-                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None):
+                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None, t2_flags=0):
         """Tables for one reconstruction set-up.  By default everything is built like motor...:204-277 (EPG dictionary
         on the GPU); `Dic_3D` (+ `Dic_3D_LR`, `alpha_values`, `alpha_values_spline`, `T2s`, `Laplac`) lets a caller bring
         its own dictionary in the reference layout [nTE, nT2, nA] — used by the drop-in row workers and per-voxel API."""
@@ -193,6 +194,7 @@ class Met2Plan:
         self.dev = _require_cuda(device)
         self.lib = _lib.load()
         self.reg_method, self.reg_matrix, self.FA_method = reg_method, reg_matrix, FA_method
+        self.t2_flags = int(t2_flags)    # MET2_T2_FLAG_* applied to every t2_fit of this plan (e.g. GCV_GRID)
         self.nTE, self.tau, self.TR = int(n_echoes), float(tau), float(TR)
         if Dic_3D is not None:
             Dic_3D = np.asarray(Dic_3D, dtype=np.float64)
@@ -258,7 +260,7 @@ class Met2Plan:
         method = self.reg_method if reg_method is None else reg_method
         cfg = _lib.T2Cfg(method=REG_METHOD_CODE[method], nTE=self.nTE, nT2=self.npc, nA=len(self.alpha_values),
                          nLambda=len(self.lambda_reg), maxfun=300, factor=1.02, lambda_fixed=1.8, brent_lo=0.0,
-                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=int(flags), reserved=0)
+                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=int(flags) | self.t2_flags, reserved=0)
         if method == "GCV":
             cfg.brent_lo = 1e-8
         if method == "BayesReg":
@@ -341,6 +343,10 @@ class Met2Plan:
         if (hr.nTE, hr.nT2) != (self.nTE, self.npc):
             raise ValueError("dictionary shape does not match the plan")
         cfg.nA = hr.nA
+        lambdas = self.lambdas
+        if cfg.flags & GCV_GRID:    # GCV over the positive part of the L-curve grid (lambda_reg[1:]; lambda_reg[0] = 0)
+            lambdas = self.lambdas[1:].contiguous()
+            cfg.nLambda = lambdas.numel()
         with torch.cuda.device(dev):
             nbytes = self.lib.met2_t2_workspace_bytes(V, ctypes.byref(cfg))
             if nbytes < 0:
@@ -348,7 +354,7 @@ class Met2Plan:
             ws = self._workspace("t2", nbytes)
             _lib.check(self.lib.met2_t2_fit(
                 _ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(hr.dic), _ptr(hr.dicT), _ptr(hr.G),
-                _ptr(self.kband), _ptr(self.lambdas), _ptr(self.logT2), _ptr(self.comp), _ptr(out["fsol"]),
+                _ptr(self.kband), _ptr(lambdas), _ptr(self.logT2), _ptr(self.comp), _ptr(out["fsol"]),
                 _ptr(out["est_signal"]), _ptr(out["reg"]), _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), _stream()),
                 "met2_t2_fit")
         return out

@@ -521,6 +521,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     if (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL) {   // objective-level parity hook: one solve at lambda_fixed
                         stage = ST_FINAL;
                         lam = A.cfg.lambda_fixed;
+                    } else if (A.cfg.flags & MET2_T2_FLAG_GCV_GRID) {   // arg-min of the objective over the lambda grid
+                        lam = S[oLam];
                     }
                 } else {   // MET2_REG_LCURVE
                     stage = ST_SEARCH; reg = true; lam = S[oLam];
@@ -568,7 +570,20 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                         // algorithms.py:276-296
                         const double nrm = reg_norm2<NS>(W, oLb, n, lane);
                         const double cost = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p);
-                        if (!B.feed(cost, lam)) {
+                        if (A.cfg.flags & MET2_T2_FLAG_GCV_GRID) {
+                            // np.argmin over the grid: first minimum, a NaN wins and stays
+                            if (gi == 0 || (SSE == SSE && (cost < SSE || cost != cost))) {
+                                SSE = cost;      // best objective so far (SSE is unused by GCV otherwise)
+                                beta = lam;      // ... and its lambda
+                            }
+                            ++gi;
+                            if (gi < A.cfg.nLambda) {
+                                lam = S[oLam + gi];
+                            } else {
+                                lam = beta;
+                                stage = ST_FINAL;
+                            }
+                        } else if (!B.feed(cost, lam)) {
                             lam = B.xf;
                             stage = ST_FINAL;
                         }

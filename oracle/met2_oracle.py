@@ -884,3 +884,16 @@ def roi_estimates(data, mask, ROIs, FA_index, Dic_3D, Laplac, T2s, ind_m, ind_t,
         out["TWC"][i] = vt
         out["reg_opt"][i], out["k_est"][i] = reg_opt2, k_est
     return out
+
+
+def nnls_gcv_grid(D, M, L, lambdas):
+    """Extension for BASELINE.json configs[2] ("GCV over a 50-point lambda grid"; the reference itself uses Brent,
+    algorithms.py:280): the reference's own objective obj_nnls_gcv (:285-296) evaluated on the grid, arg-min (np.argmin:
+    first minimum), final solve with nnls_tik (:262).  Returns (f, lambda, costs)."""
+    m, n = D.shape
+    Maug = np.concatenate((M, np.zeros(n)))
+    Im = np.eye(m)
+    with np.errstate(all="ignore"):
+        costs = np.array([obj_nnls_gcv(x, D, L, Maug, m, Im) for x in lambdas])
+    reg = lambdas[int(np.argmin(costs))]
+    return nnls_tik(D, M, L, reg), reg, costs
