@@ -226,6 +226,17 @@ __device__ __forceinline__ double rsqrt_fast(double d) {
     return r;
 }
 
+// 1/d from the single-precision hardware reciprocal plus two Newton steps in double (relative error ~1e-16).
+__device__ __forceinline__ double rcp_fast(double d) {
+    if (!(d > 1e-30 && d < 1e30)) return 1.0 / d;
+    double r = (double)__frcp_rn((float)d);
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+
 // FP64 tensor-core MMA m8n8k4 (DMMA.8x8x4 on sm_100a): D(8x8) += A(8x4) B(4x8).  Fragments: A[lane/4][lane%4],
 // B[lane%4][lane/4], C/D[lane/4][2*(lane%4) + {0,1}] (verified on B200 by tools/dmma_probe.cu; 16 cycles issue interval,
 // 26 cycles dependent latency).
@@ -297,45 +308,49 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
             const double v = jlive ? S[colg + 4 * is + q] : 0.0;
             dmma884(s0, s1, -v, v);
         }
-        // ---- T_JJ = chol(S)^-1 in the scratch sc = S[W.gs ..] (row-major 8 x 8)
-        S[W.gs + g * 8 + 2 * q] = s0;
-        S[W.gs + g * 8 + 2 * q + 1] = s1;
-        __syncwarp();
+        // ---- T_JJ = chol(S)^-1 by symmetric Gaussian elimination on the augmented block [S | I] (8 x 16, row-major in
+        //      S[W.gs .. W.gs + 128), which spans gs and rs): after the 7 steps the left half holds D L1^T (S = L1 D L1^T)
+        //      and the right half M = L1^-1, so R = D^1/2 L1^T and T_JJ[r][c] = M[c][r] / sqrt(d_c) for r <= c.
+        //      One __syncwarp per step and one reciprocal on the dependency chain (the previous version ran an 8-step
+        //      Cholesky with three barriers per step and then a serial 8 x 8 triangular inverse on 8 lanes: ~20 % of
+        //      the kernel's stall samples, profiles/r01_t2_fit_v8_ncu_summary.txt).
+        {
+            // element (r, c) lives at r*16 + ((c + r) & 15): the rotation keeps both the row-k broadcasts and the
+            // per-lane row updates free of shared-memory bank conflicts within a half-warp
+            auto AUG = [&](int r, int c) -> int { return W.gs + r * 16 + ((c + r) & 15); };
+            S[AUG(g, 2 * q)] = s0;
+            S[AUG(g, 2 * q + 1)] = s1;
+            S[AUG(g, 8 + 2 * q)] = (2 * q == g) ? 1.0 : 0.0;
+            S[AUG(g, 8 + 2 * q + 1)] = (2 * q + 1 == g) ? 1.0 : 0.0;
+            __syncwarp();
+            const int r = g, cg = 4 * q;   // this lane updates Aug[r][cg .. cg+3]
 #pragma unroll 1
-        for (int k = 0; k < 8; ++k) {
-            const double d = S[W.gs + k * 9];
-            if (!(d > 0.0)) ok = false;
-            const double ri = rsqrt_fast(d);
-            __syncwarp();
-            if (lane < 8 && lane > k) S[W.gs + k * 8 + lane] *= ri;   // row k of R
-            if (lane == k) S[W.gs + k * 9] = ri;                      // keep 1/R_kk on the diagonal
-            __syncwarp();
+            for (int k = 0; k < 7; ++k) {
+                const double d = S[AUG(k, k)];
+                if (!(d > 0.0)) ok = false;
+                if (r > k) {
+                    const double m = S[AUG(k, r)] * rcp_fast(d);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int c = cg + j;
+                        if ((c < 8) ? (c >= r) : (c - 8 <= k)) S[AUG(r, c)] = fma(-m, S[AUG(k, c)], S[AUG(r, c)]);
+                    }
+                }
+                __syncwarp();
+            }
+            if (!(S[AUG(7, 7)] > 0.0)) ok = false;
+            // T_JJ (row-major 8 x 8) -> S[W.rs ..]; Aug overlaps rs, so gather into registers first
+            const int c = lane & 7;
+            const double ric = rsqrt_fast(S[AUG(c, c)]);
+            double tv[2];
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
-                const int r = pass * 4 + (lane >> 3), c = lane & 7;
-                if (r > k && c >= r)
-                    S[W.gs + r * 8 + c] = fma(-S[W.gs + k * 8 + r], S[W.gs + k * 8 + c], S[W.gs + r * 8 + c]);
+                const int rr = pass * 4 + (lane >> 3);
+                tv[pass] = (rr < c) ? S[AUG(c, 8 + rr)] * ric : ((rr == c) ? ric : 0.0);
             }
             __syncwarp();
-        }
-        double trow[8];   // lane k < 8 owns row k of T_JJ
 #pragma unroll
-        for (int c = 0; c < 8; ++c) trow[c] = 0.0;
-        if (lane < 8) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                if (c == lane) {
-                    trow[c] = S[W.gs + c * 9];
-                } else if (c > lane) {
-                    double sacc = 0.0;
-#pragma unroll
-                    for (int l = 0; l < c; ++l)
-                        if (l >= lane) sacc = fma(trow[l], S[W.gs + l * 8 + c], sacc);
-                    trow[c] = -sacc * S[W.gs + c * 9];
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < 8; ++c) S[W.rs + lane * 8 + c] = trow[c];
+            for (int pass = 0; pass < 2; ++pass) S[W.rs + (pass * 4 + (lane >> 3)) * 8 + c] = tv[pass];
         }
         __syncwarp();
         if (b > 0) {
@@ -370,13 +385,11 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
                 if (cb < p) S[colb + kk] = -e1;
             }
         }
-        // ---- diagonal block
-        if (lane < 8) {
+        // ---- diagonal block: T[c0 + r][c0 + c] = T_JJ[r][c] for r <= c (two entries per lane)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int cc = c0 + c, rr = c0 + lane;
-                if (c >= lane && cc < p) S[oT + tri(cc) + rr] = trow[c];
-            }
+        for (int pass = 0; pass < 2; ++pass) {
+            const int rr = pass * 4 + (lane >> 3), c = lane & 7;
+            if (rr <= c && c0 + c < p) S[oT + tri(c0 + c) + c0 + rr] = S[W.rs + rr * 8 + c];
         }
         __syncwarp();
     }
