@@ -22,19 +22,24 @@ __global__ void t2_hist_kernel(const int* __restrict__ fa_index, long long V, in
     atomicAdd(&hist[f], 1);
 }
 
-__global__ void t2_tiles_kernel(const int* __restrict__ hist, int nA, int* __restrict__ bin_start,
-                                int* __restrict__ cursor, int* __restrict__ tile_fa, int* __restrict__ tile_start,
-                                int* __restrict__ tile_cnt, int* __restrict__ counters) {
+// Tiles are handed to the persistent CTAs in list order (atomic counter).  Guided self-scheduling: large tiles first
+// (few per-tile barriers and G re-stagings), small tiles for the last `V - switch_off` voxels so that the CTAs run dry
+// within a fraction of a large tile's duration of each other.
+__global__ void t2_tiles_kernel(const int* __restrict__ hist, int nA, int tile_big, int tile_small, int switch_off,
+                                int* __restrict__ bin_start, int* __restrict__ cursor, int* __restrict__ tile_fa,
+                                int* __restrict__ tile_start, int* __restrict__ tile_cnt, int* __restrict__ counters) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     int off = 0, nt = 0;
     for (int a = 0; a < nA; ++a) {
         int c = hist[a];
         bin_start[a] = off;
         cursor[a] = 0;
-        for (int s = 0; s < c; s += T2_TILE) {
+        for (int s = 0; s < c;) {
+            const int ts = (off + s < switch_off) ? tile_big : tile_small;
             tile_fa[nt] = a;
             tile_start[nt] = off + s;
-            tile_cnt[nt] = (c - s < T2_TILE) ? (c - s) : T2_TILE;
+            tile_cnt[nt] = (c - s < ts) ? (c - s) : ts;
+            s += ts;
             ++nt;
         }
         off += c;
@@ -64,13 +69,6 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
         return set_error(MET2_ERR_ARG, "met2_t2: unsupported sizes nT2=%d nTE=%d nA=%d", cfg->nT2, cfg->nTE, cfg->nA);
     if (cfg->method < MET2_REG_NNLS || cfg->method > MET2_REG_BAYESREG)
         return set_error(MET2_ERR_ARG, "met2_t2: unknown method %d", cfg->method);
-    if (cfg->method == MET2_REG_GCV) {
-        // the Jacobi work matrix ((min(nT2, nTE+1))^2 with odd stride) lives in the packed-T region
-        const int N = cfg->nT2 < cfg->nTE + 1 ? cfg->nT2 : cfg->nTE + 1;
-        if (N * (N | 1) > (cfg->nT2 * (cfg->nT2 + 1)) / 2)
-            return set_error(MET2_ERR_UNSUPPORTED, "met2_t2: GCV needs (nTE+1)^2 <= nT2(nT2+1)/2 (nTE=%d nT2=%d)",
-                             cfg->nTE, cfg->nT2);
-    }
     if (cfg->method == MET2_REG_LCURVE && (cfg->nLambda < 3 || cfg->nLambda > MET2_MAX_LAMBDAS))
         return set_error(MET2_ERR_ARG, "met2_t2: L-curve needs 3..%d lambdas", MET2_MAX_LAMBDAS);
     return MET2_OK;
@@ -127,8 +125,8 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     t2_hist_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.hist);
     count_launch();
     if ((rc = check_launch("t2_hist_kernel"))) return rc;
-    t2_tiles_kernel<<<1, 32, 0, st>>>(A.hist, cfg->nA, A.bin_start, A.cursor, A.tile_fa, A.tile_start, A.tile_cnt,
-                                      A.counters);
+    t2_tiles_kernel<<<1, 32, 0, st>>>(A.hist, cfg->nA, g.tile_big, g.tile_small, g.switch_off, A.bin_start, A.cursor,
+                                      A.tile_fa, A.tile_start, A.tile_cnt, A.counters);
     count_launch();
     if ((rc = check_launch("t2_tiles_kernel"))) return rc;
     t2_scatter_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);

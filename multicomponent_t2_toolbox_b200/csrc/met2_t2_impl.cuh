@@ -11,7 +11,8 @@
 
 namespace met2 {
 
-constexpr int T2_TILE = 256;
+constexpr int T2_TILE_MAX = 512;    // largest tile (voxels of one FA index handed to a CTA at once)
+constexpr int T2_TILE_MIN = 32;     // tail tiles
 
 struct T2Args {
     const double* sig;
@@ -549,6 +550,47 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     __syncwarp();
                     p = n;
                 };
+                // Brent methods (X2, GCV, BayesReg): the reference re-solves at the returned lambda = Brent's best
+                // abscissa xf, a point that was already evaluated.  The solution of that evaluation is kept in the
+                // (otherwise unused) L-curve arrays whenever xf moves, and handed out at the end instead of one more
+                // NNLS solve (same minimiser; MET2_T2_FLAG_COLD_START keeps the reference's extra solve).
+                int p_snap = 0;
+                double sse_snap = 0.0;
+                auto snapshot = [&](double sse_now) {
+#pragma unroll
+                    for (int tt = 0; tt < NS; ++tt) {
+                        const int i = lane + 32 * tt;
+                        if (i < p) {
+                            S[oLx + i] = S[W.xs + i];
+                            SI(oLy, i) = SI(W.ix, i);
+                        }
+                    }
+                    p_snap = p;
+                    sse_snap = sse_now;
+                };
+                auto restore = [&]() {
+                    __syncwarp();
+#pragma unroll
+                    for (int sidx = 0; sidx < NS; ++sidx) {
+                        const int col = NS * lane + sidx;
+                        if (col < n) S[W.xc + col] = 0.0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int tt = 0; tt < NS; ++tt) {
+                        const int i = lane + 32 * tt;
+                        if (i < p_snap) {
+                            const int ci = SI(oLy, i);
+                            const double xv = S[oLx + i];
+                            S[W.xs + i] = xv;
+                            SI(W.ix, i) = ci;
+                            S[W.xc + ci] = xv;
+                        }
+                    }
+                    p = p_snap;
+                    __syncwarp();
+                    (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
+                };
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
@@ -583,9 +625,19 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                                 lam = beta;
                                 stage = ST_FINAL;
                             }
-                        } else if (!B.feed(cost, lam)) {
-                            lam = B.xf;
-                            stage = ST_FINAL;
+                        } else {
+                            const double lam_eval = lam;
+                            const bool more = B.feed(cost, lam);
+                            if (warm && B.xf == lam_eval) snapshot(sse);
+                            if (!more) {
+                                lam = B.xf;
+                                stage = ST_FINAL;
+                                if (warm) {
+                                    restore();
+                                    regv = lam;
+                                    break;
+                                }
+                            }
                         }
                     } else if (method == MET2_REG_BAYESREG) {
                         // bayesian_interpolation.py:84-105
@@ -607,9 +659,17 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                             const double nrm = reg_norm2<NS>(W, oLb, n, lane);
                             const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
                                                                A.cfg.log_det_L, st, p);
-                            if (!B.feed(cost, lam)) {
+                            const double lam_eval = lam;
+                            const bool more = B.feed(cost, lam);
+                            if (warm && B.xf == lam_eval) snapshot(sse);
+                            if (!more) {
                                 lam = B.xf;
                                 stage = ST_FINAL;
+                                if (warm) {
+                                    restore();
+                                    regv = lam;
+                                    break;
+                                }
                             }
                         }
                     } else if (method == MET2_REG_X2) {
@@ -622,9 +682,18 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                             if (warm && (A.cfg.flags & MET2_T2_FLAG_FULL_START) && lam >= 1.0) full_set_start(lam);
                         } else {
                             const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
-                            if (!B.feed(cost, lam)) {
+                            const double lam_eval = lam;
+                            const bool more = B.feed(cost, lam);
+                            if (warm && B.xf == lam_eval) snapshot(sse);
+                            if (!more) {
                                 lam = B.xf;
                                 stage = ST_FINAL;
+                                if (warm) {
+                                    restore();
+                                    // k_est is what the orchestrator stores (motor...:141-143)
+                                    regv = (A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA) ? lam : sse_snap / SSE;
+                                    break;
+                                }
                             }
                         }
                     } else {   // L-curve grid
@@ -704,6 +773,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
 
 struct T2Geom {
     int grid, warps, pmax, max_tiles;
+    int tile_big, tile_small, switch_off;
     size_t smem;
 };
 
@@ -732,7 +802,23 @@ static inline T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
     int sms = sm_count();
     if (sms <= 0) sms = 148;
     g.grid = sms * per_sm;
-    g.max_tiles = (int)(V / T2_TILE) + cfg->nA + 1;
+    // guided self-scheduling of the tile list (t2_tiles_kernel): ~8 large tiles per CTA, then small tiles for the last
+    // ~12 % of the voxels; MET2_T2_TILE=<n> forces a uniform tile size (tuning / A-B runs)
+    long long big = V / ((long long)g.grid * 8);
+    big = (big + 31) & ~31LL;
+    if (big < 64) big = 64;
+    if (big > T2_TILE_MAX) big = T2_TILE_MAX;
+    g.tile_big = (int)big;
+    g.tile_small = T2_TILE_MIN;
+    g.switch_off = (int)(V - V / 8);
+    if (const char* ev = getenv("MET2_T2_TILE")) {
+        int t = atoi(ev);
+        if (t >= 1) {
+            g.tile_big = g.tile_small = t;
+            g.switch_off = (int)V;
+        }
+    }
+    g.max_tiles = (int)(V / g.tile_small) + cfg->nA + 1;
     return g;
 }
 

@@ -22,6 +22,17 @@ def slab_bounds(n_voxels, rank, world_size):
     return lo, hi
 
 
+def cyclic_slab(n_voxels, rank, world_size, chunk=2048):
+    """Block-cyclic alternative to `slab_bounds` (over-decomposition for load balance — the cost of a
+    voxel depends on its flip angle and spectrum, and both vary smoothly across the volume): chunks of `chunk`
+    consecutive voxels are dealt to the ranks round-robin.  Returns this rank's voxel indices (sorted, int64); the
+    ranks' index sets are disjoint and cover [0, n_voxels)."""
+    if world_size < 1 or not (0 <= rank < world_size) or chunk < 1:
+        raise ValueError("bad rank/world_size/chunk")
+    idx = np.arange(int(n_voxels), dtype=np.int64)
+    return idx[(idx // int(chunk)) % int(world_size) == rank]
+
+
 def masked_voxel_list(data, mask):
     """Apply the mask and the negative clamp like motor...:178-180,279 and return (flat voxel indices, signals[V,nTE])
     of the voxels with mask > 0, in C order of (x, y, z)."""

@@ -74,3 +74,14 @@ def test_slab_bounds_partition(V, W):
     assert max(sizes) - min(s for s in sizes if s > 0 or V == 0) <= max(sizes)  # contiguous, ceil-sized slabs
     with pytest.raises(ValueError):
         pipeline.slab_bounds(V, W, W)
+
+
+def test_cyclic_slab_partition():
+    from multicomponent_t2_toolbox_b200 import pipeline
+    for n, w in [(0, 2), (5, 3), (10000, 4), (552960, 8)]:
+        parts = [pipeline.cyclic_slab(n, r, w, chunk=2048) for r in range(w)]
+        allidx = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)
+        assert np.array_equal(np.sort(allidx), np.arange(n))
+        if n >= 2048 * w * 4:
+            sizes = [len(p) for p in parts]
+            assert max(sizes) - min(sizes) <= 2048
