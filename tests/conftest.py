@@ -37,3 +37,19 @@ def golden_config2():
     f[sup] = g["f_nz"]
     g["f"] = f
     return g
+
+
+@pytest.fixture(scope="session")
+def golden_methods(golden_config2):
+    """2 048 config-2 voxels fitted by the unmodified reference with the other methods (oracle/make_golden_methods.py)."""
+    import numpy as np
+    g = dict(np.load(os.path.join(GOLDEN, "methods_subset.npz")))
+    g["sig"] = np.ascontiguousarray(golden_config2["sig"][::int(g["stride"])])
+
+    def spectrum(key, npc):
+        sup = np.unpackbits(g[key + "_support"], axis=1)[:, :npc].astype(bool)
+        f = np.zeros(sup.shape)
+        f[sup] = g[key + "_fnz"]
+        return f
+    g["spectrum"] = spectrum
+    return g

@@ -350,3 +350,53 @@ def test_config3b_gcv_lambda_grid_and_half_degree_fa(phantom_sig):
     assert _rel_err(f[same], f_ref[same]).max() < REL_SPECTRUM
     assert np.abs(t2["maps"].cpu().numpy()[same, 0] - _metrics(f_ref[same], plan)[:, 0]).max() < ABS_MAPS
     assert not t2["status"].cpu().numpy().any()
+
+
+METHOD_CASES = [("NNLS", "I", "brute-force", 60), ("L_curve", "I", "spline", 60), ("BayesReg", "I", "spline", 60),
+                ("X2", "L2", "spline", 60), ("T2SPARC", "InvT2", "spline", 96), ("GCV", "L2", "brute-force", 60)]
+
+
+def test_methods_subset_vs_reference(golden_methods):
+    """Parity at scale for the other regularisation methods: 2 048 config-2 voxels fitted by the UNMODIFIED reference
+    (tests/golden/methods_subset.npz).  FA indices bit-exact; active sets: disagreement rate reported and bounded;
+    spectra 1e-6 / maps 1e-4 on the agreeing voxels.  GCV is statistical.  The measured rates go to
+    gpurun_out/parity_methods_subset.json."""
+    import json
+    import os
+    g = golden_methods
+    sig = g["sig"]
+    V = sig.shape[0]
+    rec = {}
+    for method, rm, fam, npc in METHOD_CASES:
+        key = "%s_%s" % (method, rm)
+        plan = _plan(reg_method=method, reg_matrix=rm, FA_method=fam, npc=npc)
+        fa, t2 = plan.fit(sig)
+        idx_ref = g["fa_%s_%d" % (fam, npc)].astype(np.int64)
+        fa_bad = fa["fa_index"].cpu().numpy() != idx_ref
+        f, f_ref = t2["fsol"].cpu().numpy(), g["spectrum"](key, npc)
+        sup_bad = np.any((f > 0) != (f_ref > 0), axis=1)
+        rel = _rel_err(f, f_ref)
+        mwf_ref = _metrics(f_ref, plan)[:, 0]
+        dmwf = np.abs(t2["maps"].cpu().numpy()[:, 0] - mwf_ref)
+        dreg = np.abs(t2["reg"].cpu().numpy() - g[key + "_reg"]) / np.maximum(np.abs(g[key + "_reg"]), 1e-300)
+        good = ~(fa_bad | sup_bad)
+        r = dict(voxels=int(V), fa_method=fam, fa_index_mismatches=int(fa_bad.sum()),
+                 active_set_disagreements=int(sup_bad.sum()),
+                 spectrum_rel_err_max_agreeing=float(rel[good].max()), spectrum_rel_err_over_1e6=int((rel > 1e-6).sum()),
+                 reg_rel_err_max_agreeing=float(dreg[good].max()) if method != "NNLS" else 0.0,
+                 max_abs_dMWF_agreeing=float(dmwf[good].max()), max_abs_dMWF_all=float(dmwf.max()),
+                 frac_dMWF_below_1e4=float((dmwf < ABS_MAPS).mean()), status_nonzero=int((t2["status"] != 0).sum()))
+        rec[key] = r
+    outdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(outdir, exist_ok=True)
+    with open(os.path.join(outdir, "parity_methods_subset.json"), "w") as fh:
+        json.dump(rec, fh, indent=1)
+    for key, r in rec.items():
+        assert r["fa_index_mismatches"] == 0 and r["status_nonzero"] == 0, (key, r)
+        if key.startswith("GCV"):
+            assert r["frac_dMWF_below_1e4"] > 0.85, (key, r)      # reference self-agreement under 1e-13 noise: ~96 %
+            continue
+        assert r["active_set_disagreements"] <= 2, (key, r)        # <= 1e-3 of the voxels
+        tol = 1e-5 if key.startswith("BayesReg") else REL_SPECTRUM  # flat evidence curve: see LOOSE above
+        assert r["spectrum_rel_err_max_agreeing"] < tol, (key, r)
+        assert r["max_abs_dMWF_agreeing"] < ABS_MAPS and r["max_abs_dMWF_all"] < 1e-2, (key, r)
