@@ -268,6 +268,70 @@ __device__ __forceinline__ double fit_and_sse(const Slots<NS>& W, const double* 
     return warp_sum(s);
 }
 
+// One step of iterative refinement of a PLAIN (unregularised) least-squares solution on its final positive set, with
+// the residual evaluated in D-space ("corrected semi-normal equations"): r = M - D_P x, x += T T^T (D_P^T r).
+// The Gram-domain solve squares the condition number of D_P (up to ~1e5 for 4-6 EPG columns), which leaves ~1e-6
+// relative error in the worst voxels — the size of the parity tolerance; the reference's QR-based Lawson-Hanson does not
+// have that loss.  One refinement step brings the solution to the D-space accuracy.  The step is skipped if it would
+// make a coefficient non-positive (the active set is the solver's decision, not the refinement's).
+// oR: scratch of m doubles in shared memory.
+template <int NS, int ME>
+__device__ __forceinline__ void refine_plain(const Slots<NS>& W, const double* __restrict__ Dt, int oM, int oR, int m,
+                                             int p, int lane) {
+    double fit[ME];
+    (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        const int e = lane + 32 * u;
+        if (e < m) S[oR + e] = S[oM + e] - fit[u];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < p) {
+            const double* d = Dt + SI(W.ix, i) * m;
+            double a0 = 0.0, a1 = 0.0;
+            int e = 0;
+#pragma unroll 1
+            for (; e + 1 < m; e += 2) {
+                a0 = fma(__ldg(d + e), S[oR + e], a0);
+                a1 = fma(__ldg(d + e + 1), S[oR + e + 1], a1);
+            }
+            if (e < m) a0 = fma(__ldg(d + e), S[oR + e], a0);
+            S[W.gs + i] = a0 + a1;
+        }
+    }
+    __syncwarp();
+    double y[NS], dz[NS];
+    tmul_transposed<NS>(W.T, W.gs, p, lane, y);
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < p) S[W.rs + i] = y[t];
+    }
+    __syncwarp();
+    tmul<NS>(W.T, W.rs, p, lane, dz);
+    bool ok = true;
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < p && !(S[W.xs + i] + dz[t] > 0.0)) ok = false;
+    }
+    if (__all_sync(FULL_MASK, ok)) {
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            const int i = lane + 32 * t;
+            if (i < p) {
+                const double xn = S[W.xs + i] + dz[t];
+                S[W.xs + i] = xn;
+                S[W.xc + SI(W.ix, i)] = xn;
+            }
+        }
+    }
+    __syncwarp();
+}
+
 // sum_r ((L x)_r)^2 with L in 5-band row form S[oLb + d*n + r] = L[r][r+d-2]; x in column space (S[W.xc..]).
 template <int NS>
 __device__ __forceinline__ double reg_norm2(const Slots<NS>& W, int oLb, int n, int lane) {

@@ -595,6 +595,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
                                             warm ? p : 0);
+                    if (method == MET2_REG_NNLS && nst == 0 && p > 0) refine_plain<NS, ME>(W, Dt, oM, oLx, m, p, lane);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                     if (stage == ST_FINAL) {
                         if (method == MET2_REG_GCV && (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL)) {
