@@ -107,7 +107,7 @@ __device__ __forceinline__ void compute_c(const Slots<NS>& W, const double* __re
     const bool vec = ((n & 1) == 0);
     int e = 0;
     if (nvalid > 0) {
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
         for (; e + 1 < m; e += 2) {
             const double m0 = S[oM + e], m1 = S[oM + e + 1];
             double v0[NS], v1[NS];
@@ -145,7 +145,7 @@ __device__ __forceinline__ void compute_c_sh(const Slots<NS>& W, int oD, int oM,
     if (col0 < n) {
         const bool vec = ((n & 1) == 0) && (col0 + NS <= n);
         int e = 0;
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
         for (; e + 1 < m; e += 2) {
             const double m0 = S[oM + e], m1 = S[oM + e + 1];
             double v0[NS], v1[NS];
@@ -188,7 +188,7 @@ __device__ __forceinline__ double fit_and_sse_sh(const Slots<NS>& W, int oDt, in
 #pragma unroll
     for (int u = 0; u < ME; ++u) fit[u] = f1[u] = 0.0;
     int k = 0;
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
     for (; k + 1 < p; k += 2) {
         const int d0 = oDt + SI(W.ix, k) * m, d1 = oDt + SI(W.ix, k + 1) * m;
         const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
@@ -232,7 +232,7 @@ __device__ __forceinline__ double fit_and_sse(const Slots<NS>& W, const double* 
 #pragma unroll
     for (int u = 0; u < ME; ++u) fit[u] = f1[u] = 0.0;
     int k = 0;
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
     for (; k + 1 < p; k += 2) {
         const double* d0 = Dt + SI(W.ix, k) * m;
         const double* d1 = Dt + SI(W.ix, k + 1) * m;

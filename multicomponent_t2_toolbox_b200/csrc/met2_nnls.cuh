@@ -27,6 +27,20 @@ extern __shared__ __align__(16) double S[];   // the dynamic shared memory of ev
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// Unroll factor of the runtime-trip mat-vec loops.  The kernels with ten or more resident warps per SM (nT2 <= 64) and
+// the 16-warp FA search are bound by instruction fetch — compact loops measured faster
+// (profiles/r01_t2_fit_v8_ncu_summary.txt).  A translation unit whose kernels run with three or four warps per SM
+// (T2SPARC's 96 T2 bins) has nothing to hide latency with but instruction-level parallelism and may ask for unrolled
+// loops from NS = MET2_UNROLL_WIDE_NS on (measured: T2SPARC 319 -> 281 ms per volume; the same switch slowed the FA
+// search down, 138 -> 250 ms, which is why it is per translation unit).
+#ifndef MET2_UNROLL_WIDE_NS
+#define MET2_UNROLL_WIDE_NS 99
+#endif
+template <int NS>
+struct Unroll {
+    static constexpr int v = (NS >= MET2_UNROLL_WIDE_NS) ? 4 : 1;
+};
+
 __host__ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
 __host__ __device__ __forceinline__ size_t align_up256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -152,7 +166,7 @@ __device__ __forceinline__ void tmul_transposed(int oT, int oV, int p, int lane,
         kmax[t] = (i < p) ? i : -1;
     }
     int k = 0;
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
     for (; k + 1 < p; k += 2) {
         const double v0 = S[oV + k], v1 = S[oV + k + 1];
 #pragma unroll
@@ -185,7 +199,7 @@ __device__ __forceinline__ void tmul(int oT, int oV, int p, int lane, double (&o
     for (int t = 0; t < NS; ++t) a0[t] = a1[t] = 0.0;
     int i = 0;
     int t0 = oT;
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
     for (; i + 1 < p; i += 2) {
         const double v0 = S[oV + i], v1 = S[oV + i + 1];
         const int t1 = t0 + i + 1;
@@ -474,7 +488,7 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
         int rr = lane + 32 * t;
         carry[t] = (rr < k) ? S[oT + tri(k) + rr] : 0.0;
     }
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
     for (int q = k; q + 1 < p; ++q) {
         const double c = S[W.gs + q], s = S[W.rs + q];
         const int tq1 = oT + tri(q + 1), tq = oT + tri(q);
@@ -651,7 +665,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             if (GSH) {
                 // rows of G in shared memory: one vector LDS per row and lane (columns NS*lane .. NS*lane+NS-1)
                 const bool live = col0 < n;
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
                 for (; k + 1 < p; k += 2) {
                     const int r0 = oG + SI(W.ix, k) * ldg + col0, r1 = oG + SI(W.ix, k + 1) * ldg + col0;
                     const double x0 = S[W.xs + k], x1 = S[W.xs + k + 1];
@@ -679,7 +693,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             } else {
                 const bool vec = ((ldg & 1) == 0);
                 const int nvalid = n - col0;   // columns this lane really owns (<= 0: none)
-#pragma unroll 1
+#pragma unroll (Unroll<NS>::v)
                 for (; k + 1 < p; k += 2) {
                     const double* g0 = Gg + SI(W.ix, k) * ldg + col0;
                     const double* g1 = Gg + SI(W.ix, k + 1) * ldg + col0;

@@ -409,7 +409,7 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
 
 // ---------------------------------------------------------------------------------------------- fit kernel
 // shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
-// then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64]
+// then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64 | Brent-best snapshot 48 NS]
 __host__ __device__ __forceinline__ int t2_ldg(int n) { return (n + 1) & ~1; }   // even row stride: 16-byte aligned rows
 __host__ __device__ __forceinline__ int t2_table_doubles(int n) {
     return (n * t2_ldg(n) + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
@@ -417,7 +417,8 @@ __host__ __device__ __forceinline__ int t2_table_doubles(int n) {
 
 template <int NS>
 __host__ __device__ __forceinline__ int t2_warp_doubles(int pmax) {
-    return (Slots<NS>::doubles(pmax) + 64 + 128 + 31) & ~31;
+    // + signal (64) + the L-curve curves (2 x 64), which double as the Brent-best snapshot (x: 32 NS, ix: 16 NS)
+    return (Slots<NS>::doubles(pmax) + 64 + (48 * NS > 128 ? 48 * NS : 128) + 31) & ~31;
 }
 
 constexpr int T2_MAX_THREADS = 320;
@@ -556,13 +557,14 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 // NNLS solve (same minimiser; MET2_T2_FLAG_COLD_START keeps the reference's extra solve).
                 int p_snap = 0;
                 double sse_snap = 0.0;
+                const int oSx = oLx, oSi = oLx + 32 * NS;   // x [32 NS doubles], ix [32 NS ints]
                 auto snapshot = [&](double sse_now) {
 #pragma unroll
                     for (int tt = 0; tt < NS; ++tt) {
                         const int i = lane + 32 * tt;
                         if (i < p) {
-                            S[oLx + i] = S[W.xs + i];
-                            SI(oLy, i) = SI(W.ix, i);
+                            S[oSx + i] = S[W.xs + i];
+                            SI(oSi, i) = SI(W.ix, i);
                         }
                     }
                     p_snap = p;
@@ -580,8 +582,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     for (int tt = 0; tt < NS; ++tt) {
                         const int i = lane + 32 * tt;
                         if (i < p_snap) {
-                            const int ci = SI(oLy, i);
-                            const double xv = S[oLx + i];
+                            const int ci = SI(oSi, i);
+                            const double xv = S[oSx + i];
                             S[W.xs + i] = xv;
                             SI(W.ix, i) = ci;
                             S[W.xc + ci] = xv;

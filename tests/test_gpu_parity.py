@@ -400,3 +400,35 @@ def test_methods_subset_vs_reference(golden_methods):
         tol = 1e-5 if key.startswith("BayesReg") else REL_SPECTRUM  # flat evidence curve: see LOOSE above
         assert r["spectrum_rel_err_max_agreeing"] < tol, (key, r)
         assert r["max_abs_dMWF_agreeing"] < ABS_MAPS and r["max_abs_dMWF_all"] < 1e-2, (key, r)
+
+
+def test_config4_sizes_48_echoes_100_bins():
+    """BASELINE.json configs[3]: nTE = 48, 100 T2 bins (NS = 4 / ME = 2 kernel instantiations), BayesReg + InvT2,
+    brute-force FA — a 32-voxel slice against the oracle, plus X2 / L_curve / GCV on the same sizes (active sets and
+    spectra vs the oracle for X2; status and finiteness for the others)."""
+    ph = make_phantom((8, 4, 1), n_echoes=48, tau=8.0, seed=4)
+    sig = ph["data"].reshape(-1, 48)
+    V = sig.shape[0]
+    plan = batched.Met2Plan(48, 8.0, 1000.0, reg_method="BayesReg", reg_matrix="InvT2", FA_method="brute-force", npc=100)
+    fa, t2 = plan.fit(sig)
+    Dic = plan.dict_hr.to_reference_layout()
+    ok = np.ones(V)
+    FA, idx, KM, _ = O.fitting_slice_FA_brute_force(ok, sig, V, Dic, plan.alpha_values)
+    assert np.array_equal(fa["fa_index"].cpu().numpy(), idx.astype(np.int64))
+    f_ref, s_ref, reg_ref = O.fitting_slice_T2(ok, sig, idx, V, Dic, plan.lambda_reg, 100, 48, "BayesReg", plan.Laplac)
+    f = t2["fsol"].cpu().numpy()
+    assert np.array_equal(f > 0, f_ref > 0)
+    assert _rel_err(f, f_ref).max() < 1e-3                      # BayesReg + InvT2: see LOOSE
+    assert np.abs(t2["maps"].cpu().numpy()[:, :3] - _metrics(f_ref, plan)[:, :3]).max() < ABS_MAPS
+    assert not t2["status"].cpu().numpy().any()
+    px = batched.Met2Plan(48, 8.0, 1000.0, reg_method="X2", reg_matrix="I", FA_method="brute-force", npc=100)
+    tx = px.t2_fit(sig, fa["fa_index"])
+    fx_ref, _, regx_ref = O.fitting_slice_T2(ok, sig, idx, V, Dic, px.lambda_reg, 100, 48, "X2", px.Laplac)
+    fx = tx["fsol"].cpu().numpy()
+    assert np.array_equal(fx > 0, fx_ref > 0) and _rel_err(fx, fx_ref).max() < REL_SPECTRUM
+    assert np.allclose(tx["reg"].cpu().numpy(), regx_ref, rtol=1e-6, atol=0)
+    for method, rm in (("L_curve", "L2"), ("GCV", "I"), ("T2SPARC", "InvT2"), ("NNLS", "I")):
+        pm = batched.Met2Plan(48, 8.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method="brute-force", npc=100)
+        tm = pm.t2_fit(sig, fa["fa_index"])
+        assert not tm["status"].cpu().numpy().any(), method
+        assert np.isfinite(tm["fsol"].cpu().numpy()).all() and (tm["maps"].cpu().numpy()[:, 0] >= 0).all(), method

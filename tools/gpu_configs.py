@@ -17,7 +17,7 @@ def timed(plan, sig, reps=2):
         best = r if best is None or sum(r) < sum(best) else best
     return fa, t2, best
 
-which = os.environ.get("WHICH", "1,4,5a,5b,3a").split(",")
+which = os.environ.get("WHICH", "1,4,5a,5b,3a,3b,2x").split(",")
 if "1" in which:
     ph = make_phantom((16, 16, 4), seed=1); sig = torch.as_tensor(ph["data"].reshape(-1, 32)).cuda()
     plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="NNLS", reg_matrix="I", FA_method="brute-force")
@@ -64,4 +64,26 @@ if "3a" in which:
     fa, t2, (a, b) = timed(plan, sig, reps=1)
     out["config3a"] = dict(V=V, fa_ms=a, t2_ms=b, vox_per_s=V / ((a + b) * 1e-3), status_nonzero=int((t2["status"] != 0).sum()))
     print("config3a", out["config3a"], flush=True)
+if "3b" in which:
+    # config 3 as BASELINE.json words it (extension): GCV objective on the 49-point positive lambda grid, FA brute force
+    # over 0.5 degree steps (181 angles)
+    ph = make_phantom((96, 96, 60), seed=3, fa_mode="b1", backend="gpu")
+    sig = torch.as_tensor(ph["data"].reshape(-1, 32)).cuda(); V = sig.shape[0]
+    plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="GCV", reg_matrix="L2", FA_method="brute-force", n_alphas=181,
+                            t2_flags=batched.GCV_GRID)
+    fa, t2, (a, b) = timed(plan, sig, reps=1)
+    out["config3b"] = dict(V=V, n_alphas=181, n_lambdas=49, fa_ms=a, t2_ms=b, vox_per_s=V / ((a + b) * 1e-3),
+                           status_nonzero=int((t2["status"] != 0).sum()))
+    print("config3b", out["config3b"], flush=True)
+if "2x" in which:
+    # T2 stage of every method on the config-2 volume (FA spline)
+    ph = make_phantom((96, 96, 60), seed=2, fa_mode="b1", backend="gpu")
+    sig = torch.as_tensor(ph["data"].reshape(-1, 32)).cuda(); V = sig.shape[0]
+    for method, rm in [("NNLS", "I"), ("T2SPARC", "InvT2"), ("X2", "I"), ("X2", "L2"), ("L_curve", "I"), ("BayesReg", "I"), ("GCV", "I")]:
+        plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method="spline")
+        fa, t2, (a, b) = timed(plan, sig, reps=2)
+        out["config2_%s_%s" % (method, rm)] = dict(V=V, npc=plan.npc, fa_ms=a, t2_ms=b, vox_per_s=V / ((a + b) * 1e-3),
+                                                   status_nonzero=int((t2["status"] != 0).sum()))
+        print(method, rm, out["config2_%s_%s" % (method, rm)], flush=True)
+        del t2, plan
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
