@@ -253,27 +253,37 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N
                 SI(W.gs + 3 * lane + 2, 1) = qq;
             }
             __syncwarp();
-            // ---- columns: H <- H J   (lane = row r; N <= 32)
-            if (lane < N) {
-                for (int i = 0; i < half; ++i) {
+            // ---- columns: H <- H J.  Two rotations per pass: half-warp `sub` takes pair i0 + sub, its 16 lanes the rows
+            //      (N <= 20, so at most two rows per lane); the pairs of a round touch disjoint columns
+            const int sub = lane >> 4, l16 = lane & 15;
+            for (int i0 = 0; i0 < half; i0 += 2) {
+                const int i = i0 + sub;
+                if (i < half) {
                     const int p2 = SI(W.gs + 3 * i + 2, 0), q2 = SI(W.gs + 3 * i + 2, 1);
-                    if (p2 < 0) continue;
-                    const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
-                    const double xv = S[oA + lane * LD + p2], yv = S[oA + lane * LD + q2];
-                    S[oA + lane * LD + p2] = ci * xv - si * yv;
-                    S[oA + lane * LD + q2] = si * xv + ci * yv;
+                    if (p2 >= 0) {
+                        const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                        for (int r = l16; r < N; r += 16) {
+                            const double xv = S[oA + r * LD + p2], yv = S[oA + r * LD + q2];
+                            S[oA + r * LD + p2] = ci * xv - si * yv;
+                            S[oA + r * LD + q2] = si * xv + ci * yv;
+                        }
+                    }
                 }
             }
             __syncwarp();
-            // ---- rows: H <- J^T H   (lane = column)
-            if (lane < N) {
-                for (int i = 0; i < half; ++i) {
+            // ---- rows: H <- J^T H   (16 lanes = columns)
+            for (int i0 = 0; i0 < half; i0 += 2) {
+                const int i = i0 + sub;
+                if (i < half) {
                     const int p2 = SI(W.gs + 3 * i + 2, 0), q2 = SI(W.gs + 3 * i + 2, 1);
-                    if (p2 < 0) continue;
-                    const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
-                    const double xv = S[oA + p2 * LD + lane], yv = S[oA + q2 * LD + lane];
-                    S[oA + p2 * LD + lane] = ci * xv - si * yv;
-                    S[oA + q2 * LD + lane] = si * xv + ci * yv;
+                    if (p2 >= 0) {
+                        const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                        for (int cc = l16; cc < N; cc += 16) {
+                            const double xv = S[oA + p2 * LD + cc], yv = S[oA + q2 * LD + cc];
+                            S[oA + p2 * LD + cc] = ci * xv - si * yv;
+                            S[oA + q2 * LD + cc] = si * xv + ci * yv;
+                        }
+                    }
                 }
             }
             __syncwarp();
