@@ -338,8 +338,10 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
             S[AUG(g, 8 + 2 * q + 1)] = (2 * q + 1 == g) ? 1.0 : 0.0;
             __syncwarp();
             const int r = g, cg = 4 * q;   // this lane updates Aug[r][cg .. cg+3]
+            // rows beyond the set (virtual identity rows of a partial last block) need no elimination
+            const int nv = (p - c0 < 8) ? (p - c0) : 8;
 #pragma unroll 1
-            for (int k = 0; k < 7; ++k) {
+            for (int k = 0; k < nv - 1; ++k) {
                 const double d = S[AUG(k, k)];
                 if (!(d > 0.0)) ok = false;
                 if (r > k) {
@@ -352,7 +354,7 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
                 }
                 __syncwarp();
             }
-            if (!(S[AUG(7, 7)] > 0.0)) ok = false;
+            if (!(S[AUG(nv - 1, nv - 1)] > 0.0)) ok = false;
             // T_JJ (row-major 8 x 8) -> S[W.rs ..]; Aug overlaps rs, so gather into registers first
             const int c = lane & 7;
             const double ric = rsqrt_fast(S[AUG(c, c)]);
