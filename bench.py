@@ -338,9 +338,9 @@ def run_ours(args):
 
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one t2_fit_kernel launch on this workload, from the committed
-    ncu capture (profiles/r01_t2_fit_v7_fullsize_counters.json); None if the record is missing."""
+    ncu capture (profiles/r01_t2_fit_v10_fullsize_counters.json); None if the record is missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v7_fullsize_counters.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v10_fullsize_counters.json")) as fh:
             return json.load(fh)["traffic_bytes"]
     except Exception:
         return None
