@@ -195,6 +195,7 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     shape = SHAPE if args.shape is None else tuple(int(x) for x in args.shape.split(","))
     lib = _lib.load()
