@@ -193,9 +193,14 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_fd = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout for the one JSON line
+        # NCCL prints its version banner on stdout at communicator creation: point fd 1 at stderr for the duration of
+        # the run and keep the original stdout for the one JSON line
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     shape = SHAPE if args.shape is None else tuple(int(x) for x in args.shape.split(","))
     lib = _lib.load()
@@ -330,7 +335,10 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": nvox / dt, "unit": UNIT, "cores": _CPU_STATE["cores"], "kind": "port",
                                     "sample": "%d voxels (96x192x1 slab of the config-2 phantom), %.1f s" % (nvox, dt)}
             _CPU_STATE["pool"].close()
-        print(json.dumps(line), flush=True)
+        if json_fd is None:
+            print(json.dumps(line), flush=True)
+        else:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
