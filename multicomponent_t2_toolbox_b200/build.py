@@ -62,5 +62,20 @@ def build_library(force=False, verbose=False):
     return LIB_PATH
 
 
+EXAMPLE_SRC = os.path.join(PKG_DIR, "..", "examples", "c_host", "met2_host_demo.cpp")
+EXAMPLE_BIN = os.path.join(PKG_DIR, "..", "examples", "c_host", "met2_host_demo")
+
+
+def build_c_host_example():
+    """Compile the C-ABI-only host program (examples/c_host) against libmet2.so.  Returns the binary path."""
+    nvcc = _nvcc()
+    cmd = [nvcc, "-std=c++17", "-O2", "-I", os.path.join(PKG_DIR, "..", "include"), EXAMPLE_SRC, "-L", PKG_DIR, "-lmet2",
+           "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN/../../multicomponent_t2_toolbox_b200", "-o", EXAMPLE_BIN]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed on the C host example:\n%s" % r.stderr[-4000:])
+    return EXAMPLE_BIN
+
+
 if __name__ == "__main__":
     print(build_library(force=True, verbose=True))

@@ -55,3 +55,29 @@ def test_argument_validation_without_gpu():
 def test_product_path_fails_loudly_without_cuda():
     with pytest.raises(_lib.Met2Error):
         batched.Met2Plan(32, 10.0, 1000.0)
+
+
+def _c_host_binary():
+    from multicomponent_t2_toolbox_b200 import build
+    if not os.path.exists(build.EXAMPLE_BIN):
+        build.build_c_host_example()
+    return build.EXAMPLE_BIN
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
+def test_c_host_program_links_and_fails_loudly_without_cuda():
+    """examples/c_host: a C++ program on the C ABI alone (no Python, no torch).  Without a GPU it must load libmet2.so,
+    report the ABI version and stop with an error — not compute anything on the CPU."""
+    import subprocess
+    r = subprocess.run([_c_host_binary()], capture_output=True, text=True, timeout=120)
+    assert "met2 C-ABI version 100" in r.stdout
+    assert r.returncode != 0 and ("error" in r.stderr.lower())
+
+
+@pytest.mark.gpu
+def test_c_host_program_runs_the_path_through_the_c_abi():
+    """Dictionary -> FA brute force -> X2 fit + maps driven from C++ through include/met2.h only, with self-checks."""
+    import subprocess
+    r = subprocess.run([_c_host_binary()], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.strip().endswith("OK") and " 0/256 wrong" in r.stdout
