@@ -155,7 +155,7 @@ int main() {
             !(m[0] > 0.05 && m[0] < 0.3))
             ++bad_map;                                         // fractions sum to ~1 (bins at 40/200 ms count once/twice), TWC = sum f
     }
-    std::printf("FA index: %d/%d wrong; fit: %d voxels with relative residual > 1e-3; maps: %d inconsistent\n", bad_idx,
+    std::printf("FA index: %d/%d wrong; fit: %d voxels with relative residual > 5e-3; maps: %d inconsistent\n", bad_idx,
                 V - 1, bad_fit, bad_map);
     std::printf("voxel 1: FA %d (true %d), MWF %.4f, k_est %.4f; kernel launches so far: %lld\n", idx[1], a_true[1],
                 maps[6], reg[1], (long long)met2_launch_count());
