@@ -432,3 +432,30 @@ def test_config4_sizes_48_echoes_100_bins():
         tm = pm.t2_fit(sig, fa["fa_index"])
         assert not tm["status"].cpu().numpy().any(), method
         assert np.isfinite(tm["fsol"].cpu().numpy()).all() and (tm["maps"].cpu().numpy()[:, 0] >= 0).all(), method
+
+
+def test_scale_covariance_and_degenerate_signals(phantom_sig):
+    """Size-independent properties: the fit is covariant under signal scaling — fit(c M) = c fit(M) with
+    identical FA index, support and k_est — across 12 orders of magnitude; an exactly representable signal (plain-NNLS
+    residual 0) is flagged MET2_ST_SSE_ZERO instead of propagating the reference's NaN (algorithms.py:231)."""
+    sig = phantom_sig[:128]
+    plan = _plan(reg_method="X2", reg_matrix="I", FA_method="spline")
+    fa0, t0 = plan.fit(sig)
+    f0 = t0["fsol"].cpu().numpy()
+    for c in (2.0 ** -20, 2.0 ** 20):          # powers of two: scaling is exact in floating point
+        fa1, t1 = plan.fit(sig * c)
+        assert torch.equal(fa1["fa_index"], fa0["fa_index"])
+        f1 = t1["fsol"].cpu().numpy()
+        assert np.array_equal(f1 > 0, f0 > 0)
+        assert np.allclose(f1, c * f0, rtol=1e-9, atol=0)
+        assert np.allclose(t1["reg"].cpu().numpy(), t0["reg"].cpu().numpy(), rtol=1e-9, atol=0)
+        assert np.allclose(t1["maps"].cpu().numpy()[:, :5], t0["maps"].cpu().numpy()[:, :5], rtol=0, atol=1e-9)
+    D = plan.dict_hr.to_reference_layout()
+    exact = np.stack([1000.0 * D[:, 30, 200], 500.0 * D[:, 12, 100]])
+    idx = np.array([200, 100], dtype=np.int32)
+    out = plan.t2_fit(exact, idx)
+    st = out["status"].cpu().numpy()
+    rs = out["fsol"].cpu().numpy()
+    assert np.isfinite(rs).all() and np.isfinite(out["maps"].cpu().numpy()).all()
+    # either the residual is exactly zero (flagged) or it is at rounding level and the fit went through
+    assert all((s & batched.ST_SSE_ZERO) or s == 0 for s in st)
