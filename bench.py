@@ -322,6 +322,12 @@ def run_ours(args):
                              "note": "FP64 DFMA-issue bound, not HBM/tensor (SURVEY.md 8d); achieved = algorithmic "
                                      "(reference-formulation) flops/voxel x voxels / kernel time; peak = own DFMA "
                                      "microbench (MEASURED_PEAKS.json has no FP64 entry)",
+                             "executed_tflops": (_ncu_executed_flops_per_voxel() or 0.0) * V / t2_s / 1e12
+                             if shape == SHAPE else None,
+                             "executed_note": "flops the Gram-domain, warm-started kernel really executes (ncu "
+                                              "counters of the same launch): ~14x fewer than the reference "
+                                              "formulation's F_alg, so FP64-pipe utilisation is ~5 % of peak; the "
+                                              "kernel is latency/issue bound at 10 warps per SM (DESIGN.md 4)",
                              "hbm_achieved_gbs": HBM_BYTES_PER_VOXEL * V / t2_s / 1e9,
                              "hbm_peak_gbs": _hbm_peak()},
                 "one_volume": {"ms": one_ms, "voxels": V, "gpus": world,
@@ -343,6 +349,16 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _ncu_executed_flops_per_voxel():
+    """FP64 flops per voxel the t2_fit_kernel actually EXECUTES on this workload (2 x DFMA + DADD + DMUL thread
+    instructions, same ncu capture as `_ncu_traffic`); None if the record is missing."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v10_fullsize_counters.json")) as fh:
+            return json.load(fh)["executed_fp64_flops_per_voxel"]
+    except Exception:
+        return None
 
 
 def _ncu_traffic():
