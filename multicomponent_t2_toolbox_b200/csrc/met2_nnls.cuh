@@ -538,7 +538,8 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
 // lambda/k_est within 1e-11 against SciPy's cold-started path, with 13x fewer main-loop iterations.
 template <int NS, bool GSH>
 __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
-                                         bool reg, double lam, int n, int mrows, int lane, int& status, int p0 = 0) {
+                                         bool reg, double lam, int n, int mrows, int lane, int& status, int p0 = 0,
+                                         bool t_ready = false) {
     const int itmax = 3 * n;
     auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * ldg + c] : __ldg(Gg + r * ldg + c); };
     const int col0 = NS * lane;
@@ -632,7 +633,9 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             }
             return a;
         };
-        const bool good = rebuild_T_blocked<NS>(W, Aent, p0, lane);
+        // t_ready: the caller already placed the factor of this set and lambda in the T region (shared full-set
+        // factor tables of the X2 driver)
+        const bool good = t_ready ? true : rebuild_T_blocked<NS>(W, Aent, p0, lane);
         if (good) {
             p = p0;
 #pragma unroll 1

@@ -74,6 +74,23 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
     return MET2_OK;
 }
 
+static bool t2_uses_full_tables(const met2_t2_cfg* cfg) {
+    return cfg->method == MET2_REG_X2 && (cfg->flags & MET2_T2_FLAG_FULL_START) && !(cfg->flags & MET2_T2_FLAG_COLD_START);
+}
+
+template <int NS>
+static int t2_launch_full_factors(const T2Args& A, const double* G, const double* kband, double* tfull, double* lam_tab,
+                                  cudaStream_t st) {
+    const int n = A.cfg.nT2;
+    const size_t smem = sizeof(double) * (size_t)Slots<NS>::doubles(n);
+    cudaError_t e = cudaFuncSetAttribute(t2_full_factors_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_full_factors attr: %s", cudaGetErrorString(e));
+    t2_full_factors_kernel<NS><<<T2_NTAB * A.cfg.nA, 32, smem, st>>>(G, kband, n, A.cfg.nA, A.cfg.brent_lo, A.cfg.brent_hi,
+                                                                     A.cfg.brent_xatol, A.cfg.maxfun, tfull, lam_tab);
+    count_launch();
+    return check_launch("t2_full_factors_kernel");
+}
+
 extern "C" int64_t met2_t2_workspace_bytes(int64_t V, const met2_t2_cfg* cfg) {
     if (t2_check_cfg(cfg) || V < 0) return -1;
     T2Geom g = t2_geometry_any(V, cfg);
@@ -83,6 +100,8 @@ extern "C" int64_t met2_t2_workspace_bytes(int64_t V, const met2_t2_cfg* cfg) {
     b += align256(sizeof(int) * (size_t)V);
     b += align256(sizeof(int) * (size_t)g.max_tiles) * 3;
     b += align256(sizeof(int) * 4);
+    if (t2_uses_full_tables(cfg))
+        b += align256(sizeof(double) * 8) + align256(sizeof(double) * (size_t)T2_NTAB * cfg->nA * tri(cfg->nT2));
     return (int64_t)b + 256;
 }
 
@@ -115,9 +134,27 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     A.tile_fa = reinterpret_cast<int*>(w);     w += align256(sizeof(int) * (size_t)g.max_tiles);
     A.tile_start = reinterpret_cast<int*>(w);  w += align256(sizeof(int) * (size_t)g.max_tiles);
     A.tile_cnt = reinterpret_cast<int*>(w);    w += align256(sizeof(int) * (size_t)g.max_tiles);
-    A.counters = reinterpret_cast<int*>(w);
+    A.counters = reinterpret_cast<int*>(w);  w += align256(sizeof(int) * 4);
     A.pmax = g.pmax;
     A.warps = g.warps;
+    A.tfull = nullptr;
+    A.lam_tab = nullptr;
+    A.ntab_use = T2_NTAB;
+    if (const char* ev = getenv("MET2_T2_NTAB")) {   // tuning / A-B runs
+        const int t = atoi(ev);
+        if (t >= 0 && t < T2_NTAB) A.ntab_use = t;
+    }
+    if (t2_uses_full_tables(cfg)) {
+        double* lam_tab = reinterpret_cast<double*>(w);  w += align256(sizeof(double) * 8);
+        double* tfull = reinterpret_cast<double*>(w);
+        const int ns = (cfg->nT2 + 31) / 32;
+        if (ns <= 2) rc = t2_launch_full_factors<2>(A, G, kband, tfull, lam_tab, st);
+        else if (ns == 3) rc = t2_launch_full_factors<3>(A, G, kband, tfull, lam_tab, st);
+        else rc = t2_launch_full_factors<4>(A, G, kband, tfull, lam_tab, st);
+        if (rc) return rc;
+        A.tfull = tfull;
+        A.lam_tab = lam_tab;
+    }
     cudaError_t e = cudaMemsetAsync(A.hist, 0, sizeof(int) * (size_t)cfg->nA, st);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "memset hist: %s", cudaGetErrorString(e));
     const int tb = 256;

@@ -34,7 +34,15 @@ struct T2Args {
     int* counters;    // [0] = number of tiles, [1] = next tile
     int pmax;
     int warps;
+    // shared full-set factor tables (X2 with MET2_T2_FLAG_FULL_START): the first T2_NTAB abscissae of bounded Brent do
+    // not depend on the voxel, so the inverse Cholesky factor of the FULL column set, (G_a + lam_j K)^-1 = T T^T, is
+    // built once per (flip angle, abscissa) by t2_full_factors_kernel and copied instead of being re-derived per voxel
+    const double* tfull;     // [T2_NTAB][nA][tri(nT2)], first entry NaN if not positive definite
+    const double* lam_tab;   // [T2_NTAB]
+    int ntab_use;            // how many of them the fit kernel consults
 };
+
+constexpr int T2_NTAB = 2;   // measured on config 2: 1 table 429 ms, 2 tables 426 ms, 3 tables 435 ms (no table 444 ms)
 
 // ---------------------------------------------------------------------------------------------- L-curve corner
 // Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves of length nl at S[oLx..], S[oLy..].
@@ -417,6 +425,46 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
     return log(num / (den * den));
 }
 
+// ---------------------------------------------------------------------------------------------- full-set factor tables
+// One warp per (abscissa j, flip angle a).  The abscissae are produced by the same Brent state machine the fit kernel
+// runs (so the fit kernel can match them bit for bit): x0 = a + g (b - a), x1 = the golden step that follows (and, were
+// T2_NTAB larger, the golden steps after points that were worse than x0 — the case for every voxel whose optimum is
+// small).
+template <int NS>
+__global__ void __launch_bounds__(32) t2_full_factors_kernel(const double* __restrict__ G, const double* __restrict__ kband,
+                                                             int n, int nA, double lo, double hi, double xatol,
+                                                             int maxfun, double* __restrict__ tfull,
+                                                             double* __restrict__ lam_tab) {
+    const int lane = threadIdx.x;
+    const int a = blockIdx.x % nA, j = blockIdx.x / nA;
+    Brent B;
+    double lam = B.start(lo, hi, xatol, maxfun);
+    double xs_[T2_NTAB];
+    xs_[0] = lam;
+    bool more = true;
+#pragma unroll
+    for (int q = 1; q < T2_NTAB; ++q) {
+        if (more) more = B.feed((double)q, lam);   // every new point "worse" than x0: golden steps back towards a
+        xs_[q] = more ? lam : NAN;
+    }
+    if (a == 0 && lane == 0) lam_tab[j] = xs_[j];
+    Slots<NS> W;
+    W.carve(0, n);
+    const double lj = xs_[j];
+    const double* Ga = G + (size_t)a * n * n;
+    auto Aent = [&](int r, int c) -> double {
+        double v = __ldg(Ga + r * n + c);
+        const int d = r - c + 2;   // K[r][c] = kband[d][c]
+        if (d >= 0 && d <= 4) v = fma(lj, __ldg(kband + d * n + c), v);
+        return v;
+    };
+    const bool pd = (lj == lj) && rebuild_T_blocked<NS>(W, Aent, n, lane);
+    double* out = tfull + ((size_t)j * nA + a) * tri(n);
+    for (int i = lane; i < tri(n); i += 32) out[i] = S[W.T + i];
+    __syncwarp();
+    if (!pd && lane == 0) out[0] = NAN;
+}
+
 // ---------------------------------------------------------------------------------------------- fit kernel
 // shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
 // then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64 | Brent-best snapshot 48 NS]
@@ -548,6 +596,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 // lets the secondary loop drop the few columns that do not belong, instead of ~55 single-column appends.
                 // (Host sets MET2_T2_FLAG_FULL_START only for the identity matrix: with InvT2 the long-T2 columns are
                 // barely penalised and most of them leave again — measured 2x slower for T2SPARC.)
+                bool t_ready = false;
                 auto full_set_start = [&](double lam0) {
 #pragma unroll
                     for (int tt = 0; tt < NS; ++tt) {
@@ -560,6 +609,23 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     }
                     __syncwarp();
                     p = n;
+                };
+                // If lam is one of the tabulated (voxel-independent) Brent abscissae, start its solve from the full set
+                // with the shared factor of this flip angle instead of re-deriving a factor for the carried-over set.
+                auto try_table = [&](double lam0) {
+                    t_ready = false;
+                    if (!A.tfull || !warm) return;
+                    int jt = -1;
+#pragma unroll
+                    for (int q = 0; q < T2_NTAB; ++q)
+                        if (q < A.ntab_use && lam0 == __ldg(A.lam_tab + q)) jt = q;
+                    if (jt < 0) return;
+                    const double* src = A.tfull + ((size_t)jt * A.cfg.nA + fa) * tri(n);
+                    if (!(__ldg(src) == __ldg(src))) return;   // not positive definite: normal path
+                    full_set_start(lam0);
+                    for (int i = lane; i < tri(n); i += 32) S[W.T + i] = __ldg(src + i);
+                    __syncwarp();
+                    t_ready = true;
                 };
                 // Brent methods (X2, GCV, BayesReg): the reference re-solves at the returned lambda = Brent's best
                 // abscissa xf, a point that was already evaluated.  The solution of that evaluation is kept in the
@@ -606,7 +672,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
-                                            warm ? p : 0);
+                                            warm ? p : 0, t_ready);
+                    t_ready = false;
                     if (method == MET2_REG_NNLS && nst == 0 && p > 0) refine_plain<NS, ME>(W, Dt, oM, oLx, m, p, lane);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                     if (stage == ST_FINAL) {
@@ -692,12 +759,16 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                             lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
                             reg = true;
                             stage = ST_SEARCH;
-                            if (warm && (A.cfg.flags & MET2_T2_FLAG_FULL_START) && lam >= 1.0) full_set_start(lam);
+                            if (warm && (A.cfg.flags & MET2_T2_FLAG_FULL_START) && lam >= 1.0) {
+                                try_table(lam);
+                                if (!t_ready) full_set_start(lam);
+                            }
                         } else {
                             const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
                             const double lam_eval = lam;
                             const bool more = B.feed(cost, lam);
                             if (warm && B.xf == lam_eval) snapshot(sse);
+                            if (more && (A.cfg.flags & MET2_T2_FLAG_FULL_START)) try_table(lam);
                             if (!more) {
                                 lam = B.xf;
                                 stage = ST_FINAL;
