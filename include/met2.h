@@ -77,7 +77,8 @@ typedef struct met2_fa_cfg {
                                         (algorithms.py:285-296) in reg[v] — for objective-level parity tests */
 #define MET2_T2_FLAG_GCV_GRID 32     /* GCV only (extension, BASELINE.json configs[2]): instead of Brent, evaluate the
                                         objective of algorithms.py:285-296 on `lambdas[0..nLambda)` and take the arg-min */
-#define MET2_T2_FLAG_FULL_START 16    /* X2: start the first regularised solve (lambda >= 1) from the full column set
+#define MET2_T2_FLAG_FULL_START 16    /* X2: start the solves at Brent's first (voxel-independent) abscissae from the full
+                                        column set, with inverse-Cholesky factors shared per flip angle
                                         (worth it when L = I; same minimiser) */
 #define MET2_T2_FLAG_COLD_START 4    /* start every NNLS of a lambda search from the empty set like the reference,
                                         instead of warm-starting from the previous solution (same minimiser) */

@@ -654,6 +654,59 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         // not positive definite in floating point: fall through to a cold start (p = 0, x = y = z = 0)
     }
 
+    bool have_yz = false;
+    if (secondary_first && t_ready) {
+        // Start from the FULL set with a shared factor: drop every column whose unconstrained coefficient is not positive
+        // in one go (highest position first, so the positions still to be examined do not move) instead of letting the
+        // secondary loop take them out one re-solve at a time.  x stays a feasible point on the reduced set, so the
+        // loop below continues as for any warm start; the minimiser does not depend on how the set was reached.
+        // (Measured: T2 stage 426 -> 398 ms.  The same one-step drop for EVERY warm start did not pay — X2 unchanged,
+        // L-curve 598 -> 621 ms — because a carried-over support rarely loses more than one or two columns.)
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            int i = lane + 32 * t;
+            if (i < p) S[W.gs + i] = S[W.cc + SI(W.ix, i)];
+        }
+        __syncwarp();
+        tmul_transposed<NS>(W.T, W.gs, p, lane, y);
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            int i = lane + 32 * t;
+            if (i < p) S[W.rs + i] = y[t];
+        }
+        __syncwarp();
+        tmul<NS>(W.T, W.rs, p, lane, z);
+        __syncwarp();
+        unsigned negm = 0u;
+#pragma unroll
+        for (int t = 0; t < NS; ++t) {
+            int i = lane + 32 * t;
+            if (i < p && z[t] <= 0.0) negm |= 1u << t;
+        }
+        int cur = p;
+        have_yz = (__ballot_sync(FULL_MASK, negm != 0u) == 0u);   // nothing to drop: y and z are the loop's first solve
+        while (true) {
+            int k = -1;
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                int i = lane + 32 * t;
+                if (((negm >> t) & 1u) && i < cur && i > k) k = i;
+            }
+            k = (int)__reduce_max_sync(FULL_MASK, (unsigned)(k + 1)) - 1;
+            if (k < 0 || p <= 1) break;
+            const int colk = SI(W.ix, k);
+            if (colk / NS == lane) inP &= ~(1u << (colk % NS));
+            if (lane == 0) S[W.xc + colk] = 0.0;
+            __syncwarp();
+            remove_position<NS>(W, k, p, lane, x);
+            cur = k;
+        }
+        if (!have_yz) {
+#pragma unroll
+            for (int t = 0; t < NS; ++t) y[t] = z[t] = 0.0;
+        }
+    }
+
     while (true) {
       if (!secondary_first) {
         if (p >= n || p >= mrows) break;
@@ -776,7 +829,9 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         // ---- secondary loop
         bool stop = false;
         while (true) {
-            if (fresh) {
+            if (fresh && have_yz) {
+                have_yz = false;   // computed by the block-drop step above
+            } else if (fresh) {
                 // y = T^T c_P and z = T y from scratch (after a warm-start rebuild or a removal)
 #pragma unroll
                 for (int t = 0; t < NS; ++t) {

@@ -42,7 +42,7 @@ struct T2Args {
     int ntab_use;            // how many of them the fit kernel consults
 };
 
-constexpr int T2_NTAB = 2;   // measured on config 2: 1 table 429 ms, 2 tables 426 ms, 3 tables 435 ms (no table 444 ms)
+constexpr int T2_NTAB = 3;   // measured on config 2 (T2 stage): no table 444 ms, 2 tables 398, 3 tables 390, 4 tables 390
 
 // ---------------------------------------------------------------------------------------------- L-curve corner
 // Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves of length nl at S[oLx..], S[oLy..].

@@ -15,7 +15,7 @@ ph = make_phantom(shape, seed=2, fa_mode="b1", backend="gpu")
 print("phantom s", time.time() - t0, flush=True)
 sig = torch.as_tensor(ph["data"].reshape(-1, 32)).cuda()
 V = sig.shape[0]
-plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method=fam)
+plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method=fam, t2_flags=int(os.environ.get("T2FLAGS", "0")))
 torch.cuda.synchronize()
 res = {"V": V, "method": method, "rm": rm, "fa": fam}
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
