@@ -322,47 +322,80 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
             const double v = jlive ? S[colg + 4 * is + q] : 0.0;
             dmma884(s0, s1, -v, v);
         }
-        // ---- T_JJ = chol(S)^-1 by symmetric Gaussian elimination on the augmented block [S | I] (8 x 16, row-major in
-        //      S[W.gs .. W.gs + 128), which spans gs and rs): after the 7 steps the left half holds D L1^T (S = L1 D L1^T)
-        //      and the right half M = L1^-1, so R = D^1/2 L1^T and T_JJ[r][c] = M[c][r] / sqrt(d_c) for r <= c.
-        //      One __syncwarp per step and one reciprocal on the dependency chain (the previous version ran an 8-step
-        //      Cholesky with three barriers per step and then a serial 8 x 8 triangular inverse on 8 lanes: ~20 % of
-        //      the kernel's stall samples, profiles/r01_t2_fit_v8_ncu_summary.txt).
+        // ---- T_JJ = chol(S)^-1 by symmetric Gaussian elimination on the augmented block [S | I]: after the steps the
+        //      left half holds D L1^T (S = L1 D L1^T) and the right half M = L1^-1, so R = D^1/2 L1^T and
+        //      T_JJ[r][c] = M[c][r] / sqrt(d_c) for r <= c.  The 36 upper-triangular entries of the left half and the 28
+        //      strictly-lower entries of M are exactly two per lane and stay in REGISTERS; a row is published to the
+        //      8 x 16 array FR (S[W.gs .. W.gs + 128), spanning gs and rs) once, when it becomes the pivot row.  One
+        //      __syncwarp and one fast reciprocal per step on the dependency chain.  (First version: an 8-step Cholesky
+        //      with three barriers per step plus a serial triangular inverse on 8 lanes, ~20 % of the kernel's stall
+        //      samples in profiles/r01_t2_fit_v8_ncu_summary.txt; second: the same elimination with every entry updated
+        //      in shared memory, 16 % of the executed instructions in the v11 capture.)
         {
-            // element (r, c) lives at r*16 + ((c + r) & 15): the rotation keeps both the row-k broadcasts and the
-            // per-lane row updates free of shared-memory bank conflicts within a half-warp
-            auto AUG = [&](int r, int c) -> int { return W.gs + r * 16 + ((c + r) & 15); };
-            S[AUG(g, 2 * q)] = s0;
-            S[AUG(g, 2 * q + 1)] = s1;
-            S[AUG(g, 8 + 2 * q)] = (2 * q == g) ? 1.0 : 0.0;
-            S[AUG(g, 8 + 2 * q + 1)] = (2 * q + 1 == g) ? 1.0 : 0.0;
+            const int oFR = W.gs;
+            S[oFR + g * 16 + 2 * q] = s0;
+            S[oFR + g * 16 + 2 * q + 1] = s1;
+            S[oFR + g * 16 + 8 + 2 * q] = (2 * q == g) ? 1.0 : 0.0;
+            S[oFR + g * 16 + 8 + 2 * q + 1] = (2 * q + 1 == g) ? 1.0 : 0.0;
             __syncwarp();
-            const int r = g, cg = 4 * q;   // this lane updates Aug[r][cg .. cg+3]
+            // entry e = lane + 32 s: e < 36 -> (r, c) of the upper triangle, row-major; e >= 36 -> (r, 8 + c') with c' < r
+            int er[2], ec[2];
+            double ev[2];
+#pragma unroll
+            for (int sl = 0; sl < 2; ++sl) {
+                const int e = lane + 32 * sl;
+                int rr, cc;
+                if (e < 36) {
+                    rr = 0;
+                    int rem = e;
+#pragma unroll
+                    for (int t = 0; t < 7; ++t)
+                        if (rem >= 8 - rr) {
+                            rem -= 8 - rr;
+                            ++rr;
+                        }
+                    cc = rr + rem;
+                } else {
+                    const int f = e - 36;
+                    rr = 1;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t)
+                        if (f >= (rr * (rr + 1)) / 2) ++rr;
+                    cc = 8 + f - (rr * (rr - 1)) / 2;
+                }
+                er[sl] = rr;
+                ec[sl] = cc;
+                ev[sl] = S[oFR + rr * 16 + cc];
+            }
             // rows beyond the set (virtual identity rows of a partial last block) need no elimination
             const int nv = (p - c0 < 8) ? (p - c0) : 8;
 #pragma unroll 1
             for (int k = 0; k < nv - 1; ++k) {
-                const double d = S[AUG(k, k)];
+                const double d = S[oFR + k * 17];
                 if (!(d > 0.0)) ok = false;
-                if (r > k) {
-                    const double m = S[AUG(k, r)] * rcp_fast(d);
+                const double inv = rcp_fast(d);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int c = cg + j;
-                        if ((c < 8) ? (c >= r) : (c - 8 <= k)) S[AUG(r, c)] = fma(-m, S[AUG(k, c)], S[AUG(r, c)]);
+                for (int sl = 0; sl < 2; ++sl) {
+                    if (er[sl] > k && (ec[sl] < 8 || ec[sl] - 8 <= k)) {
+                        const double m = S[oFR + k * 16 + er[sl]] * inv;
+                        ev[sl] = fma(-m, S[oFR + k * 16 + ec[sl]], ev[sl]);
                     }
                 }
+                // row k+1 is final now: publish it (this step only read row k, so one barrier per step is enough)
+#pragma unroll
+                for (int sl = 0; sl < 2; ++sl)
+                    if (er[sl] == k + 1) S[oFR + er[sl] * 16 + ec[sl]] = ev[sl];
                 __syncwarp();
             }
-            if (!(S[AUG(nv - 1, nv - 1)] > 0.0)) ok = false;
-            // T_JJ (row-major 8 x 8) -> S[W.rs ..]; Aug overlaps rs, so gather into registers first
+            if (!(S[oFR + (nv - 1) * 17] > 0.0)) ok = false;
+            // T_JJ (row-major 8 x 8) -> S[W.rs ..]; FR overlaps rs, so gather into registers first
             const int c = lane & 7;
-            const double ric = rsqrt_fast(S[AUG(c, c)]);
+            const double ric = rsqrt_fast(S[oFR + c * 17]);
             double tv[2];
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
                 const int rr = pass * 4 + (lane >> 3);
-                tv[pass] = (rr < c) ? S[AUG(c, 8 + rr)] * ric : ((rr == c) ? ric : 0.0);
+                tv[pass] = (rr < c) ? S[oFR + c * 16 + 8 + rr] * ric : ((rr == c) ? ric : 0.0);
             }
             __syncwarp();
 #pragma unroll
