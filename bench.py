@@ -355,7 +355,7 @@ def _ncu_executed_flops_per_voxel():
     """FP64 flops per voxel the t2_fit_kernel actually EXECUTES on this workload (2 x DFMA + DADD + DMUL thread
     instructions, same ncu capture as `_ncu_traffic`); None if the record is missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v10_fullsize_counters.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v12_fullsize_counters.json")) as fh:
             return json.load(fh)["executed_fp64_flops_per_voxel"]
     except Exception:
         return None
@@ -363,9 +363,9 @@ def _ncu_executed_flops_per_voxel():
 
 def _ncu_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one t2_fit_kernel launch on this workload, from the committed
-    ncu capture (profiles/r01_t2_fit_v10_fullsize_counters.json); None if the record is missing."""
+    ncu capture (profiles/r01_t2_fit_v12_fullsize_counters.json); None if the record is missing."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v10_fullsize_counters.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "r01_t2_fit_v12_fullsize_counters.json")) as fh:
             return json.load(fh)["traffic_bytes"]
     except Exception:
         return None
