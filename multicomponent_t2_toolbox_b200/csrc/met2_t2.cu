@@ -74,18 +74,22 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
     return MET2_OK;
 }
 
-static bool t2_uses_full_tables(const met2_t2_cfg* cfg) {
-    return cfg->method == MET2_REG_X2 && (cfg->flags & MET2_T2_FLAG_FULL_START) && !(cfg->flags & MET2_T2_FLAG_COLD_START);
+// number of shared full-set factor tables this configuration builds (0: none)
+static int t2_full_tables(const met2_t2_cfg* cfg) {
+    if (cfg->flags & MET2_T2_FLAG_COLD_START) return 0;
+    if (cfg->method == MET2_REG_X2 && (cfg->flags & MET2_T2_FLAG_FULL_START)) return T2_NTAB_X2;
+    if (cfg->method == MET2_REG_BAYESREG) return T2_NTAB_BAYES;
+    return 0;
 }
 
 template <int NS>
-static int t2_launch_full_factors(const T2Args& A, const double* G, const double* kband, double* tfull, double* lam_tab,
-                                  cudaStream_t st) {
+static int t2_launch_full_factors(const T2Args& A, int ntab, const double* G, const double* kband, double* tfull,
+                                  double* lam_tab, cudaStream_t st) {
     const int n = A.cfg.nT2;
     const size_t smem = sizeof(double) * (size_t)Slots<NS>::doubles(n);
     cudaError_t e = cudaFuncSetAttribute(t2_full_factors_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_full_factors attr: %s", cudaGetErrorString(e));
-    t2_full_factors_kernel<NS><<<T2_NTAB * A.cfg.nA, 32, smem, st>>>(G, kband, n, A.cfg.nA, A.cfg.brent_lo, A.cfg.brent_hi,
+    t2_full_factors_kernel<NS><<<ntab * A.cfg.nA, 32, smem, st>>>(G, kband, n, A.cfg.nA, A.cfg.brent_lo, A.cfg.brent_hi,
                                                                      A.cfg.brent_xatol, A.cfg.maxfun, tfull, lam_tab);
     count_launch();
     return check_launch("t2_full_factors_kernel");
@@ -100,8 +104,9 @@ extern "C" int64_t met2_t2_workspace_bytes(int64_t V, const met2_t2_cfg* cfg) {
     b += align256(sizeof(int) * (size_t)V);
     b += align256(sizeof(int) * (size_t)g.max_tiles) * 3;
     b += align256(sizeof(int) * 4);
-    if (t2_uses_full_tables(cfg))
-        b += align256(sizeof(double) * 8) + align256(sizeof(double) * (size_t)T2_NTAB * cfg->nA * tri(cfg->nT2));
+    if (t2_full_tables(cfg))
+        b += align256(sizeof(double) * T2_NTAB_MAX) +
+             align256(sizeof(double) * (size_t)t2_full_tables(cfg) * cfg->nA * tri(cfg->nT2));
     return (int64_t)b + 256;
 }
 
@@ -139,19 +144,23 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     A.warps = g.warps;
     A.tfull = nullptr;
     A.lam_tab = nullptr;
-    A.ntab_use = T2_NTAB;
-    if (const char* ev = getenv("MET2_T2_NTAB")) {   // tuning / A-B runs
-        const int t = atoi(ev);
-        if (t >= 0 && t < T2_NTAB) A.ntab_use = t;
-    }
-    if (t2_uses_full_tables(cfg)) {
-        double* lam_tab = reinterpret_cast<double*>(w);  w += align256(sizeof(double) * 8);
+    A.ntab = 0;
+    A.ntab_use = 0;
+    if (const int ntab = t2_full_tables(cfg)) {
+        double* lam_tab = reinterpret_cast<double*>(w);  w += align256(sizeof(double) * T2_NTAB_MAX);
         double* tfull = reinterpret_cast<double*>(w);
         const int ns = (cfg->nT2 + 31) / 32;
-        if (ns <= 2) rc = t2_launch_full_factors<2>(A, G, kband, tfull, lam_tab, st);
-        else if (ns == 3) rc = t2_launch_full_factors<3>(A, G, kband, tfull, lam_tab, st);
-        else rc = t2_launch_full_factors<4>(A, G, kband, tfull, lam_tab, st);
+        if (ns <= 2) rc = t2_launch_full_factors<2>(A, ntab, G, kband, tfull, lam_tab, st);
+        else if (ns == 3) rc = t2_launch_full_factors<3>(A, ntab, G, kband, tfull, lam_tab, st);
+        else rc = t2_launch_full_factors<4>(A, ntab, G, kband, tfull, lam_tab, st);
         if (rc) return rc;
+        A.ntab = ntab;
+        // full-set starts of the NNLS solves: X2 only (measured; for BayesReg the tables serve the evidence)
+        A.ntab_use = (cfg->method == MET2_REG_X2) ? ntab : 0;
+        if (const char* ev = getenv("MET2_T2_NTAB")) {   // tuning / A-B runs
+            const int t = atoi(ev);
+            if (t >= 0 && t < A.ntab_use) A.ntab_use = t;
+        }
         A.tfull = tfull;
         A.lam_tab = lam_tab;
     }

@@ -37,12 +37,16 @@ struct T2Args {
     // shared full-set factor tables (X2 with MET2_T2_FLAG_FULL_START): the first T2_NTAB abscissae of bounded Brent do
     // not depend on the voxel, so the inverse Cholesky factor of the FULL column set, (G_a + lam_j K)^-1 = T T^T, is
     // built once per (flip angle, abscissa) by t2_full_factors_kernel and copied instead of being re-derived per voxel
-    const double* tfull;     // [T2_NTAB][nA][tri(nT2)], first entry NaN if not positive definite
-    const double* lam_tab;   // [T2_NTAB]
-    int ntab_use;            // how many of them the fit kernel consults
+    const double* tfull;     // [ntab][nA][tri(nT2)], first entry NaN if not positive definite
+    const double* lam_tab;   // [ntab]
+    int ntab;                // tables built
+    int ntab_use;            // how many of them the NNLS full-set starts consult
 };
 
-constexpr int T2_NTAB = 3;   // measured on config 2 (T2 stage): no table 444 ms, 2 tables 398, 3 tables 390, 4 tables 390
+constexpr int T2_NTAB_X2 = 3;      // measured on config 2 (T2 stage): no table 444 ms, 2 tables 398, 3 tables 390, 4 tables 390
+constexpr int T2_NTAB_BAYES = 9;   // BayesReg: the evidence needs the FULL-set factor at every abscissa, so every tabulated
+                                   // abscissa saves a whole n x n factorisation (bayes_cost)
+constexpr int T2_NTAB_MAX = 16;
 
 // ---------------------------------------------------------------------------------------------- L-curve corner
 // Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves of length nl at S[oLx..], S[oLy..].
@@ -118,17 +122,29 @@ __device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int 
 template <int NS>
 __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg, int oKb, int n, int m, int lane,
                                              double x, double beta, double sse, double nrm, double log_det_L,
-                                             unsigned& st, int p) {
+                                             unsigned& st, int p, const double* __restrict__ ttab) {
     const int oT = W.T;
     const double bx = beta * x;
-    // T = U^-1 with A = beta*B + (beta*x)*K = U^T U, all n columns in natural order, by the blocked DMMA factorisation
-    auto Aent = [&](int r, int c) -> double {
-        double a = beta * S[oG + r * ldg + c];
-        const int d = r - c + 2;   // K[r][c] = kband[d][c]
-        if (d >= 0 && d <= 4) a = a + bx * S[oKb + d * n + c];
-        return a;
-    };
-    const bool pd = rebuild_T_blocked<NS>(W, Aent, n, lane);
+    // T = U^-1 with A = beta*B + (beta*x)*K = U^T U, all n columns in natural order.  While Brent is still on its
+    // voxel-independent golden chain (the first T2_NTAB_BAYES abscissae, bracket wider than ~1e-2), the factor T0 of
+    // B + x K comes from the shared tables (ttab) and T = T0 / sqrt(beta); afterwards A is factored here, with beta
+    // inside the matrix like the reference's cholesky(beta*B + beta*x*K).  The two differ by rounding only, which is why
+    // the tables stop before the convergence phase: there Brent compares nearly equal evidences and a 1e-16 change of
+    // the objective can move lambda by 1e-3 relative (measured with 16 tables: 2 of 2 048 voxels; with 9: none).
+    bool pd = true;
+    if (ttab) {
+        const double rsb = 1.0 / sqrt(beta);
+        for (int i = lane; i < tri(n); i += 32) S[oT + i] = __ldg(ttab + i) * rsb;
+        __syncwarp();
+    } else {
+        auto Aent = [&](int r, int c) -> double {
+            double a = beta * S[oG + r * ldg + c];
+            const int d = r - c + 2;   // K[r][c] = kband[d][c]
+            if (d >= 0 && d <= 4) a = a + bx * S[oKb + d * n + c];
+            return a;
+        };
+        pd = rebuild_T_blocked<NS>(W, Aent, n, lane);
+    }
     if (!pd) st |= MET2_ST_NOT_PD;
     // det_U = prod(diag(U)) = prod 1 / T_kk  (np.prod order)
     double det_u = 1.0;
@@ -427,9 +443,10 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
 
 // ---------------------------------------------------------------------------------------------- full-set factor tables
 // One warp per (abscissa j, flip angle a).  The abscissae are produced by the same Brent state machine the fit kernel
-// runs (so the fit kernel can match them bit for bit): x0 = a + g (b - a), x1 = the golden step that follows (and, were
-// T2_NTAB larger, the golden steps after points that were worse than x0 — the case for every voxel whose optimum is
-// small).
+// runs (so the fit kernel can match them bit for bit), fed with the objective f(x) = x: x0 = a + g (b - a), x1 = the
+// golden step to the right of it (worse), then golden steps to the left, each better than the last — the path of every
+// voxel whose optimum is small compared with the bracket, for as long as its parabolic steps are rejected.  A voxel
+// that leaves this path simply stops matching the table.
 template <int NS>
 __global__ void __launch_bounds__(32) t2_full_factors_kernel(const double* __restrict__ G, const double* __restrict__ kband,
                                                              int n, int nA, double lo, double hi, double xatol,
@@ -439,18 +456,15 @@ __global__ void __launch_bounds__(32) t2_full_factors_kernel(const double* __res
     const int a = blockIdx.x % nA, j = blockIdx.x / nA;
     Brent B;
     double lam = B.start(lo, hi, xatol, maxfun);
-    double xs_[T2_NTAB];
-    xs_[0] = lam;
     bool more = true;
-#pragma unroll
-    for (int q = 1; q < T2_NTAB; ++q) {
-        if (more) more = B.feed((double)q, lam);   // every new point "worse" than x0: golden steps back towards a
-        xs_[q] = more ? lam : NAN;
+    for (int q = 0; q < j; ++q) {
+        const double f = lam;
+        if (more) more = B.feed(f, lam);
     }
-    if (a == 0 && lane == 0) lam_tab[j] = xs_[j];
+    const double lj = more ? lam : NAN;
+    if (a == 0 && lane == 0) lam_tab[j] = lj;
     Slots<NS> W;
     W.carve(0, n);
-    const double lj = xs_[j];
     const double* Ga = G + (size_t)a * n * n;
     auto Aent = [&](int r, int c) -> double {
         double v = __ldg(Ga + r * n + c);
@@ -617,8 +631,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     if (!A.tfull || !warm) return;
                     int jt = -1;
 #pragma unroll
-                    for (int q = 0; q < T2_NTAB; ++q)
-                        if (q < A.ntab_use && lam0 == __ldg(A.lam_tab + q)) jt = q;
+                    for (int q = 0; q < A.ntab_use; ++q)
+                        if (lam0 == __ldg(A.lam_tab + q)) jt = q;
                     if (jt < 0) return;
                     const double* src = A.tfull + ((size_t)jt * A.cfg.nA + fa) * tri(n);
                     if (!(__ldg(src) == __ldg(src))) return;   // not positive definite: normal path
@@ -737,8 +751,14 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                             stage = ST_SEARCH;
                         } else {
                             const double nrm = reg_norm2<NS>(W, oLb, n, lane);
+                            const double* ttab = nullptr;
+                            if (A.tfull) {
+                                for (int q = 0; q < A.ntab; ++q)
+                                    if (lam == __ldg(A.lam_tab + q)) ttab = A.tfull + ((size_t)q * A.cfg.nA + fa) * tri(n);
+                                if (ttab && !(__ldg(ttab) == __ldg(ttab))) ttab = nullptr;   // not positive definite
+                            }
                             const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
-                                                               A.cfg.log_det_L, st, p);
+                                                               A.cfg.log_det_L, st, p, ttab);
                             const double lam_eval = lam;
                             const bool more = B.feed(cost, lam);
                             if (warm && B.xf == lam_eval) snapshot(sse);
