@@ -15,23 +15,34 @@ from tabulate import tabulate
 from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data import motor_recon_met2
 
 
+# (flag, type, default, choices, help) — the reference's flags, types, defaults and choices (run_real_data_script.py:18-62);
+# every flag is required there, and stays so here
+_FLAGS = [
+    ("--path_to_folder", str, None, None, "folder that holds the data, mask and the output directory (trailing '/')"),
+    ("--input", str, None, None, "4-D multi-echo NIfTI file inside the folder"),
+    ("--mask", str, None, None, "3-D brain-mask NIfTI file inside the folder"),
+    ("--minTE", float, None, None, "first echo time = echo spacing, ms"),
+    ("--nTE", int, 32, None, "number of echoes"),
+    ("--TR", float, None, None, "repetition time, ms"),
+    ("--FA_method", str, "spline", ["spline", "brute-force"], "flip-angle search: 15-knot spline + Brent, or exhaustive 1-degree grid"),
+    ("--FA_smooth", str, "yes", ["yes", "no"], "Gaussian-smooth (sigma 2) the data used for the flip-angle search"),
+    ("--denoise", str, "TV", ["TV", "NESMA", "None"], "pre-processing denoiser (NESMA runs on the GPU; TV is not provided)"),
+    ("--reg_method", str, "X2", ["NNLS", "T2SPARC", "X2", "L_curve", "GCV", "BayesReg"], "regularisation-weight selector"),
+    ("--reg_matrix", str, "I", ["I", "L1", "L2", "InvT2"], "Tikhonov matrix"),
+    ("--numcores", int, -1, None, "accepted for compatibility; the fit runs on the GPU"),
+    ("--myelin_T2_cutoff", float, 40, None, "upper T2 bound of the myelin-water compartment, ms"),
+    ("--savefig", str, "no", ["yes", "no"], "accepted for compatibility (no plotting backend here)"),
+    ("--savefig_slice", int, 30, None, "accepted for compatibility"),
+]
+
+
 def build_parser():
     parser = argparse.ArgumentParser(description='Myelin Water Imaging')
-    parser.add_argument("--path_to_folder", default=None, type=str, help="Path to the folder where the data is located, e.g., /home/Datasets/MET2/", required=True)
-    parser.add_argument("--input", default=None, type=str, help="Input data, e.g., Data.nii.gz", required=True)
-    parser.add_argument("--mask", default=None, type=str, help="Brain mask, e.g., Mask.nii.gz", required=True)
-    parser.add_argument("--minTE", default=None, type=float, help="Minimum Echo Time (TE, in ms)", required=True)
-    parser.add_argument("--nTE", default=32, type=int, help="Number of TEs", required=True)
-    parser.add_argument("--TR", default=None, type=float, help="Repetition Time (TR, in ms)", required=True)
-    parser.add_argument("--FA_method", default='spline', type=str, help="Method to estimate the flip angle (FA)", choices=["spline", "brute-force"], required=True)
-    parser.add_argument("--FA_smooth", default='yes', type=str, help="Smooth data for estimating the FA", choices=["yes", "no"], required=True)
-    parser.add_argument("--denoise", default='TV', type=str, help="Denoising method", choices=["TV", "NESMA", "None"], required=True)
-    parser.add_argument("--reg_method", default='X2', type=str, help="Regularization algorithm", choices=["NNLS", "T2SPARC", "X2", "L_curve", "GCV", "BayesReg"], required=True)
-    parser.add_argument("--reg_matrix", default='I', type=str, help="Regularization matrix", choices=["I", "L1", "L2", "InvT2"], required=True)
-    parser.add_argument("--numcores", default=-1, type=int, help="Number of cores used in the parallel processing (ignored: the fit runs on the GPU)", required=True)
-    parser.add_argument("--myelin_T2_cutoff", default=40, type=float, help="Maximum T2 for the myelin compartment: T2 threshold (in ms)", required=True)
-    parser.add_argument("--savefig", default='no', type=str, help="Save reconstructed maps in .png", choices=["yes", "no"], required=True)
-    parser.add_argument("--savefig_slice", default=30, type=int, help="Axial slice to save reconstructed maps, e.g., --Slice=30", required=True)
+    for flag, typ, default, choices, text in _FLAGS:
+        kw = dict(type=typ, default=default, help=text, required=True)
+        if choices:
+            kw["choices"] = choices
+        parser.add_argument(flag, **kw)
     return parser
 
 

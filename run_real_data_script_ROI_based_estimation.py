@@ -11,21 +11,31 @@ from tabulate import tabulate
 from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data_ROI import motor_recon_met2_ROIs
 
 
+# (flag, type, default, choices, required, help) — flags, types, defaults and choices of the reference's ROI script
+_FLAGS = [
+    ("--path_to_folder", str, None, None, True, "folder that holds the data, mask, ROIs and the output directory (trailing '/')"),
+    ("--input", str, None, None, True, "4-D multi-echo NIfTI file inside the folder"),
+    ("--mask", str, None, None, True, "3-D brain-mask NIfTI file inside the folder"),
+    ("--ROIs", str, None, None, True, "3-D integer label NIfTI file inside the folder (0 = background)"),
+    ("--minTE", float, None, None, True, "first echo time = echo spacing, ms"),
+    ("--nTE", int, 32, None, True, "number of echoes"),
+    ("--TR", float, None, None, True, "repetition time, ms"),
+    ("--FA_method", str, "spline", ["spline", "brute-force"], True, "flip-angle search method"),
+    ("--FA_smooth", str, "yes", ["yes", "no"], True, "Gaussian-smooth the data used for the flip-angle search"),
+    ("--denoise", str, "None", ["TV", "NESMA", "None"], True, "pre-processing denoiser (NESMA runs on the GPU; TV is not provided)"),
+    ("--reg_matrix", str, "I", ["I", "L1", "L2", "InvT2"], True, "Tikhonov matrix of the per-ROI X2 fit"),
+    ("--myelin_T2_cutoff", float, 40, None, True, "upper T2 bound of the myelin-water compartment, ms"),
+    ("--numcores", int, -1, None, False, "accepted for compatibility; the fit runs on the GPU"),
+]
+
+
 def build_parser():
     parser = argparse.ArgumentParser(description='Myelin Water Imaging')
-    parser.add_argument("--path_to_folder", default=None, type=str, help="Path to the folder where the data is located, e.g., /home/Datasets/MET2/", required=True)
-    parser.add_argument("--input", default=None, type=str, help="Input data, e.g., Data.nii.gz", required=True)
-    parser.add_argument("--mask", default=None, type=str, help="Brain mask, e.g., Mask.nii.gz", required=True)
-    parser.add_argument("--ROIs", default=None, type=str, help="Brain ROIs, e.g., ROIs.nii.gz", required=True)
-    parser.add_argument("--minTE", default=None, type=float, help="Minimum Echo Time (TE, units: ms)", required=True)
-    parser.add_argument("--nTE", default=32, type=int, help="Number of TEs", required=True)
-    parser.add_argument("--TR", default=None, type=float, help="Repetition Time (units: ms)", required=True)
-    parser.add_argument("--FA_method", choices=["spline", "brute-force"], required=True, type=str, default="spline", help="Method to estimate the flip angle (FA)")
-    parser.add_argument("--FA_smooth", choices=["yes", "no"], required=True, type=str, default="yes", help="Smooth data for estimating the FA")
-    parser.add_argument("--denoise", choices=["TV", "NESMA", "None"], required=True, type=str, default="None", help="Denoising method")
-    parser.add_argument("--reg_matrix", choices=["I", "L1", "L2", "InvT2"], required=True, type=str, default="I", help="Regularization matrix")
-    parser.add_argument("--myelin_T2_cutoff", default=40, type=float, help="Maximum T2 for the myelin compartment: T2 threshold (units: ms)", required=True)
-    parser.add_argument("--numcores", default=-1, type=int, help="Number of cores (ignored: the fit runs on the GPU)")
+    for flag, typ, default, choices, required, text in _FLAGS:
+        kw = dict(type=typ, default=default, help=text, required=required)
+        if choices:
+            kw["choices"] = choices
+        parser.add_argument(flag, **kw)
     return parser
 
 
