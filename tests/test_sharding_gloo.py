@@ -34,6 +34,12 @@ def _worker(rank, world, port, q):
     full = np.zeros(5 * 4 * 3)
     full[flat] = _fake_fit(sig)
     ok = np.array_equal(out["MWF"].reshape(-1), full) and np.array_equal(out["T2s"], np.arange(3.0))
+    # block-cyclic (over-decomposed) partition: same gather, same result
+    mine = pipeline.cyclic_slab(len(flat), rank, world, chunk=4)
+    vol2 = np.zeros(5 * 4 * 3)
+    vol2[flat[mine]] = _fake_fit(sig[mine])
+    out2 = pipeline.gather_volumes({"MWF": vol2.reshape(5, 4, 3)})
+    ok = ok and np.array_equal(out2["MWF"].reshape(-1), full) and 0 < len(mine) < len(flat)
     q.put((rank, bool(ok), hi - lo))
     dist.barrier()
     dist.destroy_process_group()
