@@ -233,6 +233,16 @@ def test_roi_estimator_against_oracle(pipeline_gold, tmp_path):
         assert np.abs(roi[k + "_ROIs"][sel] - ref[k]).max() < 1e-4, k
     assert np.allclose(roi["TWC_ROIs"][sel], ref["TWC"], rtol=1e-6)
     assert np.allclose(roi["reg_opt"][sel], ref["reg_opt"], rtol=1e-5) and np.allclose(roi["k_est"][sel], ref["k_est"], rtol=1e-6)
+    # ... and against what the UNMODIFIED reference's motor_recon_met2_ROIs wrote for the same data, mask and the six
+    # in-mask labels (oracle/make_golden_roi.py -> tests/golden/roi_x2_l2.npz)
+    from conftest import GOLDEN
+    gr = dict(np.load(os.path.join(GOLDEN, "roi_x2_l2.npz")))
+    assert np.array_equal(gr["labels"].astype(np.int64), roi["roi_values"][sel])
+    assert np.array_equal(roi["fsol_ROIs"][sel] > 0, gr["spectra"] > 0)
+    assert np.abs(roi["fsol_ROIs"][sel] - gr["spectra"]).max() < 1e-6 * gr["spectra"].max()
+    for col, k in enumerate(("MWF", "IEWF", "FWF", "T2M", "T2IE")):
+        assert np.abs(roi[k + "_ROIs"][sel] - gr["table_values"][:, col]).max() < 1e-4, k
+    assert np.allclose(roi["TWC_ROIs"][sel], gr["table_values"][:, 5], rtol=1e-6)
     assert np.allclose(np.loadtxt(out + "table_MWF.csv", delimiter=",")[sel], ref["MWF"], atol=1e-4)
     assert np.loadtxt(out + "table_Spectra.csv", delimiter=",").shape == (len(roi["roi_values"]), 60)
     assert os.path.exists(out + "ROI_%d/table_values.csv" % int(keep[0]))

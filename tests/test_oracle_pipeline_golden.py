@@ -50,3 +50,30 @@ def test_mean_spectrum_curves_match_reference(gold, oracle_run):
                                      oracle_run["mean_T2_dist"])
     for k in ("mean_T2_dist", "dist_T2_mean1", "dist_T2_mean2"):
         assert np.allclose(dg[k], gold[k], rtol=1e-9, atol=1e-12), (k, np.abs(dg[k] - gold[k]).max())
+
+
+def test_roi_estimator_matches_reference_run(gold):
+    """Oracle restatement of the ROI-based estimator (motor_recon_met2_real_data_ROI.py:405-445) against the outputs of
+    the UNMODIFIED reference's motor_recon_met2_ROIs run end to end (oracle/make_golden_roi.py: spline FA, no
+    smoothing, no denoising, reg_matrix L2)."""
+    r = dict(np.load(os.path.join(GOLDEN, "roi_x2_l2.npz")))
+    mask = gold["mask"].astype(np.int64)
+    data = gold["data"] * mask[..., None]
+    data[data < 0.0] = 0.0
+    g = O._grids("X2", "L2", "spline", 40.0, 32, 10.0, 1000.0)
+    Dic = O.create_Dic_3D(60, g["T2s"], g["T1s"], 32, 10.0, g["alpha_values"], 1000.0)
+    DicLR = O.create_Dic_3D(60, g["T2s"], g["T1s"], 32, 10.0, g["alpha_spline"], 1000.0)
+    nx, ny, nz = mask.shape
+    FA_index = np.zeros((nx, ny, nz))
+    for z in range(nz):
+        for y in range(ny):
+            FA_index[:, y, z] = O.fitting_slice_FA_spline_method(DicLR, Dic, data[:, y, z, :], mask[:, y, z],
+                                                                 g["alpha_spline"], nx, g["alpha_values"])[1]
+    out = O.roi_estimates(data, mask, r["rois"], FA_index, Dic, g["L"], g["T2s"], g["ind_m"], g["ind_t"], g["ind_csf"])
+    assert np.array_equal(out["roi_values"], r["labels"].astype(np.int64))
+    assert np.allclose(out["fsol_ROIs"], r["spectra"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(out["fsol_ROIs"] > 0, r["spectra"] > 0)
+    assert np.allclose(out["MWF"], r["MWF"], rtol=1e-9, atol=1e-12)
+    tv = r["table_values"]
+    for col, k in enumerate(("MWF", "IEWF", "FWF", "T2M", "T2IE", "TWC")):
+        assert np.allclose(out[k], tv[:, col], rtol=1e-9, atol=1e-12), k
