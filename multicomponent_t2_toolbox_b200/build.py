@@ -55,8 +55,8 @@ def build_library(force=False, verbose=False):
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc link failed:\n%s" % r.stderr[-4000:])
-    with open(os.path.join(CSRC, "ptxas.log"), "w") as fh:
-        fh.write("\n".join(logs))
+    with open(os.path.join(CSRC, "ptxas.log"), "w") as fh:   # registers / spills / stack per kernel (compile times dropped:
+        fh.write("\n".join(l for log in logs for l in log.split("\n") if "Compile time" not in l))   # they change every build)
     if verbose:
         print("\n".join(logs))
     return LIB_PATH
