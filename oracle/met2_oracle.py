@@ -8,9 +8,12 @@ the product package never does.
 
 PINNING.  The reference ships no tests, golden vectors or seeds — "parity unpinned" by the
 reference's own fixtures.  The oracle is instead pinned against OUTPUTS OF THE REFERENCE ITSELF, imported read-only
-in the build container through `oracle/ref_shim.py`: `oracle/make_golden.py` writes those outputs to
-`tests/golden/*.npz` and `tests/test_oracle.py` holds the oracle to them (bit-for-bit for indices/supports and
-<= 1e-12 for values) on any box.
+in the build container through `oracle/ref_shim.py`: `oracle/make_golden*.py` write those outputs to
+`tests/golden/*.npz` — per-function vectors (make_golden.py), 20 480 + 2 048 voxels of the config-2 phantom
+(make_golden_config2.py, make_golden_methods.py) and END-TO-END runs of the reference's two orchestrators
+(make_golden_pipeline.py: motor_recon_met2 with NESMA + smoothing; make_golden_roi.py: motor_recon_met2_ROIs) — and
+`tests/test_oracle_golden.py`, `tests/test_oracle_vs_reference.py`, `tests/test_oracle_pipeline_golden.py` hold the
+oracle to them (bit-for-bit for indices/supports and <= 1e-9 .. 1e-12 for values) on any box.
 
 Third-party arithmetic not under /root/reference (reference pins scipy==1.5.2, numpy==1.19.2 in requirements.txt:6,9;
 this image has scipy 1.18.1 / numpy 2.3.5 — the operative oracle):

@@ -3,7 +3,7 @@
 Only usable in the build container (the GPU box has no /root/reference).  Used by
 `oracle/make_golden.py` to generate the committed fixtures under tests/golden/ and by
 `tests/test_oracle_vs_reference.py` (skipped when the reference is absent) to pin the
-restatement in `oracle/met2_oracle.py` / `oracle/met2_oracle.c`.
+restatement in `oracle/met2_oracle.py`.
 
 Nothing is copied from the reference: the modules are imported from where they lie.
 The shim provides what the reference's pinned environment (scipy 1.5.2, Python 2-era
