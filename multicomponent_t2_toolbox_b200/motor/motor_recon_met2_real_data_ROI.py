@@ -21,8 +21,7 @@ def motor_recon_met2_ROIs(TE_array, path_to_data, path_to_mask, path_to_ROIs, pa
     mask = nifti_io.load(path_to_mask).get_fdata().astype(np.int64, copy=False)
     ROIs = nifti_io.load(path_to_ROIs).get_fdata().astype(np.int64, copy=False)
     nx, ny, nz, nt = data.shape
-    for c in range(nt):
-        data[:, :, :, c] = data[:, :, :, c] * mask
+    np.multiply(data, mask[..., None], out=data)   # :181-182, all echoes in one pass
     data[data < 0.0] = 0.0
     if reg_matrix not in ('I', 'L1', 'L2', 'InvT2'):
         print('Error: Wrong reg_matrix option!')

@@ -41,6 +41,57 @@ def test_nifti_int_mask_and_scaling(tmp_path):
         nifti_io.load(str(tmp_path / "bad.nii"))
 
 
+def test_parallel_gzip_is_one_standard_member(tmp_path):
+    """The threaded deflate (nifti_io._gzip_pieces) must give an ordinary gzip file: ONE member (a reader that stops
+    after the first member sees everything), correct CRC/size trailer, same bytes for any thread count, chunk
+    boundaries (4 MiB) crossed, empty payload handled."""
+    import zlib
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 4, size=(96, 96, 30, 6)).astype(np.float64)     # 13.3 MB -> four deflate chunks
+    files = []
+    for th in (1, 3, 8):
+        p = str(tmp_path / ("t%d.nii.gz" % th))
+        nifti_io.save(a, p, threads=th)
+        files.append(open(p, "rb").read())
+    assert files[0] == files[1] == files[2]
+    blob = files[0]
+    d = zlib.decompressobj(31)                                         # one member only
+    raw = d.decompress(blob)
+    assert d.eof and d.unused_data == b"" and len(raw) == 352 + a.nbytes
+    assert struct.unpack("<II", blob[-8:]) == (zlib.crc32(raw), len(raw) & 0xFFFFFFFF)
+    assert np.array_equal(nifti_io.load(str(tmp_path / "t8.nii.gz")).get_fdata(), a)
+    assert b"".join(nifti_io._gzip_pieces(b"", 1, 4)) and gzip.decompress(b"".join(nifti_io._gzip_pieces(b"", 1, 4))) == b""
+    for n in (1, nifti_io._GZ_CHUNK - 1, nifti_io._GZ_CHUNK, nifti_io._GZ_CHUNK + 1):
+        buf = rng.integers(0, 3, size=n, dtype=np.uint8).tobytes()
+        assert gzip.decompress(b"".join(nifti_io._gzip_pieces(buf, 1, 4))) == buf
+
+
+def test_nifti_big_endian_qform_and_shapes(tmp_path):
+    """A big-endian file with the affine in the qform (what some scanners write) reads like nibabel reads it; arrays of
+    every rank the toolbox writes (3-D maps, 4-D spectra, a singleton last axis) round-trip."""
+    a = np.arange(2 * 3 * 4, dtype=np.float32).reshape(2, 3, 4)
+    hdr = bytearray(348)
+    struct.pack_into(">i", hdr, 0, 348)
+    struct.pack_into(">8h", hdr, 40, 3, 2, 3, 4, 1, 1, 1, 1)
+    struct.pack_into(">hh", hdr, 70, 16, 32)
+    struct.pack_into(">8f", hdr, 76, -1.0, 2.0, 3.0, 4.0, 1.0, 1.0, 1.0, 1.0)
+    struct.pack_into(">3f", hdr, 108, 352.0, 0.0, 0.0)
+    struct.pack_into(">hh", hdr, 252, 1, 0)
+    struct.pack_into(">6f", hdr, 256, 0.0, 0.0, 0.0, 7.0, 8.0, 9.0)
+    hdr[344:348] = b"n+1\x00"
+    p = str(tmp_path / "be.nii")
+    open(p, "wb").write(bytes(hdr) + b"\x00" * 4 + a.astype(">f4").tobytes(order="F"))
+    im = nifti_io.load(p)
+    assert np.array_equal(im.get_fdata(), a.astype(np.float64))
+    assert np.allclose(im.affine, [[2, 0, 0, 7], [0, 3, 0, 8], [0, 0, -4, 9], [0, 0, 0, 1]])   # qfac = -1 flips z
+    rng = np.random.default_rng(2)
+    for shape in ((4, 5, 6), (4, 5, 6, 1), (3, 2, 2, 7), (6,)):
+        x = rng.uniform(size=shape)
+        q = str(tmp_path / "s.nii.gz")
+        nifti_io.save(x, q)
+        assert np.array_equal(nifti_io.load(q).get_fdata(), x)
+
+
 def test_cli_flags_match_reference():
     argv = ("--path_to_folder /data/ --input Data.nii.gz --mask Mask.nii.gz --minTE 10.68 --nTE 32 --TR 1000 "
             "--FA_method spline --FA_smooth yes --denoise None --reg_method X2 --reg_matrix I --numcores -1 "
