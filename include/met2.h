@@ -44,6 +44,7 @@ extern "C" {
 #define MET2_ST_NONFINITE 2u    /* NaN/Inf in the signal (the reference raises ValueError, algorithms.py:56) */
 #define MET2_ST_ITMAX 4u        /* a Lawson-Hanson solve hit itmax = 3n (ignored by the reference, algorithms.py:79-81) */
 #define MET2_ST_SSE_ZERO 8u     /* X2: plain-NNLS residual is exactly 0 -> NaN objective (algorithms.py:231) */
+#define MET2_ST_ECHO_BAD_L 32u  /* MET2_T2_FLAG_ECHO_SPACE given with a non-diagonal L: voxel skipped */
 #define MET2_ST_NOT_PD 16u      /* BayesReg: beta*B + beta*x*K not positive definite (reference: LinAlgError) */
 
 /* flip-angle search methods: run_real_data_script.py --FA_method */
@@ -80,6 +81,10 @@ typedef struct met2_fa_cfg {
 #define MET2_T2_FLAG_FULL_START 16    /* X2: start the solves at Brent's first (voxel-independent) abscissae from the full
                                         column set, with inverse-Cholesky factors shared per flip angle
                                         (worth it when L = I; same minimiser) */
+#define MET2_T2_FLAG_ECHO_SPACE 64    /* EXPERIMENTAL, off by default, X2 only, nTE <= 32, nT2 <= 64, and the caller asserts
+                                        that L is DIAGONAL (I, InvT2): Tikhonov solves in echo space (32 x 32 factor per
+                                        voxel, csrc/met2_t2_echo.cu).  A non-diagonal L skips every voxel with status
+                                        bit 32.  Same minimiser as the default path; not yet validated on a GPU */
 #define MET2_T2_FLAG_COLD_START 4    /* start every NNLS of a lambda search from the empty set like the reference,
                                         instead of warm-starting from the previous solution (same minimiser) */
 

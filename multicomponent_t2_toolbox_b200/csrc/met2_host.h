@@ -1,6 +1,10 @@
 // met2_host.h — host-side plumbing shared by the translation units of libmet2.so (error state, launch accounting).
 #pragma once
+#ifdef MET2_HOST_EMU
+#include "simt_emu.h"
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/met2.h"

@@ -18,12 +18,20 @@
 // shared-window addressing, LDS/STS); round-1 profiling of a pointer-based version showed generic LD.E + R2UR and
 // local-memory reloads dominating the issue slots (profiles/r01_t2_fit_v1_ncu_summary.txt).
 #pragma once
+#ifdef MET2_HOST_EMU
+#include "simt_emu.h"   // tests/emu: CPU emulation of the device code for the "not gpu" tests; never part of libmet2.so
+#else
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 namespace met2 {
 
+#ifdef MET2_HOST_EMU
+extern double S[];
+#else
 extern __shared__ __align__(16) double S[];   // the dynamic shared memory of every met2 kernel
+#endif
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
@@ -255,9 +263,13 @@ __device__ __forceinline__ double rcp_fast(double d) {
 // B[lane%4][lane/4], C/D[lane/4][2*(lane%4) + {0,1}] (verified on B200 by tools/dmma_probe.cu; 16 cycles issue interval,
 // 26 cycles dependent latency).
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+#ifdef MET2_HOST_EMU
+    emu_dmma884(d0, d1, a, b);
+#else
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(d0), "+d"(d1)
                  : "d"(a), "d"(b));
+#endif
 }
 
 // Blocked rebuild of the inverse Cholesky factor T for a GIVEN positive set (warm start): A = (G + lam K)_PP = R^T R,

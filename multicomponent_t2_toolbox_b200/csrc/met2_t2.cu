@@ -77,6 +77,7 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
 // number of shared full-set factor tables this configuration builds (0: none)
 static int t2_full_tables(const met2_t2_cfg* cfg) {
     if (cfg->flags & MET2_T2_FLAG_COLD_START) return 0;
+    if (t2_echo_eligible(cfg)) return 0;
     if (cfg->method == MET2_REG_X2 && (cfg->flags & MET2_T2_FLAG_FULL_START)) return T2_NTAB_X2;
     if (cfg->method == MET2_REG_BAYESREG) return T2_NTAB_BAYES;
     return 0;
@@ -178,6 +179,7 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     t2_scatter_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);
     count_launch();
     if ((rc = check_launch("t2_scatter_kernel"))) return rc;
+    if (t2_echo_eligible(cfg)) return t2_launch_echo_x2(A, st);
     switch (cfg->method) {
         case MET2_REG_NNLS: return t2_launch_nnls(A, g, st);
         case MET2_REG_T2SPARC: return t2_launch_t2sparc(A, g, st);

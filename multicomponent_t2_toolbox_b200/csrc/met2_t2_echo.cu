@@ -1,0 +1,533 @@
+// met2_t2_echo.cu — EXPERIMENTAL (opt-in, MET2_T2_FLAG_ECHO_SPACE): the X2 fit with its Tikhonov solves carried out in
+// ECHO SPACE.  Not on any default path; not yet run on a GPU (written at the end of round 1 with the GPU budget spent —
+// DESIGN.md §8 item 0).  Design evidence: tools/proto_dual_nnls.py / profiles/r01_proto_echo_space.txt (CPU): 0 of 2 000
+// support disagreements and spectra within 2.6e-11 of the unmodified reference inside the X2 search.
+//
+// For a DIAGONAL regularisation matrix L = diag(l) (reg_matrix I and InvT2) and lam > 0 the Tikhonov problem
+//     min_{x >= 0} |D x - b|^2 + lam |L x|^2,      Dt = D diag(1/l),  xt = l * x  (same sign pattern)
+// has, on a positive set P, the stationary point (push-through identity)
+//     v = (lam I_m + M_P)^-1 b,   M_P = sum_{j in P} dt_j dt_j^T   (m x m, independent of lam)
+//     zt_P = Dt_P^T v,            w_Z = lam Dt_Z^T v               (r = b - Dt_P zt_P = lam v)
+// so ONE product g = Dt^T v gives the coefficients on P and the dual on Z, a column entering / leaving P is a rank-one
+// change of M_P, and a new lambda costs one m x m factorisation (m = 32: tri(32) = 528 doubles per warp instead of
+// tri(60) = 1 830, which pins t2_fit_kernel at 10 warps per SM).  With lam > 0 both acceptance tests of nnls.f pass
+// identically (a regularised column is never dependent; its entering coefficient is w_j / (lam (1 + dt_j^T A^-1 dt_j))
+// > 0), so the control flow is the main loop + the interpolation loop of Lawson-Hanson (algorithms.py:55-82 -> nnls.f).
+//
+// The factor is the upper-triangular inverse Cholesky factor T, A^-1 = T T^T, A = lam I + M_P:
+//   new lambda     : rebuild_T_blocked (the FP64-tensor-core blocked factorisation of met2_nnls.cuh) on M_P + lam I
+//   A' = A + s d d^T: u = T^T d;  (I + s u u^T)^-1 = Q Q^T with Q upper triangular, Q_jj = delta_j, Q_ij = u_i q_j (i < j);
+//                    with tau_k = sum_{j <= k} u_j^2 (one warp scan), h_k = 1 + s tau_k:
+//                        delta_k = sqrt(h_{k-1} / h_k),   q_k = -s u_k / (h_k delta_k)
+//                    T' = T Q is a running sum along each ROW of T (one row per lane):
+//                        T'[r][j] = delta_j T[r][j] + q_j acc,   acc += T[r][j] u_j
+//                    (s = +1: h >= 1, no cancellation; s = -1: h_k >= 1 - u.u > 0, rebuilt from M_P if that fails).
+// Plain NNLS (lam = 0: the SSE of algorithms.py:213-214) stays in the Gram domain (nnls_gram).
+#include "met2_t2_impl.cuh"
+
+namespace met2 {
+
+constexpr int EC_M = 32;              // echoes (rows of the echo-space system); nTE <= 32, padded with zero rows
+constexpr int EC_LDD = 33;            // row stride of the staged Dt table: conflict-free for lane = row and lane = echo
+constexpr int EC_NCOL = 64;           // columns (nT2 <= 64), zero rows beyond nT2
+
+// per-warp shared memory (doubles): Slots<2>(pmax 32) | M_P packed lower (528) | signal (64) | v (32) | d (32) |
+// Brent-best snapshot of xt (64)
+__host__ __device__ __forceinline__ int echo_warp_doubles() {
+    return (Slots<2>::doubles(EC_M) + tri(EC_M) + 64 + 32 + 32 + 64 + 31) & ~31;
+}
+// CTA tables (doubles): G [n][ldg] | Dt [64][33] | M_full packed (528) | l (64) | 1/l (64) | logT2 (64) | comp (8)
+__host__ __device__ __forceinline__ int echo_table_doubles(int n) {
+    return (n * t2_ldg(n) + EC_NCOL * EC_LDD + tri(EC_M) + 3 * 64 + 8 + 31) & ~31;
+}
+
+struct EchoOff {
+    int Dt, Mp, B, V, D;   // offsets into S
+};
+
+// v = T (T^T b), g = Dt^T v.  lane = position / echo for the triangular products, lane + 32 s = column for g.
+__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[2]) {
+    double y[1], v[1];
+    tmul_transposed<1>(W.T, O.B, EC_M, lane, y);
+    S[W.rs + lane] = y[0];
+    __syncwarp();
+    tmul<1>(W.T, W.rs, EC_M, lane, v);
+    S[O.V + lane] = v[0];
+    __syncwarp();
+    double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
+    const int r0 = O.Dt + lane * EC_LDD, r1 = O.Dt + (lane + 32) * EC_LDD;
+#pragma unroll 1
+    for (int e = 0; e < EC_M; e += 2) {
+        const double v0 = S[O.V + e], v1 = S[O.V + e + 1];
+        g0 = fma(S[r0 + e], v0, g0);
+        h0 = fma(S[r0 + e + 1], v1, h0);
+        g1 = fma(S[r1 + e], v0, g1);
+        h1 = fma(S[r1 + e + 1], v1, h1);
+    }
+    g[0] = g0 + h0;
+    g[1] = g1 + h1;
+    __syncwarp();
+}
+
+// T <- inverse Cholesky factor of M_P + lam I.  Returns false if a pivot is not positive.
+__device__ __forceinline__ bool echo_refactor(const Slots<2>& W, const EchoOff& O, double lam, int lane) {
+    auto Aent = [&](int r, int c) -> double {
+        const int hi = (r > c) ? r : c, lo = (r > c) ? c : r;
+        double a = S[O.Mp + tri(hi) + lo];
+        if (r == c) a += lam;
+        return a;
+    };
+    __syncwarp();
+    return rebuild_T_blocked<2>(W, Aent, EC_M, lane);
+}
+
+// M_P += sgn d d^T on the packed lower triangle (row = lane), d = column j of the staged Dt table; leaves d in S[O.D..].
+__device__ __forceinline__ void echo_mp_rank1(const EchoOff& O, int j, double sgn, int lane) {
+    const double d = S[O.Dt + j * EC_LDD + lane];
+    __syncwarp();
+    S[O.D + lane] = d;
+    __syncwarp();
+    const int row = O.Mp + tri(lane);
+    const double sd = sgn * d;
+#pragma unroll 1
+    for (int c = 0; c < EC_M; ++c) {
+        if (c <= lane) S[row + c] = fma(sd, S[O.D + c], S[row + c]);
+    }
+    __syncwarp();
+}
+
+// Column j enters (sgn = +1) or leaves (sgn = -1) the positive set: M_P += sgn d d^T and the matching update of T.
+__device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O, int j, double sgn, double lam, int lane) {
+    echo_mp_rank1(O, j, sgn, lane);
+    // ---- u = T^T d, prefix sums of u^2
+    double u[1];
+    tmul_transposed<1>(W.T, O.D, EC_M, lane, u);
+    double tau[1] = {u[0] * u[0]};
+    warp_scan_positions<1>(tau, lane);
+    const double h = fma(sgn, tau[0], 1.0);
+    double hm1 = __shfl_up_sync(FULL_MASK, h, 1);
+    if (lane == 0) hm1 = 1.0;
+    const bool okh = (h > 0.0) && (hm1 > 0.0);
+    if (!__all_sync(FULL_MASK, okh)) {
+        // downdate lost positivity in floating point: refactor from the (already updated) M_P
+        return echo_refactor(W, O, lam, lane);
+    }
+    const double delta = sqrt(hm1 / h);
+    const double q = -sgn * u[0] / (h * delta);
+    S[W.gs + lane] = delta;
+    S[W.gs + 32 + lane] = q;
+    S[W.rs + lane] = u[0];
+    __syncwarp();
+    // ---- T' = T Q, one row of T per lane (row r has entries in columns j >= r)
+    {
+        double acc = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < EC_M; ++c) {
+            if (c >= lane) {
+                const int a = W.T + tri(c) + lane;
+                const double t = S[a];
+                S[a] = fma(S[W.gs + c], t, S[W.gs + 32 + c] * acc);
+                acc = fma(t, S[W.rs + c], acc);
+            }
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// Lawson-Hanson in echo space for one lambda.  On entry T is the factor of M_P + lam I for the set `inP` (bit s of lane
+// l = column l + 32 s) and x[s] holds a feasible point on it (x > 0 on P, 0 elsewhere); an empty set is allowed.
+// block_drop: the entry set is the FULL column set — drop every column whose unconstrained coefficient is not positive
+// in one go before the usual interpolation loop (x stays feasible on the reduced set).
+// On exit inP / x hold the solution (scaled unknowns xt = l * x).
+__device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, int n, double lam, int lane,
+                                          unsigned& inP, double (&x)[2], int& status, bool block_drop) {
+    const int itmax = 3 * n;
+    int iter = 0;
+    bool secondary_first = __any_sync(FULL_MASK, inP != 0u);
+    bool have_g = false;   // g is the solve for the current set (left by an accepted interpolation loop)
+    double g[2];
+    while (true) {
+        if (!secondary_first) {
+            if ((int)__reduce_add_sync(FULL_MASK, (unsigned)__popc(inP)) >= n) break;
+            // ---- entering column: arg-max of the dual w = lam g over the zero set (lam > 0: same order as g)
+            if (!have_g) echo_solve(W, O, lane, g);
+            double bv = 0.0;
+            int bj = -1;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int col = lane + 32 * s;
+                if (col < n && !((inP >> s) & 1u) && g[s] > bv) {
+                    bv = g[s];
+                    bj = col;
+                }
+            }
+            const int j = warp_argmax_pos(bv, bj);
+            if (j < 0) break;
+            if ((j & 31) == lane) inP |= 1u << (j >> 5);
+            if (!echo_change(W, O, j, 1.0, lam, lane)) status |= 2;
+        }
+        secondary_first = false;
+        have_g = false;
+        bool stop = false;
+        while (true) {
+            ++iter;
+            if (iter > itmax) {
+                status |= 1;
+                stop = true;
+                break;
+            }
+            echo_solve(W, O, lane, g);
+            const bool drop_now = block_drop;
+            block_drop = false;
+            unsigned negm = 0u;
+#pragma unroll
+            for (int s = 0; s < 2; ++s)
+                if (((inP >> s) & 1u) && g[s] <= 0.0) negm |= 1u << s;
+            if (!__any_sync(FULL_MASK, negm != 0u)) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) x[s] = ((inP >> s) & 1u) ? g[s] : 0.0;
+                have_g = true;
+                break;
+            }
+            unsigned outm = 0u;   // columns that leave now
+            if (drop_now) {
+                outm = negm;
+            } else {
+                double bt = 2.0;
+                int bi = -1;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if ((negm >> s) & 1u) {
+                        const double tt = x[s] / (x[s] - g[s]);
+                        if (tt < bt) {
+                            bt = tt;
+                            bi = lane + 32 * s;
+                        }
+                    }
+                }
+                double alpha = 0.0;
+                const int jb = warp_argmin_nonneg(bt, bi, alpha);
+                if (jb < 0) break;
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    if ((inP >> s) & 1u) {
+                        x[s] = x[s] + alpha * (g[s] - x[s]);
+                        if (x[s] <= 0.0 || lane + 32 * s == jb) outm |= 1u << s;
+                    }
+                }
+            }
+            // ---- remove them one by one (lowest column first)
+            while (true) {
+                int k = 0x7fffffff;
+                if (outm & 2u) k = lane + 32;
+                if (outm & 1u) k = lane;
+                k = (int)__reduce_min_sync(FULL_MASK, (unsigned)k);
+                if (k == 0x7fffffff) break;
+                if ((k & 31) == lane) {
+                    const unsigned bit = 1u << (k >> 5);
+                    outm &= ~bit;
+                    inP &= ~bit;
+                    if (k >> 5) x[1] = 0.0;
+                    else x[0] = 0.0;
+                }
+                if (!echo_change(W, O, k, -1.0, lam, lane)) status |= 2;
+            }
+        }
+        if (stop) break;
+    }
+}
+
+// fit = Dt xt (= D x) with lane = echo, SSE = sum (fit - b)^2.  xt is read from S[W.xc + 0..64) (column space).
+__device__ __forceinline__ double echo_fit_sse(const Slots<2>& W, const EchoOff& O, int n, int lane, double& fit) {
+    double f0 = 0.0, f1 = 0.0;
+    int j = 0;
+#pragma unroll 1
+    for (; j + 1 < n; j += 2) {
+        f0 = fma(S[O.Dt + j * EC_LDD + lane], S[W.xc + j], f0);
+        f1 = fma(S[O.Dt + (j + 1) * EC_LDD + lane], S[W.xc + j + 1], f1);
+    }
+    if (j < n) f0 = fma(S[O.Dt + j * EC_LDD + lane], S[W.xc + j], f0);
+    fit = f0 + f1;
+    const double dd = fit - S[O.B + lane];
+    return warp_sum(dd * dd);
+}
+
+constexpr int ECHO_MAX_THREADS = 416;   // 13 warps: (227 KB - 52 KB of tables) / 12.8 KB per warp at nT2 = 60
+
+__global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args A) {
+    __shared__ int s_tile, s_next, s_badL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = A.cfg.nT2, m = A.cfg.nTE;
+    const int ldg = t2_ldg(n);
+    const int oG = 0;
+    const int oDt = oG + n * ldg;
+    const int oMf = oDt + EC_NCOL * EC_LDD;
+    const int oL = oMf + tri(EC_M);
+    const int oIL = oL + 64;
+    const int oLogT2 = oIL + 64;
+    unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + 64);
+    const int wbase = echo_table_doubles(n) + warp * echo_warp_doubles();
+    Slots<2> W;
+    W.carve(wbase, EC_M);
+    EchoOff O;
+    O.Dt = oDt;
+    O.Mp = wbase + Slots<2>::doubles(EC_M);
+    const int oM = O.Mp + tri(EC_M);
+    O.B = oM;
+    O.V = oM + 64;
+    O.D = O.V + 32;
+    const int oSnap = O.D + 32;
+
+    if (threadIdx.x == 0) s_badL = 0;
+    __syncthreads();
+    // l = diag(L) from the row-band form (kband rows 5..9: kband[5 + d][r] = L[r][r + d - 2]); every other band must be 0
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+        double l = 1.0;
+        if (i < n) {
+            l = A.kband[7 * n + i];
+            bool bad = !(l > 0.0) || !(l < 1e300);
+            for (int d = 0; d < 5; ++d)
+                if (d != 2 && A.kband[(5 + d) * n + i] != 0.0) bad = true;
+            if (bad) atomicOr(&s_badL, 1);
+        }
+        S[oL + i] = l;
+        S[oIL + i] = 1.0 / l;
+        S[oLogT2 + i] = (i < n) ? A.logT2[i] : 0.0;
+        if (i < n) scomp[i] = A.comp[i];
+    }
+    const int ntiles = A.counters[0];
+
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(&A.counters[1], 1);
+            s_next = 0;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const bool badL = (s_badL != 0);
+        const int fa = A.tile_fa[tile];
+        const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
+        const double* D = A.dic + (size_t)fa * m * n;
+        const double* Dtg = A.dicT + (size_t)fa * n * m;
+        {
+            const double* Gg = A.G + (size_t)fa * n * n;
+            for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
+                const int r = i / n;
+                S[oG + r * ldg + (i - r * n)] = __ldg(Gg + i);
+            }
+            // Dt[j][e] = D[e][j] / l_j, zero rows / echoes beyond (n, m)
+            for (int i = threadIdx.x; i < EC_NCOL * EC_LDD; i += blockDim.x) {
+                const int j = i / EC_LDD, e = i - j * EC_LDD;
+                S[oDt + i] = (j < n && e < m) ? __ldg(Dtg + j * m + e) * S[oIL + j] : 0.0;
+            }
+        }
+        __syncthreads();
+        // M_full = Dt^T-table product over ALL columns, packed lower triangle
+        for (int i = threadIdx.x; i < tri(EC_M); i += blockDim.x) {
+            int r = 0;
+            while (tri(r + 1) <= i) ++r;
+            const int c = i - tri(r);
+            double a0 = 0.0, a1 = 0.0;
+            int j = 0;
+            for (; j + 1 < n; j += 2) {
+                a0 = fma(S[oDt + j * EC_LDD + r], S[oDt + j * EC_LDD + c], a0);
+                a1 = fma(S[oDt + (j + 1) * EC_LDD + r], S[oDt + (j + 1) * EC_LDD + c], a1);
+            }
+            if (j < n) a0 = fma(S[oDt + j * EC_LDD + r], S[oDt + j * EC_LDD + c], a0);
+            S[oMf + i] = a0 + a1;
+        }
+        __syncthreads();
+
+        while (true) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&s_next, 1);
+            it = __shfl_sync(FULL_MASK, it, 0);
+            if (it >= tcnt) break;
+            const long long v = A.perm[tstart + it];
+            unsigned st = load_signal<1>(A.sig, v, m, oM, lane);
+            const int fav = A.fa_index[v];
+            const bool normalise = !(A.cfg.flags & MET2_T2_FLAG_NO_NORMALISE);
+            const double km = normalise ? S[oM] : 1.0;
+            if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
+            if (!st && badL) st = MET2_ST_SKIPPED | MET2_ST_ECHO_BAD_L;
+            double regv = 0.0, fit = 0.0;
+            if (!st) {
+                __syncwarp();
+                S[oM + lane] = (lane < m) ? S[oM + lane] / km : 0.0;
+                __syncwarp();
+                // ---- plain NNLS in the Gram domain -> SSE (algorithms.py:213-214)
+                compute_c<2>(W, D, oM, m, n, lane);
+                int nst = 0;
+                int p = nnls_gram<2, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, 0, false);
+                double fit1[1];
+                const double SSE = fit_and_sse<2, 1>(W, Dtg, oM, m, p, lane, fit1);
+                if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
+                // ---- starting set of the first Tikhonov solve
+                Brent B;
+                double lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
+                unsigned inP = 0u;
+                double x[2] = {0.0, 0.0};
+                bool block_drop = false;
+                if (A.cfg.flags & MET2_T2_FLAG_FULL_START) {
+                    // every column, feasible point xt_j = ct_j / (Gt_jj + lam) with ct = c / l, Gt_jj = G_jj / l_j^2
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int j = lane + 32 * s;
+                        if (j < n) {
+                            const double il = S[oIL + j];
+                            const double djj = fma(S[oG + j * ldg + j], il * il, lam);
+                            x[s] = fmax(S[W.cc + j] * il / djj, 1e-300);
+                            inP |= 1u << s;
+                        }
+                    }
+                    for (int i = lane; i < tri(EC_M); i += 32) S[O.Mp + i] = S[oMf + i];
+                    block_drop = true;
+                } else {
+                    // the plain solution's support and coefficients (scaled); M_P by rank-one terms
+                    for (int i = lane; i < tri(EC_M); i += 32) S[O.Mp + i] = 0.0;
+                    __syncwarp();
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int j = lane + 32 * s;
+                        const double xv = (j < n) ? S[W.xc + j] : 0.0;
+                        if (xv > 0.0) {
+                            x[s] = xv * S[oL + j];
+                            inP |= 1u << s;
+                        }
+                    }
+                    for (int j = 0; j < n; ++j) {
+                        const bool in = (__shfl_sync(FULL_MASK, inP, j & 31) >> (j >> 5)) & 1u;
+                        if (in) echo_mp_rank1(O, j, 1.0, lane);
+                    }
+                }
+                __syncwarp();
+                // ---- Brent on |SSE(lam) - factor SSE| / SSE  (algorithms.py:219-233)
+                double sse_snap = 0.0;
+                int est = 0;
+                while (true) {
+                    if (!echo_refactor(W, O, lam, lane)) st |= MET2_ST_NOT_PD;
+                    echo_nnls(W, O, n, lam, lane, inP, x, est, block_drop);
+                    block_drop = false;
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) S[W.xc + lane + 32 * s] = x[s];
+                    __syncwarp();
+                    const double sse = echo_fit_sse(W, O, n, lane, fit);
+                    const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
+                    const double lam_eval = lam;
+                    const bool more = B.feed(cost, lam);
+                    if (B.xf == lam_eval) {
+                        // the reference re-solves at Brent's best abscissa: keep that evaluation's solution instead
+#pragma unroll
+                        for (int s = 0; s < 2; ++s) S[oSnap + lane + 32 * s] = x[s];
+                        sse_snap = sse;
+                    }
+                    __syncwarp();
+                    if (!more) break;
+                }
+                lam = B.xf;
+                // ---- hand out the best solution: x = xt / l
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int j = lane + 32 * s;
+                    S[W.xc + j] = S[oSnap + j];
+                }
+                __syncwarp();
+                (void)echo_fit_sse(W, O, n, lane, fit);
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int j = lane + 32 * s;
+                    S[W.xc + j] = S[oSnap + j] * S[oIL + j];
+                }
+                __syncwarp();
+                regv = (A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA) ? lam : sse_snap / SSE;
+                if (nst || (est & 1)) st |= MET2_ST_ITMAX;
+                if (est & 2) st |= MET2_ST_NOT_PD;
+            }
+            // ---- outputs: fsol = x*km, Est_Signal = (D x)*km, reg, maps (motor...:153-155, 443-472)
+            const bool fitted = !(st & MET2_ST_SKIPPED);
+            const double kmo = fitted ? km : 0.0;
+            double xk[2];
+            double vt = 0.0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int col = 2 * lane + s;
+                xk[s] = (col < n && fitted) ? S[W.xc + col] * kmo : 0.0;
+                vt += xk[s];
+                if (col < n) A.fsol[v * n + col] = xk[s];
+            }
+            if (lane < m) A.est[v * m + lane] = fitted ? fit * kmo : 0.0;
+            vt = warp_sum(vt) + 1.0e-16;
+            double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                const int col = 2 * lane + s;
+                if (col < n) {
+                    const double xn = xk[s] / vt;
+                    const unsigned char cm = scomp[col];
+                    if (cm & 1) {
+                        sm += xn;
+                        lm += xn * S[oLogT2 + col];
+                    }
+                    if (cm & 2) {
+                        stt += xn;
+                        lt += xn * S[oLogT2 + col];
+                    }
+                    if (cm & 4) sc += xn;
+                }
+            }
+            sm = warp_sum(sm);
+            stt = warp_sum(stt);
+            sc = warp_sum(sc);
+            lm = warp_sum(lm);
+            lt = warp_sum(lt);
+            if (lane == 0) {
+                double* mp = A.maps + v * 6;
+                mp[0] = sm;
+                mp[1] = stt;
+                mp[2] = sc;
+                mp[3] = exp(lm / (sm + 1.0e-16));
+                mp[4] = exp(lt / (stt + 1.0e-16));
+                mp[5] = vt;
+                A.reg[v] = fitted ? regv : 0.0;
+                A.status[v] = st;
+            }
+            __syncwarp();
+        }
+    }
+}
+
+bool t2_echo_eligible(const met2_t2_cfg* cfg) {
+    return cfg->method == MET2_REG_X2 && (cfg->flags & MET2_T2_FLAG_ECHO_SPACE) && cfg->nTE <= EC_M &&
+           cfg->nT2 <= EC_NCOL && !(cfg->flags & MET2_T2_FLAG_COLD_START);
+}
+
+#ifndef MET2_HOST_EMU
+int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
+    const int n = A.cfg.nT2;
+    const size_t tables = sizeof(double) * (size_t)echo_table_doubles(n);
+    const size_t per_warp = sizeof(double) * (size_t)echo_warp_doubles();
+    const size_t budget = 227 * 1024 - 1024;
+    int warps = (int)((budget - tables) / per_warp);
+    if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
+    if (warps < 1) return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit (echo space): tables do not fit in shared memory");
+    if (const char* ev = getenv("MET2_T2_WARPS")) {
+        const int w = atoi(ev);
+        if (w >= 1 && w < warps) warps = w;
+    }
+    const size_t smem = tables + per_warp * warps;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    cudaError_t e = cudaFuncSetAttribute(t2_echo_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_echo attr (%zu B): %s", smem, cudaGetErrorString(e));
+    t2_echo_x2_kernel<<<sms, warps * 32, smem, st>>>(A);
+    count_launch();
+    return check_launch("t2_echo_x2_kernel");
+}
+#endif  // MET2_HOST_EMU
+
+}  // namespace met2

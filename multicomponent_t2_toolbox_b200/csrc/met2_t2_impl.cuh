@@ -933,6 +933,7 @@ static inline T2Geom t2_geometry_any(long long V, const met2_t2_cfg* cfg) {
     return t2_geometry<4>(V, cfg);
 }
 
+#ifndef MET2_HOST_EMU
 template <int NS, int ME, int METHOD>
 static int t2_launch_one(const T2Args& A, const T2Geom& g, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(t2_fit_kernel<NS, ME, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -954,6 +955,7 @@ static int t2_launch_method(const T2Args& A, const T2Geom& g, cudaStream_t st) {
     if (ns == 4 && me == 2) return t2_launch_one<4, 2, METHOD>(A, g, st);
     return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: unsupported template sizes");
 }
+#endif  // MET2_HOST_EMU
 
 // one definition per method, in met2_t2_m<method>.cu
 int t2_launch_nnls(const T2Args& A, const T2Geom& g, cudaStream_t st);
@@ -962,5 +964,8 @@ int t2_launch_x2(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_lcurve(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_bayesreg(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_gcv(const T2Args& A, const T2Geom& g, cudaStream_t st);
+// met2_t2_echo.cu (experimental, MET2_T2_FLAG_ECHO_SPACE)
+bool t2_echo_eligible(const met2_t2_cfg* cfg);
+int t2_launch_echo_x2(const T2Args& A, cudaStream_t st);
 
 }  // namespace met2

@@ -1,0 +1,104 @@
+// emu_kernels.cpp — TEST INFRASTRUCTURE ONLY: the T2 fit kernels of csrc/ compiled by g++ against the SIMT emulator
+// (simt_emu.h) and exposed through a tiny C interface for tests/test_emu_kernels.py.  Host arrays in, host arrays out;
+// one emulated thread block walks every tile.  Nothing here is reachable from the product library.
+#define MET2_HOST_EMU 1
+#include "simt_emu.h"
+
+namespace simt {
+Block* g_block = nullptr;
+emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+}  // namespace simt
+
+#include "met2_t2_echo.cu"
+
+namespace met2 {
+alignas(16) double S[40960];   // 320 KB: more than any kernel's dynamic shared memory
+int set_error(int code, const char*, ...) { return code; }
+int check_launch(const char*) { return 0; }
+void count_launch(int) {}
+int sm_count() { return 1; }
+}  // namespace met2
+
+using namespace met2;
+
+// Host stand-in for t2_hist / t2_tiles / t2_scatter: one tile per populated flip-angle index (split at T2_TILE_MAX).
+static void make_tiles(const int* fa_index, long long V, int nA, std::vector<int>& perm, std::vector<int>& tile_fa,
+                       std::vector<int>& tile_start, std::vector<int>& tile_cnt) {
+    std::vector<std::vector<int>> bins(nA);
+    for (long long v = 0; v < V; ++v) {
+        int f = fa_index[v];
+        if (f < 0 || f >= nA) f = 0;
+        bins[f].push_back((int)v);
+    }
+    for (int a = 0; a < nA; ++a) {
+        for (size_t s = 0; s < bins[a].size(); s += T2_TILE_MAX) {
+            tile_fa.push_back(a);
+            tile_start.push_back((int)perm.size() + 0);
+            const size_t c = std::min(bins[a].size() - s, (size_t)T2_TILE_MAX);
+            tile_cnt.push_back((int)c);
+            for (size_t i = 0; i < c; ++i) perm.push_back(bins[a][s + i]);
+        }
+    }
+}
+
+struct Prepared {
+    std::vector<int> perm, tile_fa, tile_start, tile_cnt;
+    int counters[4];
+};
+
+static T2Args make_args(Prepared& P, const double* sig, const int* fa_index, long long V, const met2_t2_cfg* cfg,
+                        const double* dic, const double* dicT, const double* G, const double* kband,
+                        const double* lambdas, const double* logT2, const unsigned char* comp, double* fsol, double* est,
+                        double* reg, double* maps, unsigned* status) {
+    make_tiles(fa_index, V, cfg->nA, P.perm, P.tile_fa, P.tile_start, P.tile_cnt);
+    P.counters[0] = (int)P.tile_fa.size();
+    P.counters[1] = 0;
+    T2Args A;
+    memset(&A, 0, sizeof(A));
+    A.sig = sig; A.fa_index = fa_index; A.V = V; A.cfg = *cfg;
+    A.dic = dic; A.dicT = dicT; A.G = G; A.kband = kband; A.lambdas = lambdas; A.logT2 = logT2; A.comp = comp;
+    A.fsol = fsol; A.est = est; A.reg = reg; A.maps = maps; A.status = status;
+    A.perm = P.perm.data(); A.tile_fa = P.tile_fa.data(); A.tile_start = P.tile_start.data();
+    A.tile_cnt = P.tile_cnt.data(); A.counters = P.counters;
+    return A;
+}
+
+extern "C" {
+
+// The experimental echo-space X2 kernel (csrc/met2_t2_echo.cu).  Returns the number of warp collectives executed.
+long long emu_t2_echo_x2(const double* sig, const int* fa_index, long long V, const met2_t2_cfg* cfg, const double* dic,
+                         const double* dicT, const double* G, const double* kband, const double* logT2,
+                         const unsigned char* comp, double* fsol, double* est, double* reg, double* maps,
+                         unsigned* status, int warps) {
+    if (!t2_echo_eligible(cfg)) return -1;
+    Prepared P;
+    T2Args A = make_args(P, sig, fa_index, V, cfg, dic, dicT, G, kband, nullptr, logT2, comp, fsol, est, reg, maps, status);
+    if ((size_t)(echo_table_doubles(cfg->nT2) + warps * echo_warp_doubles()) > sizeof(S) / sizeof(double)) return -2;
+    return simt::run_block(warps * 32, 0, 1, [&]() { t2_echo_x2_kernel(A); });
+}
+
+// The production kernel t2_fit_kernel<2, 1, METHOD> (nT2 <= 64, nTE <= 32) without the shared full-set factor tables
+// (A.tfull = NULL: those only shortcut factorisations) — same code path as the GPU otherwise.
+long long emu_t2_fit(const double* sig, const int* fa_index, long long V, const met2_t2_cfg* cfg, const double* dic,
+                     const double* dicT, const double* G, const double* kband, const double* lambdas, const double* logT2,
+                     const unsigned char* comp, double* fsol, double* est, double* reg, double* maps, unsigned* status,
+                     int warps) {
+    if (cfg->nT2 > 64 || cfg->nTE > 32) return -1;
+    Prepared P;
+    T2Args A = make_args(P, sig, fa_index, V, cfg, dic, dicT, G, kband, lambdas, logT2, comp, fsol, est, reg, maps, status);
+    const bool plain = (cfg->method == MET2_REG_NNLS);
+    A.pmax = plain ? std::min(cfg->nT2, cfg->nTE) : cfg->nT2;
+    if (cfg->method == MET2_REG_GCV)
+        while (tri(A.pmax) < gcv_region_doubles(cfg->nT2)) ++A.pmax;
+    A.warps = warps;
+    if ((size_t)(t2_table_doubles(cfg->nT2) + warps * t2_warp_doubles<2>(A.pmax)) > sizeof(S) / sizeof(double)) return -2;
+    switch (cfg->method) {
+        case MET2_REG_NNLS: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_NNLS>(A); });
+        case MET2_REG_T2SPARC: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_T2SPARC>(A); });
+        case MET2_REG_X2: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_X2>(A); });
+        case MET2_REG_LCURVE: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_LCURVE>(A); });
+        default: return -3;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,270 @@
+// simt_emu.h — TEST INFRASTRUCTURE ONLY.  A single-threaded SIMT emulator that lets g++ compile and run the device code
+// of multicomponent_t2_toolbox_b200/csrc/*.cuh|*.cu on the CPU, so that the kernels' control flow, indexing and warp
+// collectives can be exercised in the `-m "not gpu"` tests (this container has no GPU).  It is never linked into
+// libmet2.so: the csrc headers include it only under MET2_HOST_EMU, which only tests/emu/*.cpp define.
+//
+// Model: ONE thread block; every CUDA thread is a ucontext fiber; the scheduler runs the fibers round-robin and a fiber
+// yields whenever it waits at a barrier.  Warp collectives (__shfl*_sync, __reduce_*_sync, votes, the FP64 MMA) are
+// "deposit -> warp barrier -> read -> warp barrier" on a per-warp exchange buffer, which is exact for the code under
+// test: every collective is called with the full mask from warp-uniform control flow.  Shared memory is one global
+// array; `__shared__` locals become statics (one block at a time).  Arithmetic is IEEE double with explicit std::fma,
+// compiled with -ffp-contract=off like the library's -fmad=false.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ucontext.h>
+
+#include <cmath>
+#include <functional>
+#include <vector>
+
+#define __host__
+#define __device__
+#define __global__
+#define __forceinline__ inline __attribute__((always_inline))
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+typedef void* cudaStream_t;
+struct double2 {
+    double x, y;
+};
+struct emu_dim3 {
+    unsigned x, y, z;
+};
+
+namespace simt {
+
+struct Fiber {
+    ucontext_t ctx;
+    std::vector<char> stack;
+    int tid = 0;
+    bool done = false;
+};
+
+struct Block {
+    std::vector<Fiber> fibers;
+    ucontext_t sched;
+    int cur = 0;
+    int nthreads = 0;
+    // barriers: generation counters
+    int cta_arrived = 0, cta_gen = 0;
+    std::vector<int> warp_arrived, warp_gen;
+    std::vector<uint64_t> xbuf;   // [warp][32][2] exchange slots
+    std::function<void()> body;
+    long long collectives = 0;
+};
+
+extern Block* g_block;
+extern emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+
+inline int lane_id() { return g_block->cur & 31; }
+inline int warp_id() { return g_block->cur >> 5; }
+
+inline void yield() {
+    Block* b = g_block;
+    swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+}
+
+inline void warp_barrier() {
+    Block* b = g_block;
+    const int w = warp_id();
+    const int gen = b->warp_gen[w];
+    if (++b->warp_arrived[w] == 32) {
+        b->warp_arrived[w] = 0;
+        ++b->warp_gen[w];
+        return;
+    }
+    while (b->warp_gen[w] == gen) yield();
+}
+
+inline void cta_barrier() {
+    Block* b = g_block;
+    const int gen = b->cta_gen;
+    if (++b->cta_arrived == b->nthreads) {
+        b->cta_arrived = 0;
+        ++b->cta_gen;
+        return;
+    }
+    while (b->cta_gen == gen) yield();
+}
+
+inline uint64_t* slot(int lane, int k = 0) { return &g_block->xbuf[((size_t)warp_id() * 32 + lane) * 2 + k]; }
+
+template <class T>
+inline uint64_t to_bits(T v) {
+    uint64_t u = 0;
+    memcpy(&u, &v, sizeof(T));
+    return u;
+}
+template <class T>
+inline T from_bits(uint64_t u) {
+    T v;
+    memcpy(&v, &u, sizeof(T));
+    return v;
+}
+
+// every lane deposits v; returns the value deposited by lane `src`
+template <class T>
+inline T exchange(T v, int src) {
+    ++g_block->collectives;
+    *slot(lane_id()) = to_bits(v);
+    warp_barrier();
+    T r = from_bits<T>(*slot(src & 31));
+    warp_barrier();
+    return r;
+}
+
+template <class T, class F>
+inline T reduce_all(T v, F f) {
+    ++g_block->collectives;
+    *slot(lane_id()) = to_bits(v);
+    warp_barrier();
+    T r = from_bits<T>(*slot(0));
+    for (int l = 1; l < 32; ++l) r = f(r, from_bits<T>(*slot(l)));
+    warp_barrier();
+    return r;
+}
+
+static void fiber_entry() {
+    Block* b = g_block;
+    b->body();
+    b->fibers[b->cur].done = true;
+    swapcontext(&b->fibers[b->cur].ctx, &b->sched);
+}
+
+// Run `body` as one thread block of `nthreads` threads (a multiple of 32).
+inline long long run_block(int nthreads, int block_index, int grid, std::function<void()> body) {
+    Block blk;
+    g_block = &blk;
+    blk.nthreads = nthreads;
+    blk.body = body;
+    blk.fibers.resize(nthreads);
+    blk.warp_arrived.assign(nthreads / 32, 0);
+    blk.warp_gen.assign(nthreads / 32, 0);
+    blk.xbuf.assign((size_t)nthreads * 2, 0);
+    g_blockIdx = {(unsigned)block_index, 0, 0};
+    g_blockDim = {(unsigned)nthreads, 1, 1};
+    g_gridDim = {(unsigned)grid, 1, 1};
+    for (int t = 0; t < nthreads; ++t) {
+        Fiber& f = blk.fibers[t];
+        f.tid = t;
+        f.stack.resize(512 * 1024);
+        getcontext(&f.ctx);
+        f.ctx.uc_stack.ss_sp = f.stack.data();
+        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_link = &blk.sched;
+        makecontext(&f.ctx, (void (*)())fiber_entry, 0);
+    }
+    int live = nthreads;
+    long long idle_rounds = 0;
+    while (live > 0) {
+        int progressed = 0;
+        for (int t = 0; t < nthreads; ++t) {
+            Fiber& f = blk.fibers[t];
+            if (f.done) continue;
+            blk.cur = t;
+            g_threadIdx = {(unsigned)t, 0, 0};
+            swapcontext(&blk.sched, &f.ctx);
+            ++progressed;
+            if (f.done) --live;
+        }
+        if (!progressed) break;
+        if (++idle_rounds > 2000000000LL) {
+            fprintf(stderr, "simt_emu: scheduler ran away\n");
+            abort();
+        }
+    }
+    g_block = nullptr;
+    return blk.collectives;
+}
+
+}  // namespace simt
+
+#define threadIdx (simt::g_threadIdx)
+#define blockIdx (simt::g_blockIdx)
+#define blockDim (simt::g_blockDim)
+#define gridDim (simt::g_gridDim)
+
+// ------------------------------------------------------------------------------------------------ intrinsics
+inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier(); }
+inline void __syncthreads() { simt::cta_barrier(); }
+
+template <class T>
+inline T __ldg(const T* p) { return *p; }
+
+template <class T>
+inline T __shfl_sync(unsigned, T v, int src) { return simt::exchange<T>(v, src); }
+template <class T>
+inline T __shfl_xor_sync(unsigned, T v, int o) { return simt::exchange<T>(v, simt::lane_id() ^ o); }
+template <class T>
+inline T __shfl_up_sync(unsigned, T v, int o) {
+    const int l = simt::lane_id();
+    return simt::exchange<T>(v, (l - o >= 0) ? l - o : l);
+}
+inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    return simt::reduce_all<unsigned>(v, [](unsigned a, unsigned b) { return a > b ? a : b; });
+}
+inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    return simt::reduce_all<unsigned>(v, [](unsigned a, unsigned b) { return a < b ? a : b; });
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned v) {
+    return simt::reduce_all<unsigned>(v, [](unsigned a, unsigned b) { return a + b; });
+}
+inline int __reduce_add_sync(unsigned, int v) {
+    return simt::reduce_all<int>(v, [](int a, int b) { return a + b; });
+}
+inline unsigned __ballot_sync(unsigned, bool pred) {
+    ++simt::g_block->collectives;
+    *simt::slot(simt::lane_id()) = pred ? 1u : 0u;
+    simt::warp_barrier();
+    unsigned r = 0;
+    for (int l = 0; l < 32; ++l)
+        if (*simt::slot(l)) r |= 1u << l;
+    simt::warp_barrier();
+    return r;
+}
+inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
+inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
+
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline long long __double_as_longlong(double d) { return simt::from_bits<long long>(simt::to_bits(d)); }
+inline double __longlong_as_double(long long v) { return simt::from_bits<double>(simt::to_bits(v)); }
+inline float __frcp_rn(float x) { return 1.0f / x; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline double rsqrt(double x) { return 1.0 / sqrt(x); }
+inline int atomicAdd(int* p, int v) {
+    int o = *p;
+    *p = o + v;
+    return o;
+}
+inline int atomicOr(int* p, int v) {
+    int o = *p;
+    *p = o | v;
+    return o;
+}
+using std::fma;
+using std::isfinite;
+
+// FP64 MMA m8n8k4: D(8x8) += A(8x4) B(4x8); fragments A[lane/4][lane%4], B[lane%4][lane/4], C/D[lane/4][2*(lane%4)+{0,1}]
+inline void emu_dmma884(double& d0, double& d1, double a, double b) {
+    ++simt::g_block->collectives;
+    const int lane = simt::lane_id();
+    *simt::slot(lane, 0) = simt::to_bits(a);
+    *simt::slot(lane, 1) = simt::to_bits(b);
+    simt::warp_barrier();
+    const int g = lane >> 2, q = lane & 3;
+    for (int k = 0; k < 4; ++k) {
+        const double av = simt::from_bits<double>(*simt::slot(4 * g + k, 0));
+        const double b0 = simt::from_bits<double>(*simt::slot(4 * (2 * q) + k, 1));
+        const double b1 = simt::from_bits<double>(*simt::slot(4 * (2 * q + 1) + k, 1));
+        d0 = std::fma(av, b0, d0);
+        d1 = std::fma(av, b1, d1);
+    }
+    simt::warp_barrier();
+}
