@@ -161,11 +161,31 @@ inline long long run_block(int nthreads, int block_index, int grid, std::functio
         f.ctx.uc_link = &blk.sched;
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }
+    // Scheduling order of the fibers inside a round.  A kernel whose results depend on it has a missing barrier (a lane
+    // reading what another lane of the same phase writes): SIMT_EMU_ORDER=reverse runs the lanes 31..0, =shuffle draws a
+    // new pseudo-random permutation every round.  The tests run every kernel under all three orders.
+    std::vector<int> order(nthreads);
+    for (int t = 0; t < nthreads; ++t) order[t] = t;
+    const char* ord = getenv("SIMT_EMU_ORDER");
+    const bool reverse = ord && !strcmp(ord, "reverse"), shuffle = ord && !strcmp(ord, "shuffle");
+    if (reverse)
+        for (int t = 0; t < nthreads; ++t) order[t] = nthreads - 1 - t;
+    uint64_t rng = 0x9E3779B97F4A7C15ull;
     int live = nthreads;
     long long idle_rounds = 0;
     while (live > 0) {
         int progressed = 0;
-        for (int t = 0; t < nthreads; ++t) {
+        if (shuffle) {
+            for (int t = nthreads - 1; t > 0; --t) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                const int u = (int)((rng >> 33) % (uint64_t)(t + 1));
+                const int tmp = order[t];
+                order[t] = order[u];
+                order[u] = tmp;
+            }
+        }
+        for (int oi = 0; oi < nthreads; ++oi) {
+            const int t = order[oi];
             Fiber& f = blk.fibers[t];
             if (f.done) continue;
             blk.cur = t;

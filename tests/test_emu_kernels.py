@@ -1,0 +1,142 @@
+"""The T2 fit kernels' OWN SOURCE (csrc/met2_t2_impl.cuh, met2_nnls.cuh, met2_t2_echo.cu) compiled by g++ against the
+single-threaded SIMT emulator of tests/emu and run on the CPU — control flow, shared-memory indexing, warp collectives
+and the blocked FP64-MMA factorisation included — against voxels fitted by the unmodified reference
+(tests/golden/config2_subset.npz) and against the oracle.  This container has no GPU; the `-m gpu` tests repeat the same
+comparisons on the device.  Tolerances are BASELINE.json's: active sets bit-exact, spectra 1e-6 relative, maps 1e-4.
+
+Every kernel is run under three lane-scheduling orders (0..31, 31..0, a fresh random permutation every round): a result
+that depends on the order means a missing barrier between a write and a read of two lanes.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import met2_oracle as O
+from emu import emu
+
+ORDERS = ("forward", "reverse", "shuffle")
+
+
+@pytest.fixture(scope="module")
+def setup(golden_config2):
+    gr = O._grids("X2", "I", "spline", 40.0, 32, 10.0, 1000.0)
+    Dic = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, gr["alpha_values"], 1000.0)
+    emu.build()
+    return dict(gr=gr, Dic=Dic, g=golden_config2)
+
+
+def _run(order, *args, **kw):
+    old = os.environ.get("SIMT_EMU_ORDER")
+    os.environ["SIMT_EMU_ORDER"] = order
+    try:
+        return emu.t2_fit(*args, **kw)
+    finally:
+        if old is None:
+            del os.environ["SIMT_EMU_ORDER"]
+        else:
+            os.environ["SIMT_EMU_ORDER"] = old
+
+
+def _pick(g, n, offset=0):
+    sel = np.arange(offset, len(g["sig"]), len(g["sig"]) // n)[:n]
+    return sel, g["sig"][sel], g["fa_idx"][sel].astype(np.int32)
+
+
+def _check(out, f_ref, reg_ref, ind_m, tol_f=1e-6):
+    assert np.all(out["status"] == 0)
+    assert np.array_equal(out["fsol"] > 0, f_ref > 0)                                  # active sets bit-exact
+    scale = np.abs(f_ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(out["fsol"] - f_ref) / scale) < tol_f
+    assert np.max(np.abs(out["reg"] - reg_ref) / np.abs(reg_ref)) < 1e-6
+    mwf = f_ref[:, ind_m].sum(1) / f_ref.sum(1)
+    assert np.max(np.abs(out["maps"][:, 0] - mwf)) < 1e-4
+
+
+def _same(a, b):
+    return all(np.array_equal(a[k], b[k]) for k in ("fsol", "est_signal", "reg", "maps", "status"))
+
+
+def test_production_x2_kernel_against_reference(setup):
+    """t2_fit_kernel<2,1,X2> (warm starts, full-set start, Brent-best snapshot) vs the unmodified reference."""
+    g, gr = setup["g"], setup["gr"]
+    sel, sig, fa = _pick(g, 16)
+    outs = [_run(o, sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16) for o in ORDERS]
+    _check(outs[0], g["f"][sel], g["reg"][sel], gr["ind_m"])
+    assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
+    cold = _run("forward", sig[:4], fa[:4], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=4)   # MET2_T2_FLAG_COLD_START
+    _check(cold, g["f"][sel[:4]], g["reg"][sel[:4]], gr["ind_m"])
+
+
+def test_echo_space_x2_kernel_against_reference(setup):
+    """The experimental echo-space kernel (met2_t2_echo.cu): same tolerances, both starting strategies."""
+    g, gr = setup["g"], setup["gr"]
+    sel, sig, fa = _pick(g, 16, offset=7)
+    outs = [_run(o, sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=True) for o in ORDERS]
+    _check(outs[0], g["f"][sel], g["reg"][sel], gr["ind_m"], tol_f=1e-8)
+    assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
+    # est_signal = D f * km (motor...:155) and the lambda-returning variant
+    D = np.transpose(setup["Dic"], (2, 0, 1))[fa]
+    assert np.allclose(outs[0]["est_signal"], np.einsum("vec,vc->ve", D, outs[0]["fsol"]), rtol=1e-10, atol=1e-9)
+    nofull = _run("forward", sig[:6], fa[:6], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=0, echo=True)
+    _check(nofull, g["f"][sel[:6]], g["reg"][sel[:6]], gr["ind_m"], tol_f=1e-8)
+    lam = _run("forward", sig[:3], fa[:3], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16 | 1, echo=True)
+    for i in range(3):
+        Dv = np.ascontiguousarray(setup["Dic"][:, :, fa[i]])
+        _, reg, _ = O.nnls_x2(Dv, sig[i] / sig[i, 0], gr["L"], 1.02)
+        assert abs(lam["reg"][i] - reg) < 1e-9 * max(1.0, abs(reg))
+
+
+def test_echo_space_invt2_and_rejects_non_diagonal(setup):
+    g = setup["g"]
+    gi = O._grids("X2", "InvT2", "spline", 40.0, 32, 10.0, 1000.0)
+    sel, sig, fa = _pick(g, 8, offset=3)
+    out = _run("shuffle", sig, fa, setup["Dic"], gi["L"], gi["T2s"], "X2", flags=0, echo=True)
+    ref = [O.t2_fit_voxel(sig[i], np.ascontiguousarray(setup["Dic"][:, :, fa[i]]), "X2", gi["L"], gi["lambda_reg"])
+           for i in range(len(sel))]
+    _check(out, np.array([r[0] for r in ref]), np.array([r[2] for r in ref]), gi["ind_m"])
+    prod = _run("forward", sig, fa, setup["Dic"], gi["L"], gi["T2s"], "X2", flags=0)
+    assert np.array_equal(prod["fsol"] > 0, out["fsol"] > 0)
+    # L2 is tridiagonal: the echo-space formulation does not apply -> every voxel skipped with MET2_ST_ECHO_BAD_L
+    g2 = O._grids("X2", "L2", "spline", 40.0, 32, 10.0, 1000.0)
+    bad = _run("forward", sig[:2], fa[:2], setup["Dic"], g2["L"], g2["T2s"], "X2", flags=0, echo=True)
+    assert np.all(bad["status"] == (1 | 32)) and not bad["fsol"].any() and not bad["est_signal"].any()
+
+
+def test_edge_voxels_both_kernels(setup):
+    """Empty / NaN / M[0] = 0 voxels and a bad FA index: flagged, all-zero outputs, neighbours unaffected
+    (motor...:124-131, algorithms.py:56)."""
+    g, gr = setup["g"], setup["gr"]
+    sel, sig, fa = _pick(g, 6, offset=11)
+    sig = sig.copy()
+    fa = fa.copy()
+    sig[1] = 0.0
+    sig[2, 5] = np.nan
+    sig[3, 0] = 0.0
+    fa[4] = 999
+    for echo in (False, True):
+        out = _run("forward", sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=echo)
+        assert list(out["status"]) == [0, 1, 3, 1, 1, 0]
+        assert not out["fsol"][1:5].any() and not out["est_signal"][1:5].any() and not out["reg"][1:5].any()
+        keep = [0, 5]
+        assert np.array_equal(out["fsol"][keep] > 0, g["f"][sel[keep]] > 0)
+        assert np.max(np.abs(out["fsol"][keep] - g["f"][sel[keep]])) < 1e-6 * np.abs(g["f"][sel[keep]]).max()
+
+
+def test_production_other_methods_against_oracle(setup):
+    """NNLS (with its D-space refinement step), fixed-lambda Tikhonov (L = I and L2) and the L-curve grid + corner."""
+    g, gr = setup["g"], setup["gr"]
+    sel, sig, fa = _pick(g, 5, offset=19)
+    Dv = [np.ascontiguousarray(setup["Dic"][:, :, a]) for a in fa]
+    g2 = O._grids("X2", "L2", "spline", 40.0, 32, 10.0, 1000.0)
+    cases = (("NNLS", gr["L"], {}), ("T2SPARC", gr["L"], {}), ("T2SPARC", g2["L"], {}),
+             ("L_curve", gr["L"], dict(lambdas=gr["lambda_reg"])))
+    for method, L, kw in cases:
+        out = _run("shuffle", sig, fa, setup["Dic"], L, gr["T2s"], method, **kw)
+        for i in range(len(sel)):
+            f_ref, s_ref, reg_ref = O.t2_fit_voxel(sig[i], Dv[i], method, L, gr["lambda_reg"])
+            assert out["status"][i] == 0
+            assert np.array_equal(out["fsol"][i] > 0, f_ref > 0), (method, i)
+            assert np.max(np.abs(out["fsol"][i] - f_ref)) < 1e-6 * np.abs(f_ref).max(), (method, i)
+            assert np.max(np.abs(out["est_signal"][i] - s_ref)) < 1e-6 * np.abs(s_ref).max()
+            assert abs(out["reg"][i] - reg_ref) <= 1e-9 * max(1.0, abs(reg_ref))
