@@ -65,6 +65,7 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
            factor=1.02, lambda_fixed=1.8):
     """Run the (emulated) fit kernel.  Returns dict(fsol, est_signal, reg, maps, status, collectives)."""
     lib = ctypes.CDLL(build())
+    lib.emu_counters((ctypes.c_longlong * 3)())   # reset
     sig = np.ascontiguousarray(sig, dtype=np.float64)
     fa_index = np.ascontiguousarray(fa_index, dtype=np.int32)
     V, m = sig.shape
@@ -101,4 +102,7 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
     if rc < 0:
         raise RuntimeError("emulated kernel refused the configuration (%d)" % rc)
     out["collectives"] = int(rc)
+    cnt = (ctypes.c_longlong * 3)()
+    lib.emu_counters(cnt)
+    out["counters"] = dict(fma=int(cnt[0]), smem=int(cnt[1]), syncwarp=int(cnt[2]))
     return out

@@ -7,12 +7,15 @@
 namespace simt {
 Block* g_block = nullptr;
 emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
+long long n_fma = 0, n_smem = 0, n_syncwarp = 0;
 }  // namespace simt
 
 #include "met2_t2_echo.cu"
 
 namespace met2 {
-alignas(16) double S[40960];   // 320 KB: more than any kernel's dynamic shared memory
+constexpr size_t S_DOUBLES = 40960;   // 320 KB: more than any kernel's dynamic shared memory
+alignas(16) static double s_storage[S_DOUBLES];
+simt::Shared S = {s_storage};
 int set_error(int code, const char*, ...) { return code; }
 int check_launch(const char*) { return 0; }
 void count_launch(int) {}
@@ -65,6 +68,14 @@ static T2Args make_args(Prepared& P, const double* sig, const int* fa_index, lon
 
 extern "C" {
 
+// work counters since the last call: [fma, shared-memory accesses, __syncwarp] per thread (divide by 32 for warp level)
+void emu_counters(long long* out) {
+    out[0] = simt::n_fma;
+    out[1] = simt::n_smem;
+    out[2] = simt::n_syncwarp;
+    simt::n_fma = simt::n_smem = simt::n_syncwarp = 0;
+}
+
 // The experimental echo-space X2 kernel (csrc/met2_t2_echo.cu).  Returns the number of warp collectives executed.
 long long emu_t2_echo_x2(const double* sig, const int* fa_index, long long V, const met2_t2_cfg* cfg, const double* dic,
                          const double* dicT, const double* G, const double* kband, const double* logT2,
@@ -73,7 +84,7 @@ long long emu_t2_echo_x2(const double* sig, const int* fa_index, long long V, co
     if (!t2_echo_eligible(cfg)) return -1;
     Prepared P;
     T2Args A = make_args(P, sig, fa_index, V, cfg, dic, dicT, G, kband, nullptr, logT2, comp, fsol, est, reg, maps, status);
-    if ((size_t)(echo_table_doubles(cfg->nT2) + warps * echo_warp_doubles()) > sizeof(S) / sizeof(double)) return -2;
+    if ((size_t)(echo_table_doubles(cfg->nT2) + warps * echo_warp_doubles()) > S_DOUBLES) return -2;
     return simt::run_block(warps * 32, 0, 1, [&]() { t2_echo_x2_kernel(A); });
 }
 
@@ -91,7 +102,7 @@ long long emu_t2_fit(const double* sig, const int* fa_index, long long V, const 
     if (cfg->method == MET2_REG_GCV)
         while (tri(A.pmax) < gcv_region_doubles(cfg->nT2)) ++A.pmax;
     A.warps = warps;
-    if ((size_t)(t2_table_doubles(cfg->nT2) + warps * t2_warp_doubles<2>(A.pmax)) > sizeof(S) / sizeof(double)) return -2;
+    if ((size_t)(t2_table_doubles(cfg->nT2) + warps * t2_warp_doubles<2>(A.pmax)) > S_DOUBLES) return -2;
     switch (cfg->method) {
         case MET2_REG_NNLS: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_NNLS>(A); });
         case MET2_REG_T2SPARC: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_T2SPARC>(A); });

@@ -63,6 +63,23 @@ struct Block {
 extern Block* g_block;
 extern emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 
+// Work counters (per THREAD events; divide by 32 for warp-level instruction estimates): explicit fma() calls, accesses to
+// the shared-memory array S, warp barriers.  A cost model for comparing kernel variants without a GPU.
+extern long long n_fma, n_smem, n_syncwarp;
+
+// The dynamic shared memory: S[i] and S + off like the device array, with access counting.
+struct Shared {
+    double* data;
+    double& operator[](long i) {
+        ++n_smem;
+        return data[i];
+    }
+    double* operator+(long off) {
+        ++n_smem;
+        return data + off;
+    }
+};
+
 inline int lane_id() { return g_block->cur & 31; }
 inline int warp_id() { return g_block->cur >> 5; }
 
@@ -212,7 +229,10 @@ inline long long run_block(int nthreads, int block_index, int grid, std::functio
 #define gridDim (simt::g_gridDim)
 
 // ------------------------------------------------------------------------------------------------ intrinsics
-inline void __syncwarp(unsigned = 0xffffffffu) { simt::warp_barrier(); }
+inline void __syncwarp(unsigned = 0xffffffffu) {
+    ++simt::n_syncwarp;
+    simt::warp_barrier();
+}
 inline void __syncthreads() { simt::cta_barrier(); }
 
 template <class T>
@@ -268,8 +288,13 @@ inline int atomicOr(int* p, int v) {
     *p = o | v;
     return o;
 }
-using std::fma;
 using std::isfinite;
+namespace met2 {   // unqualified fma() inside namespace met2 resolves here: counted, then the correctly rounded std::fma
+inline double fma(double a, double b, double c) {
+    ++simt::n_fma;
+    return std::fma(a, b, c);
+}
+}  // namespace met2
 
 // FP64 MMA m8n8k4: D(8x8) += A(8x4) B(4x8); fragments A[lane/4][lane%4], B[lane%4][lane/4], C/D[lane/4][2*(lane%4)+{0,1}]
 inline void emu_dmma884(double& d0, double& d1, double a, double b) {
