@@ -418,6 +418,10 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
         __syncwarp();
     }
     // ---- H = C^T C (r x r) and g = C^T 1
+    // every lane has read the residual diagonal (S[W.rs + piv] above) before g overwrites S[W.rs ..]: without this
+    // barrier the loop exit was a write-after-read race between lanes (found by the SIMT emulator's sequential lane
+    // schedule, tests/emu; harmless while the warp runs in lockstep, which is what the GPU did)
+    __syncwarp();
     const int LD = r | 1;
     for (int a = 0; a < r; ++a) {
         const int b = a + lane;

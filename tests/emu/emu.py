@@ -14,7 +14,7 @@ CSRC = os.path.join(ROOT, "multicomponent_t2_toolbox_b200", "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libmet2_emu.so")
 
-METHODS = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3}
+METHODS = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3, "GCV": 4, "BayesReg": 5}
 
 
 class T2Cfg(ctypes.Structure):   # met2_t2_cfg of include/met2.h
@@ -78,6 +78,12 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
     cfg = T2Cfg(method=METHODS[method], nTE=m, nT2=n, nA=nA, nLambda=len(lam), maxfun=300, factor=factor,
                 lambda_fixed=lambda_fixed, brent_lo=0.0, brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0,
                 flags=int(flags) | (64 if echo else 0), reserved=0)
+    if method == "GCV":                      # algorithms.py:280
+        cfg.brent_lo = 1e-8
+    if method == "BayesReg":                 # bayesian_interpolation.py:100-101
+        cfg.brent_lo, cfg.brent_hi, cfg.maxfun = 1e-8, 2.0, 200
+        with np.errstate(divide="ignore"):
+            cfg.log_det_L = float(np.log(np.linalg.det(np.asarray(L, dtype=np.float64))))
     out = dict(fsol=np.zeros((V, n)), est_signal=np.zeros((V, m)), reg=np.zeros(V), maps=np.zeros((V, 6)),
                status=np.zeros(V, dtype=np.uint32))
     P = ctypes.c_void_p

@@ -15,7 +15,7 @@ long long n_fma = 0, n_smem = 0, n_syncwarp = 0;
 namespace met2 {
 constexpr size_t S_DOUBLES = 40960;   // 320 KB: more than any kernel's dynamic shared memory
 alignas(16) static double s_storage[S_DOUBLES];
-simt::Shared S = {s_storage};
+simt::Shared S = {s_storage, (long)S_DOUBLES};
 int set_error(int code, const char*, ...) { return code; }
 int check_launch(const char*) { return 0; }
 void count_launch(int) {}
@@ -84,7 +84,9 @@ long long emu_t2_echo_x2(const double* sig, const int* fa_index, long long V, co
     if (!t2_echo_eligible(cfg)) return -1;
     Prepared P;
     T2Args A = make_args(P, sig, fa_index, V, cfg, dic, dicT, G, kband, nullptr, logT2, comp, fsol, est, reg, maps, status);
-    if ((size_t)(echo_table_doubles(cfg->nT2) + warps * echo_warp_doubles()) > S_DOUBLES) return -2;
+    const size_t need = (size_t)(echo_table_doubles(cfg->nT2) + warps * echo_warp_doubles());
+    if (need > S_DOUBLES) return -2;
+    S.size = (long)need;
     return simt::run_block(warps * 32, 0, 1, [&]() { t2_echo_x2_kernel(A); });
 }
 
@@ -102,12 +104,16 @@ long long emu_t2_fit(const double* sig, const int* fa_index, long long V, const 
     if (cfg->method == MET2_REG_GCV)
         while (tri(A.pmax) < gcv_region_doubles(cfg->nT2)) ++A.pmax;
     A.warps = warps;
-    if ((size_t)(t2_table_doubles(cfg->nT2) + warps * t2_warp_doubles<2>(A.pmax)) > S_DOUBLES) return -2;
+    const size_t need = (size_t)(t2_table_doubles(cfg->nT2) + warps * t2_warp_doubles<2>(A.pmax));
+    if (need > S_DOUBLES) return -2;
+    S.size = (long)need;
     switch (cfg->method) {
         case MET2_REG_NNLS: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_NNLS>(A); });
         case MET2_REG_T2SPARC: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_T2SPARC>(A); });
         case MET2_REG_X2: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_X2>(A); });
         case MET2_REG_LCURVE: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_LCURVE>(A); });
+        case MET2_REG_GCV: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_GCV>(A); });
+        case MET2_REG_BAYESREG: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_BAYESREG>(A); });
         default: return -3;
     }
 }

@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <execinfo.h>
 #include <ucontext.h>
 
 #include <cmath>
@@ -70,12 +71,24 @@ extern long long n_fma, n_smem, n_syncwarp;
 // The dynamic shared memory: S[i] and S + off like the device array, with access counting.
 struct Shared {
     double* data;
+    long size;    // doubles the kernel under test may touch (its dynamic shared-memory size): checked on every access
+    void check(long i) const {
+        if (i < 0 || i >= size) {
+            fprintf(stderr, "simt_emu: shared-memory access out of bounds: S[%ld], size %ld doubles (thread %u)\n", i, size,
+                    g_threadIdx.x);
+            void* bt[16];
+            backtrace_symbols_fd(bt, backtrace(bt, 16), 2);   // resolve with addr2line -e tests/emu/_build/libmet2_emu.so
+            abort();
+        }
+    }
     double& operator[](long i) {
         ++n_smem;
+        check(i);
         return data[i];
     }
     double* operator+(long off) {
         ++n_smem;
+        check(off);
         return data + off;
     }
 };
