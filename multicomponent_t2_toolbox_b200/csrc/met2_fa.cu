@@ -336,6 +336,7 @@ static FaGeom fa_geometry_any(const met2_fa_cfg* cfg) {
     return fa_geometry<4>(cfg);
 }
 
+#ifndef MET2_HOST_EMU   // launches and the C entry points: not part of the CPU emulation build (tests/emu)
 template <int NS, int ME>
 static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
     cudaError_t e;
@@ -366,9 +367,11 @@ static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
     }
     return rc;
 }
+#endif  // MET2_HOST_EMU
 
 }  // namespace met2
 
+#ifndef MET2_HOST_EMU
 using namespace met2;
 
 static int fa_check_cfg(const met2_fa_cfg* cfg) {
@@ -447,3 +450,4 @@ extern "C" int met2_fa_fit(const double* sig, int64_t V, const met2_fa_cfg* cfg,
     if (ns == 4 && me == 2) return fa_launch<4, 2>(A, g, st);
     return set_error(MET2_ERR_UNSUPPORTED, "met2_fa_fit: unsupported template sizes");
 }
+#endif  // MET2_HOST_EMU

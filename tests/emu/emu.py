@@ -112,3 +112,46 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
     lib.emu_counters(cnt)
     out["counters"] = dict(fma=int(cnt[0]), smem=int(cnt[1]), syncwarp=int(cnt[2]))
     return out
+
+
+class FaCfg(ctypes.Structure):   # met2_fa_cfg of include/met2.h
+    _fields_ = [("method", ctypes.c_int32), ("nTE", ctypes.c_int32), ("nT2", ctypes.c_int32), ("nA", ctypes.c_int32),
+                ("nKnots", ctypes.c_int32), ("final_solve", ctypes.c_int32),
+                ("brent_lo", ctypes.c_double), ("brent_hi", ctypes.c_double), ("brent_xatol", ctypes.c_double),
+                ("brent_maxfun", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None, warps=2):
+    """Run the (emulated) flip-angle stage: brute force over `alpha_values`, or the spline method when the coarse
+    dictionary is given.  Returns dict(fa_index, fa_deg, km, fsol_sum, status)."""
+    lib = ctypes.CDLL(build())
+    lib.emu_counters((ctypes.c_longlong * 3)())
+    sig = np.ascontiguousarray(sig, dtype=np.float64)
+    V, m = sig.shape
+    eye = np.eye(Dic_3D.shape[1])
+    dic, dicT, G, _ = tables(np.asarray(Dic_3D, dtype=np.float64), eye)
+    nA, _, n = dic.shape
+    alphas = np.ascontiguousarray(alpha_values, dtype=np.float64)
+    spline = Dic_3D_LR is not None
+    P = ctypes.c_void_p
+
+    def ptr(a):
+        return a.ctypes.data_as(P) if a is not None else None
+
+    dic_s = dicT_s = G_s = knots = None
+    if spline:
+        dic_s, dicT_s, G_s, _ = tables(np.asarray(Dic_3D_LR, dtype=np.float64), eye)
+        knots = np.ascontiguousarray(alpha_values_spline, dtype=np.float64)
+    cfg = FaCfg(method=1 if spline else 0, nTE=m, nT2=n, nA=nA, nKnots=(len(knots) if spline else 0), final_solve=1,
+                brent_lo=90.0, brent_hi=180.0, brent_xatol=1e-5, brent_maxfun=500, reserved=0)
+    out = dict(fa_index=np.zeros(V, dtype=np.int32), fa_deg=np.zeros(V), km=np.zeros(V), fsol_sum=np.zeros(n),
+               status=np.zeros(V, dtype=np.uint32))
+    fn = lib.emu_fa_fit
+    fn.restype = ctypes.c_longlong
+    fn.argtypes = [P, ctypes.c_longlong, ctypes.POINTER(FaCfg)] + [P] * 13 + [ctypes.c_int]
+    rc = fn(ptr(sig), V, ctypes.byref(cfg), ptr(dic), ptr(dicT), ptr(G), ptr(alphas), ptr(dic_s), ptr(dicT_s), ptr(G_s),
+            ptr(knots), ptr(out["fa_index"]), ptr(out["fa_deg"]), ptr(out["km"]), ptr(out["fsol_sum"]),
+            ptr(out["status"]), warps)
+    if rc < 0:
+        raise RuntimeError("emulated FA stage refused the configuration (%d)" % rc)
+    return out

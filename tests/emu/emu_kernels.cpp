@@ -11,6 +11,7 @@ long long n_fma = 0, n_smem = 0, n_syncwarp = 0;
 }  // namespace simt
 
 #include "met2_t2_echo.cu"
+#include "met2_fa.cu"
 
 namespace met2 {
 constexpr size_t S_DOUBLES = 40960;   // 320 KB: more than any kernel's dynamic shared memory
@@ -116,6 +117,49 @@ long long emu_t2_fit(const double* sig, const int* fa_index, long long V, const 
         case MET2_REG_BAYESREG: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_BAYESREG>(A); });
         default: return -3;
     }
+}
+
+// The flip-angle stage (csrc/met2_fa.cu): fa_search_kernel -> [spline_weights_kernel] -> fa_select_kernel ->
+// reduce_partials_kernel, nT2 <= 64 and nTE <= 32, one emulated block each (the search kernel walks all voxels with
+// `warps` warps; the select kernel has its fixed FA_WARPS warps).  dic_s/dicT_s/G_s/knots: the coarse (spline) tables
+// or NULL for brute force.
+long long emu_fa_fit(const double* sig, long long V, const met2_fa_cfg* cfg, const double* dic, const double* dicT,
+                     const double* G, const double* alphas, const double* dic_s, const double* dicT_s, const double* G_s,
+                     const double* knots, int* fa_index, double* fa_deg, double* km, double* fsol_sum, unsigned* status,
+                     int warps) {
+    if (cfg->nT2 > 64 || cfg->nTE > 32) return -1;
+    const bool spline = cfg->method == MET2_FA_SPLINE;
+    FaArgs A;
+    memset(&A, 0, sizeof(A));
+    A.sig = sig; A.V = V; A.cfg = *cfg;
+    A.dic = dic; A.dicT = dicT; A.G = G; A.alphas = alphas;
+    if (spline) {
+        A.dic_s = dic_s; A.dicT_s = dicT_s; A.G_s = G_s; A.knots = knots; A.nS = cfg->nKnots;
+    } else {
+        A.dic_s = dic; A.dicT_s = dicT; A.G_s = G; A.knots = nullptr; A.nS = cfg->nA;
+    }
+    A.fa_index = fa_index; A.fa_deg = fa_deg; A.km = km; A.fsol_sum = fsol_sum; A.status = status;
+    const int nSr = spline ? cfg->nKnots : 1;
+    std::vector<double> resid((size_t)V * nSr), wsp(MET2_MAX_KNOTS * MET2_MAX_KNOTS), partial((size_t)FA_WARPS * cfg->nT2);
+    std::vector<int> ws_p(V), ws_ix((size_t)V * FA_CARRY);
+    std::vector<double> ws_x((size_t)V * FA_CARRY);
+    A.resid = resid.data(); A.wsp = wsp.data(); A.partial = fsol_sum ? partial.data() : nullptr;
+    A.ws_p = ws_p.data(); A.ws_ix = ws_ix.data(); A.ws_x = ws_x.data();
+    A.pmax = std::min(cfg->nT2, cfg->nTE);
+    for (long long v = 0; v < V; ++v) status[v] = 0;
+    long long c = 0;
+    S.size = fa_table_doubles(cfg->nT2, cfg->nTE) + warps * fa_warp_doubles<2>(A.pmax);
+    if ((size_t)S.size > S_DOUBLES) return -2;
+    c += simt::run_block(warps * 32, 0, 1, [&]() { fa_search_kernel<2, 1>(A); });
+    if (spline) c += simt::run_block(32, 0, 1, [&]() { spline_weights_kernel(A.knots, A.cfg.nKnots, A.wsp); });
+    S.size = FA_WARPS * fa_warp_doubles<2>(A.pmax);
+    c += simt::run_block(FA_WARPS * 32, 0, 1, [&]() { fa_select_kernel<2, 1>(A); });
+    if (fsol_sum) {
+        const int nb = (cfg->nT2 + 127) / 128;
+        for (int b = 0; b < nb; ++b)
+            c += simt::run_block(128, b, nb, [&]() { reduce_partials_kernel(A.partial, (long long)FA_WARPS, A.cfg.nT2, A.fsol_sum); });
+    }
+    return c;
 }
 
 }  // extern "C"

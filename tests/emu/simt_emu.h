@@ -296,6 +296,11 @@ inline int atomicAdd(int* p, int v) {
     *p = o + v;
     return o;
 }
+inline unsigned atomicOr(unsigned* p, unsigned v) {
+    unsigned o = *p;
+    *p = o | v;
+    return o;
+}
 inline int atomicOr(int* p, int v) {
     int o = *p;
     *p = o | v;

@@ -166,3 +166,39 @@ def test_production_bayesreg_and_gcv_against_oracle(setup):
         f_ref, _, _ = O.t2_fit_voxel(sig[i], Dv[i], "GCV", gr["L"], gr["lambda_reg"])
         assert out["status"][i] == 0
         assert abs(out["maps"][i, 0] - f_ref[gr["ind_m"]].sum() / f_ref.sum()) < 1e-4
+
+
+def test_fa_stage_kernels_against_reference(setup):
+    """csrc/met2_fa.cu under the emulator: fa_search_kernel (warm-started plain NNLS per search angle) ->
+    spline_weights_kernel -> fa_select_kernel (not-a-knot spline + the bounded-Brent replica + grid snap, NNLS at the
+    chosen angle) -> reduce_partials_kernel.  Spline method against the FA indices / km the unmodified reference
+    produced (fa_estimation.py:35-72); brute force against the oracle (fa_estimation.py:74-112).  Bit-exact indices."""
+    g, gr = setup["g"], setup["gr"]
+    sel = np.arange(3, len(g["sig"]), len(g["sig"]) // 20)[:20]
+    sig = g["sig"][sel]
+    DicLR = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, gr["alpha_spline"], 1000.0)
+    outs = []
+    for order in ORDERS:
+        os.environ["SIMT_EMU_ORDER"] = order
+        try:
+            outs.append(emu.fa_fit(sig, setup["Dic"], gr["alpha_values"], DicLR, gr["alpha_spline"]))
+        finally:
+            del os.environ["SIMT_EMU_ORDER"]
+    out = outs[0]
+    assert np.all(out["status"] == 0)
+    assert np.array_equal(out["fa_index"], g["fa_idx"][sel])
+    assert np.array_equal(out["fa_deg"], gr["alpha_values"][g["fa_idx"][sel]])
+    assert np.max(np.abs(out["km"] - g["km"][sel]) / g["km"][sel]) < 1e-9
+    for other in outs[1:]:
+        assert all(np.array_equal(out[k], other[k]) for k in ("fa_index", "fa_deg", "km", "status"))
+        assert np.allclose(out["fsol_sum"], other["fsol_sum"], rtol=1e-13, atol=0)   # summation order follows the warps
+    a91 = np.linspace(90.0, 180.0, 91)
+    D91 = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, a91, 1000.0)
+    sig_b = sig[:8].copy()
+    sig_b[3] = 0.0                                                  # empty voxel: index 0, status skipped
+    out = emu.fa_fit(sig_b, D91, a91)
+    FA, idx, KM, F = O.fitting_slice_FA_brute_force((sig_b.sum(1) > 0).astype(float), sig_b, 8, D91, a91)
+    assert list(out["status"]) == [0, 0, 0, 1, 0, 0, 0, 0]
+    assert np.array_equal(out["fa_index"], idx.astype(np.int32)) and np.array_equal(out["fa_deg"], FA)
+    assert np.max(np.abs(out["km"] - KM)) < 1e-8 * KM.max()
+    assert np.max(np.abs(out["fsol_sum"] - F)) < 1e-6 * np.abs(F).max()
