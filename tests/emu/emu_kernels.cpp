@@ -67,6 +67,18 @@ static T2Args make_args(Prepared& P, const double* sig, const int* fa_index, lon
     return A;
 }
 
+// The production kernel t2_fit_kernel<NS, ME, METHOD> without the shared full-set factor tables (A.tfull = NULL: those
+// only shortcut factorisations) — same code path as the GPU otherwise.  Instantiated for the reference's sizes
+// (nT2 <= 64, nTE <= 32: every method), T2SPARC's 96 bins (NS = 3) and BASELINE.json's config 4 (100 bins, 48 echoes:
+// NS = 4, ME = 2; NNLS, X2, BayesReg).
+template <int NS, int ME, int METHOD>
+static long long run_t2(T2Args& A, int warps) {
+    const size_t need = (size_t)(t2_table_doubles(A.cfg.nT2) + warps * t2_warp_doubles<NS>(A.pmax));
+    if (need > S_DOUBLES) return -2;
+    S.size = (long)need;
+    return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<NS, ME, METHOD>(A); });
+}
+
 extern "C" {
 
 // work counters since the last call: [fma, shared-memory accesses, __syncwarp] per thread (divide by 32 for warp level)
@@ -91,13 +103,10 @@ long long emu_t2_echo_x2(const double* sig, const int* fa_index, long long V, co
     return simt::run_block(warps * 32, 0, 1, [&]() { t2_echo_x2_kernel(A); });
 }
 
-// The production kernel t2_fit_kernel<2, 1, METHOD> (nT2 <= 64, nTE <= 32) without the shared full-set factor tables
-// (A.tfull = NULL: those only shortcut factorisations) — same code path as the GPU otherwise.
 long long emu_t2_fit(const double* sig, const int* fa_index, long long V, const met2_t2_cfg* cfg, const double* dic,
                      const double* dicT, const double* G, const double* kband, const double* lambdas, const double* logT2,
                      const unsigned char* comp, double* fsol, double* est, double* reg, double* maps, unsigned* status,
                      int warps) {
-    if (cfg->nT2 > 64 || cfg->nTE > 32) return -1;
     Prepared P;
     T2Args A = make_args(P, sig, fa_index, V, cfg, dic, dicT, G, kband, lambdas, logT2, comp, fsol, est, reg, maps, status);
     const bool plain = (cfg->method == MET2_REG_NNLS);
@@ -105,18 +114,28 @@ long long emu_t2_fit(const double* sig, const int* fa_index, long long V, const 
     if (cfg->method == MET2_REG_GCV)
         while (tri(A.pmax) < gcv_region_doubles(cfg->nT2)) ++A.pmax;
     A.warps = warps;
-    const size_t need = (size_t)(t2_table_doubles(cfg->nT2) + warps * t2_warp_doubles<2>(A.pmax));
-    if (need > S_DOUBLES) return -2;
-    S.size = (long)need;
-    switch (cfg->method) {
-        case MET2_REG_NNLS: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_NNLS>(A); });
-        case MET2_REG_T2SPARC: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_T2SPARC>(A); });
-        case MET2_REG_X2: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_X2>(A); });
-        case MET2_REG_LCURVE: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_LCURVE>(A); });
-        case MET2_REG_GCV: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_GCV>(A); });
-        case MET2_REG_BAYESREG: return simt::run_block(warps * 32, 0, 1, [&]() { t2_fit_kernel<2, 1, MET2_REG_BAYESREG>(A); });
-        default: return -3;
+    const int ns = (cfg->nT2 + 31) / 32, me = (cfg->nTE + 31) / 32;
+    if (ns <= 2 && me == 1) {
+        switch (cfg->method) {
+            case MET2_REG_NNLS: return run_t2<2, 1, MET2_REG_NNLS>(A, warps);
+            case MET2_REG_T2SPARC: return run_t2<2, 1, MET2_REG_T2SPARC>(A, warps);
+            case MET2_REG_X2: return run_t2<2, 1, MET2_REG_X2>(A, warps);
+            case MET2_REG_LCURVE: return run_t2<2, 1, MET2_REG_LCURVE>(A, warps);
+            case MET2_REG_GCV: return run_t2<2, 1, MET2_REG_GCV>(A, warps);
+            case MET2_REG_BAYESREG: return run_t2<2, 1, MET2_REG_BAYESREG>(A, warps);
+            default: return -3;
+        }
     }
+    if (ns == 3 && me == 1 && cfg->method == MET2_REG_T2SPARC) return run_t2<3, 1, MET2_REG_T2SPARC>(A, warps);
+    if (ns == 4 && me == 2) {
+        switch (cfg->method) {
+            case MET2_REG_NNLS: return run_t2<4, 2, MET2_REG_NNLS>(A, warps);
+            case MET2_REG_X2: return run_t2<4, 2, MET2_REG_X2>(A, warps);
+            case MET2_REG_BAYESREG: return run_t2<4, 2, MET2_REG_BAYESREG>(A, warps);
+            default: return -3;
+        }
+    }
+    return -1;
 }
 
 // The flip-angle stage (csrc/met2_fa.cu): fa_search_kernel -> [spline_weights_kernel] -> fa_select_kernel ->

@@ -202,3 +202,40 @@ def test_fa_stage_kernels_against_reference(setup):
     assert np.array_equal(out["fa_index"], idx.astype(np.int32)) and np.array_equal(out["fa_deg"], FA)
     assert np.max(np.abs(out["km"] - KM)) < 1e-8 * KM.max()
     assert np.max(np.abs(out["fsol_sum"] - F)) < 1e-6 * np.abs(F).max()
+
+
+def _synthetic(npc, nte, nv, method, matrix, seed=3):
+    """Three-compartment spectra (myelin 20 ms, IE 60-90 ms, free water 1.5 s) through the oracle's EPG dictionary."""
+    gr = O._grids(method, matrix, "brute-force", 40.0, nte, 10.0, 1000.0, npc=npc, n_alphas=7)
+    Dic = O.create_Dic_3D(npc, gr["T2s"], gr["T1s"], nte, 10.0, gr["alpha_values"], 1000.0)
+    rng = np.random.default_rng(seed)
+    fa = rng.integers(0, 7, nv).astype(np.int32)
+    lt = np.log(gr["T2s"])
+    sig = np.zeros((nv, nte))
+    for i in range(nv):
+        spec = (0.15 * np.exp(-0.5 * ((lt - np.log(20.0)) / 0.15) ** 2)
+                + 0.8 * np.exp(-0.5 * ((lt - np.log(rng.uniform(60.0, 90.0))) / 0.12) ** 2)
+                + 0.05 * np.exp(-0.5 * ((lt - np.log(1500.0)) / 0.1) ** 2))
+        s = Dic[:, :, fa[i]] @ spec
+        sig[i] = 1000.0 * np.abs(s + rng.normal(0.0, s[0] / 150.0, nte))
+    return gr, Dic, sig, fa
+
+
+@pytest.mark.parametrize("method,matrix,npc,nte,nv,tol", [
+    ("T2SPARC", "InvT2", 96, 32, 3, 1e-6),       # the reference's T2SPARC grid: three column slots per lane
+    ("NNLS", "I", 100, 48, 3, 1e-6),             # BASELINE.json config 4 sizes: four column slots, two echo slots
+    ("X2", "I", 100, 48, 2, 1e-6),
+    ("BayesReg", "InvT2", 100, 48, 2, 1e-3),     # flat evidence: the reference does not reproduce itself (DESIGN.md §5)
+])
+def test_production_kernels_large_sizes(method, matrix, npc, nte, nv, tol):
+    emu.build()
+    gr, Dic, sig, fa = _synthetic(npc, nte, nv, method, matrix)
+    out = _run("shuffle", sig, fa, Dic, gr["L"], gr["T2s"], method, lambdas=gr["lambda_reg"])
+    assert np.all(out["status"] == 0)
+    for i in range(nv):
+        f_ref, s_ref, reg_ref = O.t2_fit_voxel(sig[i], np.ascontiguousarray(Dic[:, :, fa[i]]), method, gr["L"],
+                                               gr["lambda_reg"])
+        assert np.array_equal(out["fsol"][i] > 0, f_ref > 0)
+        assert np.max(np.abs(out["fsol"][i] - f_ref)) < tol * np.abs(f_ref).max()
+        assert abs(out["reg"][i] - reg_ref) <= tol * max(1.0, abs(reg_ref))
+        assert abs(out["maps"][i, 0] - f_ref[gr["ind_m"]].sum() / f_ref.sum()) < 1e-4
