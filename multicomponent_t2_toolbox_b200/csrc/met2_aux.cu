@@ -200,11 +200,11 @@ extern "C" int met2_segment_means(const double* sig, const int32_t* fa_index, co
         const long long warps = (V + SEG_RUN - 1) / SEG_RUN;
         const int tb = 128;
         const unsigned nb = (unsigned)((warps * 32 + tb - 1) / tb);
-        seg_accumulate_kernel<<<nb, tb, 0, st>>>(sig, fa_index, label, V, nTE, nA, nSeg, mean_signal, hist, counts);
+        MET2_LAUNCH(nb, tb, 0, st, seg_accumulate_kernel)(sig, fa_index, label, V, nTE, nA, nSeg, mean_signal, hist, counts);
         count_launch();
     }
     const long long total = (long long)nSeg * nTE * nT2;
-    seg_finish_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dic, hist, counts, nTE, nT2, nA, nSeg, mean_signal,
+    MET2_LAUNCH((unsigned)((total + 255) / 256), 256, 0, st, seg_finish_kernel)(dic, hist, counts, nTE, nT2, nA, nSeg, mean_signal,
                                                                         mean_kernel);
     count_launch();
     return check_launch("met2_segment_means");
@@ -217,12 +217,12 @@ extern "C" int met2_nesma_filter(const double* vol, const int32_t* mask, int nx,
     cudaStream_t st = (cudaStream_t)stream;
     const long long V3 = (long long)nx * ny * nz;
     dim3 tgrid((unsigned)((V3 + 31) / 32), (unsigned)((nt + 31) / 32));
-    to_echo_major_kernel<<<tgrid, dim3(32, 8), 0, st>>>(vol, tmp, V3, nt);
+    MET2_LAUNCH(tgrid, dim3(32, 8), 0, st, to_echo_major_kernel)(vol, tmp, V3, nt);
     const unsigned nb = (unsigned)((V3 + 127) / 128);
     if (nt <= 32)
-        nesma_kernel<32><<<nb, 128, 0, st>>>(tmp, mask, nx, ny, nz, nt, half_window, threshold_percent, out);
+        MET2_LAUNCH(nb, 128, 0, st, nesma_kernel<32>)(tmp, mask, nx, ny, nz, nt, half_window, threshold_percent, out);
     else
-        nesma_kernel<64><<<nb, 128, 0, st>>>(tmp, mask, nx, ny, nz, nt, half_window, threshold_percent, out);
+        MET2_LAUNCH(nb, 128, 0, st, nesma_kernel<64>)(tmp, mask, nx, ny, nz, nt, half_window, threshold_percent, out);
     count_launch(2);
     return check_launch("met2_nesma_filter");
 }

@@ -76,7 +76,11 @@ __global__ void epg_signals_kernel(const double* __restrict__ alphas, const doub
 
 // G[a] = D_a^T D_a, one block per angle; D_a staged in shared memory.
 __global__ void gram_kernel(const double* __restrict__ dic, int nTE, int nT2, double* __restrict__ G) {
+#ifdef MET2_HOST_EMU
+    double* sD = simt::g_shared.data;
+#else
     extern __shared__ double sD[];
+#endif
     const double* D = dic + (size_t)blockIdx.x * nTE * nT2;
     for (int i = threadIdx.x; i < nTE * nT2; i += blockDim.x) sD[i] = D[i];
     __syncthreads();
@@ -121,7 +125,7 @@ extern "C" int met2_epg_dictionary(const double* alphas_deg, int nA, const doubl
         return set_error(MET2_ERR_ARG, "met2_epg_dictionary: bad argument (nA=%d nT2=%d nTE=%d)", nA, nT2, nTE);
     cudaStream_t st = (cudaStream_t)stream;
     int total = nA * nT2;
-    epg_dictionary_kernel<<<(total + 127) / 128, 128, 0, st>>>(alphas_deg, nA, T2s, T1s, nT2, nTE, tau_ms, TR_ms, dic,
+    MET2_LAUNCH((total + 127) / 128, 128, 0, st, epg_dictionary_kernel)(alphas_deg, nA, T2s, T1s, nT2, nTE, tau_ms, TR_ms, dic,
                                                                dicT);
     count_launch();
     return check_launch("epg_dictionary_kernel");
@@ -133,7 +137,7 @@ extern "C" int met2_epg_signals(const double* alphas_deg, const double* T2s, con
         return set_error(MET2_ERR_ARG, "met2_epg_signals: bad argument");
     if (N == 0) return MET2_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    epg_signals_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>(alphas_deg, T2s, T1s, (long long)N, nTE, tau_ms, sig);
+    MET2_LAUNCH((unsigned)((N + 127) / 128), 128, 0, st, epg_signals_kernel)(alphas_deg, T2s, T1s, (long long)N, nTE, tau_ms, sig);
     count_launch();
     return check_launch("epg_signals_kernel");
 }
@@ -147,7 +151,7 @@ extern "C" int met2_gram_tables(const double* dic, int nA, int nTE, int nT2, con
         size_t smem = sizeof(double) * (size_t)nTE * nT2;
         cudaError_t e = cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "gram_kernel attr: %s", cudaGetErrorString(e));
-        gram_kernel<<<nA, 256, smem, st>>>(dic, nTE, nT2, G);
+        MET2_LAUNCH(nA, 256, smem, st, gram_kernel)(dic, nTE, nT2, G);
         count_launch();
         int rc = check_launch("gram_kernel");
         if (rc) return rc;
@@ -156,7 +160,7 @@ extern "C" int met2_gram_tables(const double* dic, int nA, int nTE, int nT2, con
         cudaError_t e = cudaMemsetAsync(kband, 0, sizeof(double) * 10 * nT2, st);
         if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "memset kband: %s", cudaGetErrorString(e));
         if (band_err) cudaMemsetAsync(band_err, 0, sizeof(int32_t), st);
-        band_kernel<<<1, 256, 0, st>>>(L, nT2, kband, band_err);
+        MET2_LAUNCH(1, 256, 0, st, band_kernel)(L, nT2, kband, band_err);
         count_launch();
         return check_launch("band_kernel");
     }

@@ -336,7 +336,6 @@ static FaGeom fa_geometry_any(const met2_fa_cfg* cfg) {
     return fa_geometry<4>(cfg);
 }
 
-#ifndef MET2_HOST_EMU   // launches and the C entry points: not part of the CPU emulation build (tests/emu)
 template <int NS, int ME>
 static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
     cudaError_t e;
@@ -345,33 +344,31 @@ static int fa_launch(const FaArgs& A, const FaGeom& g, cudaStream_t st) {
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_search attr: %s", cudaGetErrorString(e));
     e = cudaFuncSetAttribute(fa_select_kernel<NS, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "fa_select attr: %s", cudaGetErrorString(e));
-    fa_search_kernel<NS, ME><<<g.grid_search, g.warps_search * 32, g.smem_search, st>>>(A);
+    MET2_LAUNCH(g.grid_search, g.warps_search * 32, g.smem_search, st, fa_search_kernel<NS, ME>)(A);
     count_launch();
     int rc = check_launch("fa_search_kernel");
     if (rc) return rc;
     if (A.cfg.method == MET2_FA_SPLINE) {
-        spline_weights_kernel<<<1, 32, 0, st>>>(A.knots, A.cfg.nKnots, A.wsp);
+        MET2_LAUNCH(1, 32, 0, st, spline_weights_kernel)(A.knots, A.cfg.nKnots, A.wsp);
         count_launch();
         rc = check_launch("spline_weights_kernel");
         if (rc) return rc;
     }
-    fa_select_kernel<NS, ME><<<g.grid, FA_WARPS * 32, g.smem, st>>>(A);
+    MET2_LAUNCH(g.grid, FA_WARPS * 32, g.smem, st, fa_select_kernel<NS, ME>)(A);
     count_launch();
     rc = check_launch("fa_select_kernel");
     if (rc) return rc;
     if (A.fsol_sum) {
-        reduce_partials_kernel<<<(A.cfg.nT2 + 127) / 128, 128, 0, st>>>(A.partial, (long long)g.grid * FA_WARPS,
+        MET2_LAUNCH((A.cfg.nT2 + 127) / 128, 128, 0, st, reduce_partials_kernel)(A.partial, (long long)g.grid * FA_WARPS,
                                                                         A.cfg.nT2, A.fsol_sum);
         count_launch();
         rc = check_launch("reduce_partials_kernel");
     }
     return rc;
 }
-#endif  // MET2_HOST_EMU
 
 }  // namespace met2
 
-#ifndef MET2_HOST_EMU
 using namespace met2;
 
 static int fa_check_cfg(const met2_fa_cfg* cfg) {
@@ -450,4 +447,3 @@ extern "C" int met2_fa_fit(const double* sig, int64_t V, const met2_fa_cfg* cfg,
     if (ns == 4 && me == 2) return fa_launch<4, 2>(A, g, st);
     return set_error(MET2_ERR_UNSUPPORTED, "met2_fa_fit: unsupported template sizes");
 }
-#endif  // MET2_HOST_EMU

@@ -9,6 +9,15 @@
 
 #include "../../include/met2.h"
 
+// Kernel launch: `MET2_LAUNCH(grid, block, dynamic_smem_bytes, stream, kernel<...>)(args...)` is the CUDA launch
+// `kernel<...><<<grid, block, smem, stream>>>(args...)`; under MET2_HOST_EMU (tests/emu, CPU) the same host code drives
+// the SIMT emulator instead.  The kernel name comes last so that template argument lists may contain commas.
+#ifdef MET2_HOST_EMU
+#define MET2_LAUNCH(grid, block, smem, stream, ...) simt::make_launch(dim3(grid), dim3(block), (size_t)(smem), __VA_ARGS__)
+#else
+#define MET2_LAUNCH(grid, block, smem, stream, ...) __VA_ARGS__<<<(grid), (block), (smem), (stream)>>>
+#endif
+
 namespace met2 {
 
 int set_error(int code, const char* fmt, ...);

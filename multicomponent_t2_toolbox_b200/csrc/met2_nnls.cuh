@@ -28,7 +28,7 @@
 namespace met2 {
 
 #ifdef MET2_HOST_EMU
-extern simt::Shared S;
+static simt::Shared& S = simt::g_shared;
 #else
 extern __shared__ __align__(16) double S[];   // the dynamic shared memory of every met2 kernel
 #endif

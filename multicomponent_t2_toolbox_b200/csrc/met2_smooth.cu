@@ -57,9 +57,9 @@ extern "C" int met2_gaussian_smooth(const double* vol, int nx, int ny, int nz, i
     const long long total = (long long)nx * ny * nz * nt;
     const int tb = 256;
     const unsigned nb = (unsigned)((total + tb - 1) / tb);
-    gauss1d_kernel<<<nb, tb, 0, st>>>(vol, out, nx, ny, nz, nt, 0, weights, radius);
-    gauss1d_kernel<<<nb, tb, 0, st>>>(out, tmp, nx, ny, nz, nt, 1, weights, radius);
-    gauss1d_kernel<<<nb, tb, 0, st>>>(tmp, out, nx, ny, nz, nt, 2, weights, radius);
+    MET2_LAUNCH(nb, tb, 0, st, gauss1d_kernel)(vol, out, nx, ny, nz, nt, 0, weights, radius);
+    MET2_LAUNCH(nb, tb, 0, st, gauss1d_kernel)(out, tmp, nx, ny, nz, nt, 1, weights, radius);
+    MET2_LAUNCH(nb, tb, 0, st, gauss1d_kernel)(tmp, out, nx, ny, nz, nt, 2, weights, radius);
     count_launch(3);
     return check_launch("gauss1d_kernel");
 }

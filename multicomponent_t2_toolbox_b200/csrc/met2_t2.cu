@@ -90,7 +90,7 @@ static int t2_launch_full_factors(const T2Args& A, int ntab, const double* G, co
     const size_t smem = sizeof(double) * (size_t)Slots<NS>::doubles(n);
     cudaError_t e = cudaFuncSetAttribute(t2_full_factors_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_full_factors attr: %s", cudaGetErrorString(e));
-    t2_full_factors_kernel<NS><<<ntab * A.cfg.nA, 32, smem, st>>>(G, kband, n, A.cfg.nA, A.cfg.brent_lo, A.cfg.brent_hi,
+    MET2_LAUNCH(ntab * A.cfg.nA, 32, smem, st, t2_full_factors_kernel<NS>)(G, kband, n, A.cfg.nA, A.cfg.brent_lo, A.cfg.brent_hi,
                                                                      A.cfg.brent_xatol, A.cfg.maxfun, tfull, lam_tab);
     count_launch();
     return check_launch("t2_full_factors_kernel");
@@ -169,14 +169,14 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "memset hist: %s", cudaGetErrorString(e));
     const int tb = 256;
     const unsigned nb = (unsigned)((V + tb - 1) / tb);
-    t2_hist_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.hist);
+    MET2_LAUNCH(nb, tb, 0, st, t2_hist_kernel)(fa_index, V, cfg->nA, A.hist);
     count_launch();
     if ((rc = check_launch("t2_hist_kernel"))) return rc;
-    t2_tiles_kernel<<<1, 32, 0, st>>>(A.hist, cfg->nA, g.tile_big, g.tile_small, g.switch_off, A.bin_start, A.cursor,
+    MET2_LAUNCH(1, 32, 0, st, t2_tiles_kernel)(A.hist, cfg->nA, g.tile_big, g.tile_small, g.switch_off, A.bin_start, A.cursor,
                                       A.tile_fa, A.tile_start, A.tile_cnt, A.counters);
     count_launch();
     if ((rc = check_launch("t2_tiles_kernel"))) return rc;
-    t2_scatter_kernel<<<nb, tb, 0, st>>>(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);
+    MET2_LAUNCH(nb, tb, 0, st, t2_scatter_kernel)(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);
     count_launch();
     if ((rc = check_launch("t2_scatter_kernel"))) return rc;
     if (t2_echo_eligible(cfg)) return t2_launch_echo_x2(A, st);

@@ -506,7 +506,6 @@ bool t2_echo_eligible(const met2_t2_cfg* cfg) {
            cfg->nT2 <= EC_NCOL && !(cfg->flags & MET2_T2_FLAG_COLD_START);
 }
 
-#ifndef MET2_HOST_EMU
 int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
     const int n = A.cfg.nT2;
     const size_t tables = sizeof(double) * (size_t)echo_table_doubles(n);
@@ -524,10 +523,9 @@ int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
     if (sms <= 0) sms = 148;
     cudaError_t e = cudaFuncSetAttribute(t2_echo_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_echo attr (%zu B): %s", smem, cudaGetErrorString(e));
-    t2_echo_x2_kernel<<<sms, warps * 32, smem, st>>>(A);
+    MET2_LAUNCH(sms, warps * 32, smem, st, t2_echo_x2_kernel)(A);
     count_launch();
     return check_launch("t2_echo_x2_kernel");
 }
-#endif  // MET2_HOST_EMU
 
 }  // namespace met2

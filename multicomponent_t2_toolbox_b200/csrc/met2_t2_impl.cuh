@@ -937,13 +937,12 @@ static inline T2Geom t2_geometry_any(long long V, const met2_t2_cfg* cfg) {
     return t2_geometry<4>(V, cfg);
 }
 
-#ifndef MET2_HOST_EMU
 template <int NS, int ME, int METHOD>
 static int t2_launch_one(const T2Args& A, const T2Geom& g, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(t2_fit_kernel<NS, ME, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)g.smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_fit attr (%zu B): %s", g.smem, cudaGetErrorString(e));
-    t2_fit_kernel<NS, ME, METHOD><<<g.grid, g.warps * 32, g.smem, st>>>(A);
+    MET2_LAUNCH(g.grid, g.warps * 32, g.smem, st, t2_fit_kernel<NS, ME, METHOD>)(A);
     count_launch();
     return check_launch("t2_fit_kernel");
 }
@@ -959,7 +958,6 @@ static int t2_launch_method(const T2Args& A, const T2Geom& g, cudaStream_t st) {
     if (ns == 4 && me == 2) return t2_launch_one<4, 2, METHOD>(A, g, st);
     return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: unsupported template sizes");
 }
-#endif  // MET2_HOST_EMU
 
 // one definition per method, in met2_t2_m<method>.cu
 int t2_launch_nnls(const T2Args& A, const T2Geom& g, cudaStream_t st);

@@ -1,10 +1,14 @@
-"""TEST INFRASTRUCTURE ONLY — builds tests/emu/emu_kernels.cpp (the T2 fit kernels of csrc/ compiled by g++ against the
-single-threaded SIMT emulator simt_emu.h) and calls it with numpy arrays.  Lets the `-m "not gpu"` tests run the
-kernels' real source — control flow, shared-memory indexing, warp collectives, the blocked FP64-MMA factorisation —
-on the CPU.  Not a fallback: nothing in the product package imports this."""
+"""TEST INFRASTRUCTURE ONLY — the CUDA sources of multicomponent_t2_toolbox_b200/csrc compiled by g++ against the
+single-threaded SIMT emulator (simt_emu.h) into tests/emu/_build/libmet2_emu.so.  The library exports the SAME C ABI as
+libmet2.so (include/met2.h): the host code of every entry point (argument checks, workspace carving, geometry, launch
+sequence) runs unchanged and its MET2_LAUNCH sites drive the emulator, so the `-m "not gpu"` tests exercise the kernels'
+real source — control flow, shared-memory indexing (bounds-checked), warp collectives, the blocked FP64-MMA
+factorisation — with HOST (numpy) pointers.  Not a fallback: nothing in the product package imports this, and
+multicomponent_t2_toolbox_b200/_lib.py only ever loads libmet2.so."""
 import ctypes
 import os
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -15,6 +19,7 @@ BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(BUILD, "libmet2_emu.so")
 
 METHODS = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3, "GCV": 4, "BayesReg": 5}
+P = ctypes.c_void_p
 
 
 class T2Cfg(ctypes.Structure):   # met2_t2_cfg of include/met2.h
@@ -25,23 +30,81 @@ class T2Cfg(ctypes.Structure):   # met2_t2_cfg of include/met2.h
                 ("log_det_L", ctypes.c_double), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
+class FaCfg(ctypes.Structure):   # met2_fa_cfg of include/met2.h
+    _fields_ = [("method", ctypes.c_int32), ("nTE", ctypes.c_int32), ("nT2", ctypes.c_int32), ("nA", ctypes.c_int32),
+                ("nKnots", ctypes.c_int32), ("final_solve", ctypes.c_int32),
+                ("brent_lo", ctypes.c_double), ("brent_hi", ctypes.c_double), ("brent_xatol", ctypes.c_double),
+                ("brent_maxfun", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+def _sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu")) + \
+        [os.path.join(HERE, "emu_runtime.cpp")]
+
+
 def build(force=False):
-    deps = [os.path.join(HERE, f) for f in ("emu_kernels.cpp", "simt_emu.h")]
-    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
-    deps.append(os.path.join(ROOT, "include", "met2.h"))
+    """g++ every csrc/*.cu (as C++, -DMET2_HOST_EMU) + emu_runtime.cpp -> libmet2_emu.so.  Rebuilds when a source is
+    newer than the library."""
+    deps = _sources() + [os.path.join(HERE, "simt_emu.h"), os.path.join(ROOT, "include", "met2.h")]
+    deps += [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", "-I", HERE, "-I", CSRC,
-           "-I", os.path.join(ROOT, "include"), os.path.join(HERE, "emu_kernels.cpp"), "-o", LIB]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    flags = ["-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-DMET2_HOST_EMU=1", "-x", "c++", "-I", HERE, "-I", CSRC,
+             "-I", os.path.join(ROOT, "include")]
+
+    def compile_one(src):
+        obj = os.path.join(BUILD, os.path.basename(src) + ".o")
+        r = subprocess.run(["g++"] + flags + ["-c", src, "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed on %s (SIMT emulation build):\n%s" % (src, r.stderr[-6000:]))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        objs = list(ex.map(compile_one, _sources()))
+    r = subprocess.run(["g++", "-shared", "-o", LIB] + objs, capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("g++ failed on the SIMT-emulated kernels:\n" + r.stderr[-6000:])
+        raise RuntimeError("link of libmet2_emu.so failed:\n" + r.stderr[-4000:])
     return LIB
 
 
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(build())
+        _lib.met2_last_error.restype = ctypes.c_char_p
+        _lib.met2_t2_workspace_bytes.restype = ctypes.c_int64
+        _lib.met2_t2_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.POINTER(T2Cfg)]
+        _lib.met2_fa_workspace_bytes.restype = ctypes.c_int64
+        _lib.met2_fa_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.POINTER(FaCfg)]
+        _lib.met2_segment_workspace_bytes.restype = ctypes.c_int64
+        _lib.met2_segment_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(P) if a is not None else None
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().met2_last_error().decode()))
+
+
+def counters(reset_only=False):
+    """Work since the last call: per-THREAD counts of fma(), shared-memory accesses, __syncwarp, warp collectives
+    (divide by 32 for warp level) and the number of kernel launches."""
+    cnt = (ctypes.c_longlong * 5)()
+    lib().emu_counters(cnt)
+    return None if reset_only else dict(fma=int(cnt[0]), smem=int(cnt[1]), syncwarp=int(cnt[2]),
+                                        collectives=int(cnt[3]), launches=int(cnt[4]))
+
+
 def tables(Dic_3D, L):
-    """Host (numpy) versions of what met2_epg_dictionary / met2_gram_tables hand to the fit kernel:
+    """numpy versions of what met2_epg_dictionary / met2_gram_tables hand to the fit kernels:
     dic [nA][nTE][nT2], dicT [nA][nT2][nTE], G [nA][nT2][nT2], kband [10][nT2]."""
     dic = np.ascontiguousarray(np.transpose(Dic_3D, (2, 0, 1)))
     dicT = np.ascontiguousarray(np.transpose(Dic_3D, (2, 1, 0)))
@@ -61,11 +124,40 @@ def tables(Dic_3D, L):
     return dic, dicT, G, kband
 
 
+def epg_dictionary(alphas, T2s, T1s, nTE, tau, TR):
+    """met2_epg_dictionary -> (dic [nA][nTE][nT2], dicT [nA][nT2][nTE])."""
+    alphas = np.ascontiguousarray(alphas, dtype=np.float64)
+    T2s = np.ascontiguousarray(T2s, dtype=np.float64)
+    T1s = np.ascontiguousarray(T1s, dtype=np.float64)
+    dic = np.zeros((len(alphas), nTE, len(T2s)))
+    dicT = np.zeros((len(alphas), len(T2s), nTE))
+    fn = lib().met2_epg_dictionary
+    fn.argtypes = [P, ctypes.c_int, P, P, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, P, P, P]
+    _check(fn(_ptr(alphas), len(alphas), _ptr(T2s), _ptr(T1s), len(T2s), nTE, tau, TR, _ptr(dic), _ptr(dicT), None),
+           "met2_epg_dictionary")
+    return dic, dicT
+
+
+def gram_tables(dic, L):
+    """met2_gram_tables -> (G [nA][nT2][nT2], kband [10][nT2], band_err)."""
+    dic = np.ascontiguousarray(dic, dtype=np.float64)
+    nA, nTE, n = dic.shape
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    G = np.zeros((nA, n, n))
+    kband = np.full((10, n), np.nan)
+    err = np.full(1, -1, dtype=np.int32)
+    fn = lib().met2_gram_tables
+    fn.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P, P, P, P]
+    _check(fn(_ptr(dic), nA, nTE, n, _ptr(L), _ptr(G), _ptr(kband), _ptr(err), None), "met2_gram_tables")
+    return G, kband, int(err[0])
+
+
 def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lambdas=None, myelin_T2=40.0, warps=2,
            factor=1.02, lambda_fixed=1.8):
-    """Run the (emulated) fit kernel.  Returns dict(fsol, est_signal, reg, maps, status, collectives)."""
-    lib = ctypes.CDLL(build())
-    lib.emu_counters((ctypes.c_longlong * 3)())   # reset
+    """met2_t2_fit on host arrays (counting sort, tile list, shared full-set factor tables and the fit kernel, all
+    emulated).  `warps` caps the warps per block (MET2_T2_WARPS).  Returns dict(fsol, est_signal, reg, maps, status,
+    counters)."""
+    counters(reset_only=True)
     sig = np.ascontiguousarray(sig, dtype=np.float64)
     fa_index = np.ascontiguousarray(fa_index, dtype=np.int32)
     V, m = sig.shape
@@ -86,46 +178,31 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
             cfg.log_det_L = float(np.log(np.linalg.det(np.asarray(L, dtype=np.float64))))
     out = dict(fsol=np.zeros((V, n)), est_signal=np.zeros((V, m)), reg=np.zeros(V), maps=np.zeros((V, 6)),
                status=np.zeros(V, dtype=np.uint32))
-    P = ctypes.c_void_p
-
-    def ptr(a):
-        return a.ctypes.data_as(P)
-
-    if echo:
-        fn = lib.emu_t2_echo_x2
-        fn.restype = ctypes.c_longlong
-        fn.argtypes = [P, P, ctypes.c_longlong, ctypes.POINTER(T2Cfg)] + [P] * 11 + [ctypes.c_int]
-        rc = fn(ptr(sig), ptr(fa_index), V, ctypes.byref(cfg), ptr(dic), ptr(dicT), ptr(G), ptr(kband), ptr(logT2),
-                ptr(comp), ptr(out["fsol"]), ptr(out["est_signal"]), ptr(out["reg"]), ptr(out["maps"]),
-                ptr(out["status"]), warps)
-    else:
-        fn = lib.emu_t2_fit
-        fn.restype = ctypes.c_longlong
-        fn.argtypes = [P, P, ctypes.c_longlong, ctypes.POINTER(T2Cfg)] + [P] * 12 + [ctypes.c_int]
-        rc = fn(ptr(sig), ptr(fa_index), V, ctypes.byref(cfg), ptr(dic), ptr(dicT), ptr(G), ptr(kband), ptr(lam),
-                ptr(logT2), ptr(comp), ptr(out["fsol"]), ptr(out["est_signal"]), ptr(out["reg"]), ptr(out["maps"]),
-                ptr(out["status"]), warps)
-    if rc < 0:
-        raise RuntimeError("emulated kernel refused the configuration (%d)" % rc)
-    out["collectives"] = int(rc)
-    cnt = (ctypes.c_longlong * 3)()
-    lib.emu_counters(cnt)
-    out["counters"] = dict(fma=int(cnt[0]), smem=int(cnt[1]), syncwarp=int(cnt[2]))
+    old = os.environ.get("MET2_T2_WARPS")
+    os.environ["MET2_T2_WARPS"] = str(warps)
+    try:
+        nbytes = lib().met2_t2_workspace_bytes(V, ctypes.byref(cfg))
+        if nbytes < 0:
+            raise RuntimeError("met2_t2_workspace_bytes: " + lib().met2_last_error().decode())
+        ws = np.zeros(int(nbytes) + 512, dtype=np.uint8)
+        fn = lib().met2_t2_fit
+        fn.argtypes = [P, P, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [P] * 14
+        _check(fn(_ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(kband),
+                  _ptr(lam), _ptr(logT2), _ptr(comp), _ptr(out["fsol"]), _ptr(out["est_signal"]), _ptr(out["reg"]),
+                  _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), None), "met2_t2_fit")
+    finally:
+        if old is None:
+            del os.environ["MET2_T2_WARPS"]
+        else:
+            os.environ["MET2_T2_WARPS"] = old
+    out["counters"] = counters()
     return out
 
 
-class FaCfg(ctypes.Structure):   # met2_fa_cfg of include/met2.h
-    _fields_ = [("method", ctypes.c_int32), ("nTE", ctypes.c_int32), ("nT2", ctypes.c_int32), ("nA", ctypes.c_int32),
-                ("nKnots", ctypes.c_int32), ("final_solve", ctypes.c_int32),
-                ("brent_lo", ctypes.c_double), ("brent_hi", ctypes.c_double), ("brent_xatol", ctypes.c_double),
-                ("brent_maxfun", ctypes.c_int32), ("reserved", ctypes.c_int32)]
-
-
-def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None, warps=2):
-    """Run the (emulated) flip-angle stage: brute force over `alpha_values`, or the spline method when the coarse
-    dictionary is given.  Returns dict(fa_index, fa_deg, km, fsol_sum, status)."""
-    lib = ctypes.CDLL(build())
-    lib.emu_counters((ctypes.c_longlong * 3)())
+def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None):
+    """met2_fa_fit on host arrays: brute force over `alpha_values`, or the spline method when the coarse dictionary is
+    given.  Returns dict(fa_index, fa_deg, km, fsol_sum, status)."""
+    counters(reset_only=True)
     sig = np.ascontiguousarray(sig, dtype=np.float64)
     V, m = sig.shape
     eye = np.eye(Dic_3D.shape[1])
@@ -133,11 +210,6 @@ def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None, 
     nA, _, n = dic.shape
     alphas = np.ascontiguousarray(alpha_values, dtype=np.float64)
     spline = Dic_3D_LR is not None
-    P = ctypes.c_void_p
-
-    def ptr(a):
-        return a.ctypes.data_as(P) if a is not None else None
-
     dic_s = dicT_s = G_s = knots = None
     if spline:
         dic_s, dicT_s, G_s, _ = tables(np.asarray(Dic_3D_LR, dtype=np.float64), eye)
@@ -146,12 +218,58 @@ def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None, 
                 brent_lo=90.0, brent_hi=180.0, brent_xatol=1e-5, brent_maxfun=500, reserved=0)
     out = dict(fa_index=np.zeros(V, dtype=np.int32), fa_deg=np.zeros(V), km=np.zeros(V), fsol_sum=np.zeros(n),
                status=np.zeros(V, dtype=np.uint32))
-    fn = lib.emu_fa_fit
-    fn.restype = ctypes.c_longlong
-    fn.argtypes = [P, ctypes.c_longlong, ctypes.POINTER(FaCfg)] + [P] * 13 + [ctypes.c_int]
-    rc = fn(ptr(sig), V, ctypes.byref(cfg), ptr(dic), ptr(dicT), ptr(G), ptr(alphas), ptr(dic_s), ptr(dicT_s), ptr(G_s),
-            ptr(knots), ptr(out["fa_index"]), ptr(out["fa_deg"]), ptr(out["km"]), ptr(out["fsol_sum"]),
-            ptr(out["status"]), warps)
-    if rc < 0:
-        raise RuntimeError("emulated FA stage refused the configuration (%d)" % rc)
+    nbytes = lib().met2_fa_workspace_bytes(V, ctypes.byref(cfg))
+    if nbytes < 0:
+        raise RuntimeError("met2_fa_workspace_bytes: " + lib().met2_last_error().decode())
+    ws = np.zeros(int(nbytes) + 512, dtype=np.uint8)
+    fn = lib().met2_fa_fit
+    fn.argtypes = [P, ctypes.c_int64, ctypes.POINTER(FaCfg)] + [P] * 15
+    _check(fn(_ptr(sig), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(alphas), _ptr(dic_s), _ptr(dicT_s),
+              _ptr(G_s), _ptr(knots), _ptr(out["fa_index"]), _ptr(out["fa_deg"]), _ptr(out["km"]), _ptr(out["fsol_sum"]),
+              _ptr(out["status"]), _ptr(ws), None), "met2_fa_fit")
+    out["counters"] = counters()
     return out
+
+
+def gaussian_smooth(vol, sigma=2.0, truncate=4.0):
+    """met2_gaussian_smooth with scipy.ndimage's kernel (radius = int(truncate * sigma + 0.5))."""
+    vol = np.ascontiguousarray(vol, dtype=np.float64)
+    nx, ny, nz, nt = vol.shape
+    radius = int(truncate * sigma + 0.5)
+    x = np.arange(-radius, radius + 1)
+    w = np.exp(-0.5 / (sigma * sigma) * x ** 2)
+    w = np.ascontiguousarray(w / w.sum())
+    out, tmp = np.zeros_like(vol), np.zeros_like(vol)
+    fn = lib().met2_gaussian_smooth
+    fn.argtypes = [P] + [ctypes.c_int] * 4 + [P, ctypes.c_int, P, P, P]
+    _check(fn(_ptr(vol), nx, ny, nz, nt, _ptr(w), radius, _ptr(out), _ptr(tmp), None), "met2_gaussian_smooth")
+    return out
+
+
+def nesma_filter(vol, mask, half_window=6, threshold=2.5):
+    vol = np.ascontiguousarray(vol, dtype=np.float64)
+    mask = np.ascontiguousarray(mask, dtype=np.int32)
+    nx, ny, nz, nt = vol.shape
+    out, tmp = np.zeros_like(vol), np.zeros_like(vol)
+    fn = lib().met2_nesma_filter
+    fn.argtypes = [P, P] + [ctypes.c_int] * 5 + [ctypes.c_double, P, P, P]
+    _check(fn(_ptr(vol), _ptr(mask), nx, ny, nz, nt, half_window, threshold, _ptr(out), _ptr(tmp), None),
+           "met2_nesma_filter")
+    return out
+
+
+def segment_means(sig, fa_index, label, nSeg, dic):
+    """met2_segment_means -> (mean_signal [nSeg][nTE], mean_kernel [nSeg][nTE][nT2], counts [nSeg])."""
+    sig = np.ascontiguousarray(sig, dtype=np.float64)
+    fa_index = np.ascontiguousarray(fa_index, dtype=np.int32)
+    label = np.ascontiguousarray(label, dtype=np.int32)
+    dic = np.ascontiguousarray(dic, dtype=np.float64)
+    V, m = sig.shape
+    nA, _, n = dic.shape
+    ms, mk, cnt = np.zeros((nSeg, m)), np.zeros((nSeg, m, n)), np.zeros(nSeg, dtype=np.int32)
+    ws = np.zeros(int(lib().met2_segment_workspace_bytes(nSeg, nA)) + 512, dtype=np.uint8)
+    fn = lib().met2_segment_means
+    fn.argtypes = [P, P, P, ctypes.c_int64] + [ctypes.c_int] * 4 + [P] * 6
+    _check(fn(_ptr(sig), _ptr(fa_index), _ptr(label), V, m, n, nA, nSeg, _ptr(dic), _ptr(ms), _ptr(mk), _ptr(cnt),
+              _ptr(ws), None), "met2_segment_means")
+    return ms, mk, cnt

@@ -35,9 +35,36 @@ typedef void* cudaStream_t;
 struct double2 {
     double x, y;
 };
-struct emu_dim3 {
+struct dim3 {
     unsigned x, y, z;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
+typedef dim3 emu_dim3;
+
+// the few CUDA runtime calls the host side of csrc/ makes
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaDeviceProp {
+    int multiProcessorCount;
+};
+template <class F>
+inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+    memset(p, v, n);
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetDevice(int* d) {
+    *d = 0;
+    return cudaSuccess;
+}
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
+    const char* ev = getenv("SIMT_EMU_SMS");
+    p->multiProcessorCount = ev ? atoi(ev) : 2;   // "SMs" of the emulated device: sizes the persistent grids
+    return cudaSuccess;
+}
 
 namespace simt {
 
@@ -67,6 +94,8 @@ extern emu_dim3 g_threadIdx, g_blockIdx, g_blockDim, g_gridDim;
 // Work counters (per THREAD events; divide by 32 for warp-level instruction estimates): explicit fma() calls, accesses to
 // the shared-memory array S, warp barriers.  A cost model for comparing kernel variants without a GPU.
 extern long long n_fma, n_smem, n_syncwarp;
+struct Shared;
+extern Shared g_shared;   // the block's dynamic shared memory (csrc: `S`)
 
 // The dynamic shared memory: S[i] and S + off like the device array, with access counting.
 struct Shared {
@@ -169,18 +198,22 @@ static void fiber_entry() {
 }
 
 // Run `body` as one thread block of `nthreads` threads (a multiple of 32).
-inline long long run_block(int nthreads, int block_index, int grid, std::function<void()> body) {
+inline long long run_block(int nthreads, int block_index, int grid, std::function<void()> body, dim3 bdim = dim3(0)) {
     Block blk;
     g_block = &blk;
     blk.nthreads = nthreads;
     blk.body = body;
     blk.fibers.resize(nthreads);
+    if (nthreads % 32) {
+        fprintf(stderr, "simt_emu: block size %d is not a multiple of 32\n", nthreads);
+        abort();
+    }
     blk.warp_arrived.assign(nthreads / 32, 0);
     blk.warp_gen.assign(nthreads / 32, 0);
     blk.xbuf.assign((size_t)nthreads * 2, 0);
-    g_blockIdx = {(unsigned)block_index, 0, 0};
-    g_blockDim = {(unsigned)nthreads, 1, 1};
-    g_gridDim = {(unsigned)grid, 1, 1};
+    g_blockIdx = dim3((unsigned)block_index, 0, 0);
+    g_blockDim = bdim.x ? bdim : dim3((unsigned)nthreads, 1, 1);
+    g_gridDim = dim3((unsigned)grid, 1, 1);
     for (int t = 0; t < nthreads; ++t) {
         Fiber& f = blk.fibers[t];
         f.tid = t;
@@ -219,7 +252,8 @@ inline long long run_block(int nthreads, int block_index, int grid, std::functio
             Fiber& f = blk.fibers[t];
             if (f.done) continue;
             blk.cur = t;
-            g_threadIdx = {(unsigned)t, 0, 0};
+            g_threadIdx = dim3((unsigned)t % g_blockDim.x, ((unsigned)t / g_blockDim.x) % g_blockDim.y,
+                               (unsigned)t / (g_blockDim.x * g_blockDim.y));
             swapcontext(&blk.sched, &f.ctx);
             ++progressed;
             if (f.done) --live;
@@ -232,6 +266,33 @@ inline long long run_block(int nthreads, int block_index, int grid, std::functio
     }
     g_block = nullptr;
     return blk.collectives;
+}
+
+extern long long n_collectives, n_launches;
+
+// `MET2_LAUNCH(grid, block, smem, stream, kernel)(args...)` of csrc/met2_host.h: runs the blocks of a 1-D grid one after
+// the other, each as run_block; the dynamic shared memory is bounds-checked against the size the host code asked for.
+template <class... P>
+struct Launch {
+    dim3 grid, block;
+    size_t smem;
+    void (*kern)(P...);
+    template <class... Q>
+    void operator()(Q&&... args) const {
+        if (grid.y != 1 || grid.z != 1) {
+            fprintf(stderr, "simt_emu: only 1-D grids are emulated\n");
+            abort();
+        }
+        const int nthreads = (int)(block.x * block.y * block.z);
+        g_shared.size = (long)(smem / sizeof(double));
+        ++n_launches;
+        for (unsigned b = 0; b < grid.x; ++b)
+            n_collectives += run_block(nthreads, (int)b, (int)grid.x, [&]() { kern(args...); }, block);
+    }
+};
+template <class... P>
+inline Launch<P...> make_launch(dim3 grid, dim3 block, size_t smem, void (*kern)(P...)) {
+    return Launch<P...>{grid, block, smem, kern};
 }
 
 }  // namespace simt
@@ -285,14 +346,23 @@ inline unsigned __ballot_sync(unsigned, bool pred) {
 inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
 inline bool __all_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 
+// CUDA's global-scope integer min / max
+inline int min(int a, int b) { return a < b ? a : b; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline long long min(long long a, long long b) { return a < b ? a : b; }
+inline long long max(long long a, long long b) { return a > b ? a : b; }
+inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
+inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
+
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline long long __double_as_longlong(double d) { return simt::from_bits<long long>(simt::to_bits(d)); }
 inline double __longlong_as_double(long long v) { return simt::from_bits<double>(simt::to_bits(v)); }
 inline float __frcp_rn(float x) { return 1.0f / x; }
 inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 inline double rsqrt(double x) { return 1.0 / sqrt(x); }
-inline int atomicAdd(int* p, int v) {
-    int o = *p;
+template <class T>
+inline T atomicAdd(T* p, T v) {   // one fiber runs at a time: plain read-modify-write is atomic here
+    T o = *p;
     *p = o + v;
     return o;
 }

@@ -26,11 +26,19 @@ def setup(golden_config2):
     return dict(gr=gr, Dic=Dic, g=golden_config2)
 
 
-def _run(order, *args, **kw):
+def _run(order, sig, fa, Dic, *args, **kw):
+    """met2_t2_fit under the emulator with the given lane-scheduling order.  The dictionary is cut down to the flip
+    angles these voxels use (the shared factor tables are built per angle: 273 angles would only cost emulation time);
+    an out-of-range index stays out of range."""
+    fa = np.asarray(fa)
+    valid = (fa >= 0) & (fa < Dic.shape[2])
+    uniq, inv = np.unique(fa[valid], return_inverse=True)
+    fa_c = np.full(fa.shape, len(uniq) + 5, dtype=np.int32)
+    fa_c[valid] = inv
     old = os.environ.get("SIMT_EMU_ORDER")
     os.environ["SIMT_EMU_ORDER"] = order
     try:
-        return emu.t2_fit(*args, **kw)
+        return emu.t2_fit(sig, fa_c, np.ascontiguousarray(Dic[:, :, uniq]), *args, **kw)
     finally:
         if old is None:
             del os.environ["SIMT_EMU_ORDER"]
