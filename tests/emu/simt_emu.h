@@ -70,10 +70,16 @@ namespace simt {
 
 struct Fiber {
     ucontext_t ctx;
-    std::vector<char> stack;
+    char* stack = nullptr;   // from the process-wide pool below (allocated once, never zeroed, reused by every block)
     int tid = 0;
     bool done = false;
 };
+constexpr size_t FIBER_STACK = 512 * 1024;
+inline char* fiber_stack(int t) {
+    static std::vector<char*> pool;
+    while ((int)pool.size() <= t) pool.push_back(static_cast<char*>(malloc(FIBER_STACK)));
+    return pool[t];
+}
 
 struct Block {
     std::vector<Fiber> fibers;
@@ -217,10 +223,10 @@ inline long long run_block(int nthreads, int block_index, int grid, std::functio
     for (int t = 0; t < nthreads; ++t) {
         Fiber& f = blk.fibers[t];
         f.tid = t;
-        f.stack.resize(512 * 1024);
+        f.stack = fiber_stack(t);
         getcontext(&f.ctx);
-        f.ctx.uc_stack.ss_sp = f.stack.data();
-        f.ctx.uc_stack.ss_size = f.stack.size();
+        f.ctx.uc_stack.ss_sp = f.stack;
+        f.ctx.uc_stack.ss_size = FIBER_STACK;
         f.ctx.uc_link = &blk.sched;
         makecontext(&f.ctx, (void (*)())fiber_entry, 0);
     }

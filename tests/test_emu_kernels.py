@@ -68,7 +68,7 @@ def _same(a, b):
 def test_production_x2_kernel_against_reference(setup):
     """t2_fit_kernel<2,1,X2> (warm starts, full-set start, Brent-best snapshot) vs the unmodified reference."""
     g, gr = setup["g"], setup["gr"]
-    sel, sig, fa = _pick(g, 16)
+    sel, sig, fa = _pick(g, 10)
     outs = [_run(o, sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16) for o in ORDERS]
     _check(outs[0], g["f"][sel], g["reg"][sel], gr["ind_m"])
     assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
@@ -79,7 +79,7 @@ def test_production_x2_kernel_against_reference(setup):
 def test_echo_space_x2_kernel_against_reference(setup):
     """The experimental echo-space kernel (met2_t2_echo.cu): same tolerances, both starting strategies."""
     g, gr = setup["g"], setup["gr"]
-    sel, sig, fa = _pick(g, 16, offset=7)
+    sel, sig, fa = _pick(g, 10, offset=7)
     outs = [_run(o, sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=True) for o in ORDERS]
     _check(outs[0], g["f"][sel], g["reg"][sel], gr["ind_m"], tol_f=1e-8)
     assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
@@ -182,7 +182,7 @@ def test_fa_stage_kernels_against_reference(setup):
     chosen angle) -> reduce_partials_kernel.  Spline method against the FA indices / km the unmodified reference
     produced (fa_estimation.py:35-72); brute force against the oracle (fa_estimation.py:74-112).  Bit-exact indices."""
     g, gr = setup["g"], setup["gr"]
-    sel = np.arange(3, len(g["sig"]), len(g["sig"]) // 20)[:20]
+    sel = np.arange(3, len(g["sig"]), len(g["sig"]) // 12)[:12]
     sig = g["sig"][sel]
     DicLR = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, gr["alpha_spline"], 1000.0)
     outs = []
@@ -247,3 +247,40 @@ def test_production_kernels_large_sizes(method, matrix, npc, nte, nv, tol):
         assert np.max(np.abs(out["fsol"][i] - f_ref)) < tol * np.abs(f_ref).max()
         assert abs(out["reg"][i] - reg_ref) <= tol * max(1.0, abs(reg_ref))
         assert abs(out["maps"][i, 0] - f_ref[gr["ind_m"]].sum() / f_ref.sum()) < 1e-4
+
+
+def test_whole_chain_against_the_reference_orchestrator_run():
+    """Every kernel of the path in sequence, emulated: EPG dictionary -> NESMA -> Gaussian smoothing -> FA spline search ->
+    X2-I fit + maps, against the output volumes of the UNMODIFIED reference's motor_recon_met2 run end to end
+    (tests/golden/pipeline_nesma_x2.npz, oracle/make_golden_pipeline.py; denoise=NESMA, FA_smooth=yes).  The two
+    preprocessing stages run on the whole 14x12x10 volume, the fits on every 13th masked voxel."""
+    g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "pipeline_nesma_x2.npz")))
+    mask = g["mask"].astype(np.int64)
+    data = g["data"] * mask[..., None]
+    data[data < 0.0] = 0.0                                                     # motor...:178-180
+    gr = O._grids("X2", "I", "spline", 40.0, 32, float(g["TE"][1] - g["TE"][0]), 1000.0)
+    tau = float(g["TE"][1] - g["TE"][0])
+    dic, _ = emu.epg_dictionary(gr["alpha_values"], gr["T2s"], gr["T1s"], 32, tau, 1000.0)
+    dic_lr, _ = emu.epg_dictionary(gr["alpha_spline"], gr["T2s"], gr["T1s"], 32, tau, 1000.0)
+    Dic, DicLR = np.transpose(dic, (1, 2, 0)), np.transpose(dic_lr, (1, 2, 0))
+    den = emu.nesma_filter(data, mask.astype(np.int32))                        # Step 1 (motor...:305-333)
+    smooth = emu.gaussian_smooth(den, 2.0)                                     # FA-stage copy (motor...:336-346)
+    flat = np.nonzero(mask.reshape(-1) > 0)[0][::13]
+    assert len(flat) >= 40
+    sig = den.reshape(-1, 32)[flat]
+    sig_fa = smooth.reshape(-1, 32)[flat]
+    fa = emu.fa_fit(sig_fa, Dic, gr["alpha_values"], DicLR, gr["alpha_spline"])          # Step 2
+    assert np.array_equal(fa["fa_deg"], g["FA"].reshape(-1)[flat])                      # FA map bit-exact
+    out = _run("shuffle", sig, fa["fa_index"], Dic, gr["L"], gr["T2s"], "X2", flags=16)  # Steps 3 and 4
+    f_ref = g["fsol_4D"].reshape(-1, 60)[flat]
+    assert np.array_equal(out["fsol"] > 0, f_ref > 0)                                    # active sets bit-exact
+    scale = np.abs(f_ref).max(axis=1, keepdims=True)
+    scale[scale == 0] = 1.0
+    assert np.max(np.abs(out["fsol"] - f_ref) / scale) < 1e-6
+    for i, k in enumerate(("MWF", "IEWF", "FWF", "T2_M", "T2_IE")):
+        assert np.max(np.abs(out["maps"][:, i] - g[k].reshape(-1)[flat])) < 1e-4, k
+    for got, k in ((out["maps"][:, 5], "TWC"), (out["reg"], "reg_param")):
+        ref = g[k].reshape(-1)[flat]
+        assert np.max(np.abs(got - ref)) <= 1e-6 * np.abs(ref).max(), k
+    s_ref = g["Est_Signal"].reshape(-1, 32)[flat]
+    assert np.max(np.abs(out["est_signal"] - s_ref)) <= 1e-6 * np.abs(s_ref).max()
