@@ -94,3 +94,44 @@ def test_segment_means_against_the_restatement(golden_dictionary):
         assert np.max(np.abs(ms[seg] - s_ref)) < 1e-12 * np.abs(s_ref).max()
         assert np.max(np.abs(mk[seg] - k_ref)) < 1e-12 * np.abs(k_ref).max()
     assert cnt[2] == 0 and np.isnan(ms[2]).all() and np.isnan(mk[2]).all()   # the reference divides by nv = 0
+
+
+def test_c_abi_argument_checks_and_empty_batches():
+    """Error behaviour of the entry points (include/met2.h conventions): negative return + message, nothing launched;
+    an empty batch is a successful no-op.  Same host code as libmet2.so."""
+    import ctypes
+    L = emu.lib()
+    L.met2_last_error.restype = ctypes.c_char_p
+    n, m = 60, 32
+    cfg = emu.T2Cfg(method=2, nTE=m, nT2=n, nA=1, nLambda=50, maxfun=300, factor=1.02, lambda_fixed=1.8, brent_lo=0.0,
+                    brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=0, reserved=0)
+    assert L.met2_t2_workspace_bytes(10, ctypes.byref(cfg)) > 0
+    emu.counters(reset_only=True)
+    for field, bad in (("nT2", 0), ("nT2", 129), ("nTE", 65), ("nA", 0), ("method", 6), ("method", -1)):
+        c = emu.T2Cfg.from_buffer_copy(cfg)
+        setattr(c, field, bad)
+        assert L.met2_t2_workspace_bytes(10, ctypes.byref(c)) == -1
+        assert b"met2_t2" in L.met2_last_error()
+    c = emu.T2Cfg.from_buffer_copy(cfg)
+    c.method, c.nLambda = 3, 2                                      # L-curve needs at least 3 lambdas
+    assert L.met2_t2_workspace_bytes(10, ctypes.byref(c)) == -1
+    buf = np.zeros(4096)
+    p = buf.ctypes.data_as(ctypes.c_void_p)
+    fn = L.met2_t2_fit
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(emu.T2Cfg)] + [ctypes.c_void_p] * 14
+    args = [p, p, 0, ctypes.byref(cfg)] + [p] * 13 + [None]
+    assert fn(*args) == 0                                           # V = 0: nothing to do
+    args[2] = 1
+    args[7] = None                                                  # X2 without kband
+    assert fn(*args) == -1 and b"kband" in L.met2_last_error()
+    args[7] = p
+    args[4] = None                                                  # dic = NULL
+    assert fn(*args) == -1 and b"NULL" in L.met2_last_error()
+    fcfg = emu.FaCfg(method=1, nTE=m, nT2=n, nA=273, nKnots=3, final_solve=1, brent_lo=90.0, brent_hi=180.0,
+                     brent_xatol=1e-5, brent_maxfun=500, reserved=0)
+    assert L.met2_fa_workspace_bytes(10, ctypes.byref(fcfg)) == -1 and b"knots" in L.met2_last_error()
+    assert emu.counters()["launches"] == 0
+    d, _ = emu.epg_dictionary([120.0], [20.0, 80.0], [1000.0, 1000.0], 8, 10.0, 1000.0)
+    assert d.shape == (1, 8, 2) and emu.counters()["launches"] == 1
+    with pytest.raises(RuntimeError, match="bad argument"):
+        emu.epg_dictionary([120.0], np.ones(200), np.ones(200), 8, 10.0, 1000.0)      # nT2 > MET2_MAX_NT2
