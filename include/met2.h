@@ -81,10 +81,11 @@ typedef struct met2_fa_cfg {
 #define MET2_T2_FLAG_FULL_START 16    /* X2: start the solves at Brent's first (voxel-independent) abscissae from the full
                                         column set, with inverse-Cholesky factors shared per flip angle
                                         (worth it when L = I; same minimiser) */
-#define MET2_T2_FLAG_ECHO_SPACE 64    /* EXPERIMENTAL, off by default, X2 only, nTE <= 32, nT2 <= 64, and the caller asserts
-                                        that L is DIAGONAL (I, InvT2): Tikhonov solves in echo space (32 x 32 factor per
-                                        voxel, csrc/met2_t2_echo.cu).  A non-diagonal L skips every voxel with status
-                                        bit 32.  Same minimiser as the default path; not yet validated on a GPU */
+#define MET2_T2_FLAG_ECHO_SPACE 64    /* EXPERIMENTAL, off by default: X2 (nT2 <= 64) and T2SPARC (nT2 <= 128) with
+                                        nTE <= 32 and a DIAGONAL L (I, InvT2; asserted by the caller): Tikhonov solves
+                                        in echo space (32 x 32 factor per voxel, csrc/met2_t2_echo.cu).  A non-diagonal
+                                        L skips every voxel with MET2_ST_ECHO_BAD_L.  Same minimiser as the default
+                                        path; validated on the CPU emulator only so far */
 #define MET2_T2_FLAG_COLD_START 4    /* start every NNLS of a lambda search from the empty set like the reference,
                                         instead of warm-starting from the previous solution (same minimiser) */
 

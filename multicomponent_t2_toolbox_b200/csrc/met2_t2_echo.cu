@@ -45,8 +45,10 @@ struct EchoOff {
     int Dt, Mp, B, V, D;   // offsets into S
 };
 
-// v = T (T^T b), g = Dt^T v.  lane = position / echo for the triangular products, lane + 32 s = column for g.
-__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[2]) {
+// v = T (T^T b), g = Dt^T v.  lane = position / echo for the triangular products, lane + 32 s = column for g (NC column
+// slots per lane: nT2 <= 32 NC).
+template <int NC>
+__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[NC]) {
     double y[1], v[1];
     tmul_transposed<1>(W.T, O.B, EC_M, lane, y);
     S[W.rs + lane] = y[0];
@@ -54,18 +56,21 @@ __device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, 
     tmul<1>(W.T, W.rs, EC_M, lane, v);
     S[O.V + lane] = v[0];
     __syncwarp();
-    double g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0;
-    const int r0 = O.Dt + lane * EC_LDD, r1 = O.Dt + (lane + 32) * EC_LDD;
+    double g0[NC], g1[NC];
+#pragma unroll
+    for (int s = 0; s < NC; ++s) g0[s] = g1[s] = 0.0;
+    const int r0 = O.Dt + lane * EC_LDD;
 #pragma unroll 1
     for (int e = 0; e < EC_M; e += 2) {
         const double v0 = S[O.V + e], v1 = S[O.V + e + 1];
-        g0 = fma(S[r0 + e], v0, g0);
-        h0 = fma(S[r0 + e + 1], v1, h0);
-        g1 = fma(S[r1 + e], v0, g1);
-        h1 = fma(S[r1 + e + 1], v1, h1);
+#pragma unroll
+        for (int s = 0; s < NC; ++s) {
+            g0[s] = fma(S[r0 + 32 * s * EC_LDD + e], v0, g0[s]);
+            g1[s] = fma(S[r0 + 32 * s * EC_LDD + e + 1], v1, g1[s]);
+        }
     }
-    g[0] = g0 + h0;
-    g[1] = g1 + h1;
+#pragma unroll
+    for (int s = 0; s < NC; ++s) g[s] = g0[s] + g1[s];
     __syncwarp();
 }
 
@@ -140,22 +145,23 @@ __device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O,
 // block_drop: the entry set is the FULL column set — drop every column whose unconstrained coefficient is not positive
 // in one go before the usual interpolation loop (x stays feasible on the reduced set).
 // On exit inP / x hold the solution (scaled unknowns xt = l * x).
+template <int NC>
 __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, int n, double lam, int lane,
-                                          unsigned& inP, double (&x)[2], int& status, bool block_drop) {
+                                          unsigned& inP, double (&x)[NC], int& status, bool block_drop) {
     const int itmax = 3 * n;
     int iter = 0;
     bool secondary_first = __any_sync(FULL_MASK, inP != 0u);
     bool have_g = false;   // g is the solve for the current set (left by an accepted interpolation loop)
-    double g[2];
+    double g[NC];
     while (true) {
         if (!secondary_first) {
             if ((int)__reduce_add_sync(FULL_MASK, (unsigned)__popc(inP)) >= n) break;
             // ---- entering column: arg-max of the dual w = lam g over the zero set (lam > 0: same order as g)
-            if (!have_g) echo_solve(W, O, lane, g);
+            if (!have_g) echo_solve<NC>(W, O, lane, g);
             double bv = 0.0;
             int bj = -1;
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NC; ++s) {
                 const int col = lane + 32 * s;
                 if (col < n && !((inP >> s) & 1u) && g[s] > bv) {
                     bv = g[s];
@@ -177,16 +183,16 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
                 stop = true;
                 break;
             }
-            echo_solve(W, O, lane, g);
+            echo_solve<NC>(W, O, lane, g);
             const bool drop_now = block_drop;
             block_drop = false;
             unsigned negm = 0u;
 #pragma unroll
-            for (int s = 0; s < 2; ++s)
+            for (int s = 0; s < NC; ++s)
                 if (((inP >> s) & 1u) && g[s] <= 0.0) negm |= 1u << s;
             if (!__any_sync(FULL_MASK, negm != 0u)) {
 #pragma unroll
-                for (int s = 0; s < 2; ++s) x[s] = ((inP >> s) & 1u) ? g[s] : 0.0;
+                for (int s = 0; s < NC; ++s) x[s] = ((inP >> s) & 1u) ? g[s] : 0.0;
                 have_g = true;
                 break;
             }
@@ -197,7 +203,7 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
                 double bt = 2.0;
                 int bi = -1;
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < NC; ++s) {
                     if ((negm >> s) & 1u) {
                         const double tt = x[s] / (x[s] - g[s]);
                         if (tt < bt) {
@@ -210,7 +216,7 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
                 const int jb = warp_argmin_nonneg(bt, bi, alpha);
                 if (jb < 0) break;
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
+                for (int s = 0; s < NC; ++s) {
                     if ((inP >> s) & 1u) {
                         x[s] = x[s] + alpha * (g[s] - x[s]);
                         if (x[s] <= 0.0 || lane + 32 * s == jb) outm |= 1u << s;
@@ -220,16 +226,18 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
             // ---- remove them one by one (lowest column first)
             while (true) {
                 int k = 0x7fffffff;
-                if (outm & 2u) k = lane + 32;
-                if (outm & 1u) k = lane;
+#pragma unroll
+                for (int s = NC - 1; s >= 0; --s)
+                    if ((outm >> s) & 1u) k = lane + 32 * s;
                 k = (int)__reduce_min_sync(FULL_MASK, (unsigned)k);
                 if (k == 0x7fffffff) break;
                 if ((k & 31) == lane) {
                     const unsigned bit = 1u << (k >> 5);
                     outm &= ~bit;
                     inP &= ~bit;
-                    if (k >> 5) x[1] = 0.0;
-                    else x[0] = 0.0;
+#pragma unroll
+                    for (int s = 0; s < NC; ++s)
+                        if (s == (k >> 5)) x[s] = 0.0;
                 }
                 if (!echo_change(W, O, k, -1.0, lam, lane)) status |= 2;
             }
@@ -238,16 +246,16 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
     }
 }
 
-// fit = Dt xt (= D x) with lane = echo, SSE = sum (fit - b)^2.  xt is read from S[W.xc + 0..64) (column space).
-__device__ __forceinline__ double echo_fit_sse(const Slots<2>& W, const EchoOff& O, int n, int lane, double& fit) {
+// fit = Dt xt (= D x) with lane = echo, SSE = sum (fit - b)^2.  xt is read from S[oX + 0..n) (column space).
+__device__ __forceinline__ double echo_fit_sse(int oX, const EchoOff& O, int n, int lane, double& fit) {
     double f0 = 0.0, f1 = 0.0;
     int j = 0;
 #pragma unroll 1
     for (; j + 1 < n; j += 2) {
-        f0 = fma(S[O.Dt + j * EC_LDD + lane], S[W.xc + j], f0);
-        f1 = fma(S[O.Dt + (j + 1) * EC_LDD + lane], S[W.xc + j + 1], f1);
+        f0 = fma(S[O.Dt + j * EC_LDD + lane], S[oX + j], f0);
+        f1 = fma(S[O.Dt + (j + 1) * EC_LDD + lane], S[oX + j + 1], f1);
     }
-    if (j < n) f0 = fma(S[O.Dt + j * EC_LDD + lane], S[W.xc + j], f0);
+    if (j < n) f0 = fma(S[O.Dt + j * EC_LDD + lane], S[oX + j], f0);
     fit = f0 + f1;
     const double dd = fit - S[O.B + lane];
     return warp_sum(dd * dd);
@@ -409,12 +417,12 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                 int est = 0;
                 while (true) {
                     if (!echo_refactor(W, O, lam, lane)) st |= MET2_ST_NOT_PD;
-                    echo_nnls(W, O, n, lam, lane, inP, x, est, block_drop);
+                    echo_nnls<2>(W, O, n, lam, lane, inP, x, est, block_drop);
                     block_drop = false;
 #pragma unroll
                     for (int s = 0; s < 2; ++s) S[W.xc + lane + 32 * s] = x[s];
                     __syncwarp();
-                    const double sse = echo_fit_sse(W, O, n, lane, fit);
+                    const double sse = echo_fit_sse(W.xc, O, n, lane, fit);
                     const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
                     const double lam_eval = lam;
                     const bool more = B.feed(cost, lam);
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                     S[W.xc + j] = S[oSnap + j];
                 }
                 __syncwarp();
-                (void)echo_fit_sse(W, O, n, lane, fit);
+                (void)echo_fit_sse(W.xc, O, n, lane, fit);
                 __syncwarp();
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -501,13 +509,215 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
     }
 }
 
+// ---------------------------------------------------------------------------------------------- fixed-lambda Tikhonov
+// T2SPARC (algorithms.py:262-269 with reg = 1.8, motor...:138) in echo space, nT2 <= 32 NC (the reference's 96 bins:
+// NC = 3).  One solve per voxel from the empty set: the factor of lam I is T = I / sqrt(lam), every entering / leaving
+// column is one rank-one update of the 32 x 32 factor — no Gram matrix, no n x n factor (the Gram-domain kernel keeps
+// tri(96) = 4 656 doubles per voxel and runs at three warps per SM).
+// per-warp shared memory (doubles): Slots<2>(pmax 32) | M_P (528) | signal (64) | v (32) | d (32) | x column space (32 NC)
+template <int NC>
+__host__ __device__ __forceinline__ int echo_tik_warp_doubles() {
+    return (Slots<2>::doubles(EC_M) + tri(EC_M) + 64 + 32 + 32 + 32 * NC + 31) & ~31;
+}
+// CTA tables (doubles): Dt [32 NC][33] | l | 1/l | logT2 (32 NC each) | comp
+template <int NC>
+__host__ __device__ __forceinline__ int echo_tik_table_doubles() {
+    return (32 * NC * EC_LDD + 3 * 32 * NC + (32 * NC + 7) / 8 + 31) & ~31;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args A) {
+    __shared__ int s_tile, s_next, s_badL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = A.cfg.nT2, m = A.cfg.nTE;
+    constexpr int NCOL = 32 * NC;
+    const int oDt = 0;
+    const int oL = oDt + NCOL * EC_LDD;
+    const int oIL = oL + NCOL;
+    const int oLogT2 = oIL + NCOL;
+    unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + NCOL);
+    const int wbase = echo_tik_table_doubles<NC>() + warp * echo_tik_warp_doubles<NC>();
+    Slots<2> W;
+    W.carve(wbase, EC_M);
+    EchoOff O;
+    O.Dt = oDt;
+    O.Mp = wbase + Slots<2>::doubles(EC_M);
+    const int oM = O.Mp + tri(EC_M);
+    O.B = oM;
+    O.V = oM + 64;
+    O.D = O.V + 32;
+    const int oX = O.D + 32;
+    const double lam = A.cfg.lambda_fixed;
+    const double tdiag = 1.0 / sqrt(lam);
+
+    if (threadIdx.x == 0) s_badL = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < NCOL; i += blockDim.x) {
+        double l = 1.0;
+        if (i < n) {
+            l = A.kband[7 * n + i];
+            bool bad = !(l > 0.0) || !(l < 1e300);
+            for (int d = 0; d < 5; ++d)
+                if (d != 2 && A.kband[(5 + d) * n + i] != 0.0) bad = true;
+            if (bad) atomicOr(&s_badL, 1);
+        }
+        S[oL + i] = l;
+        S[oIL + i] = 1.0 / l;
+        S[oLogT2 + i] = (i < n) ? A.logT2[i] : 0.0;
+        if (i < n) scomp[i] = A.comp[i];
+    }
+    const int ntiles = A.counters[0];
+
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s_tile = atomicAdd(&A.counters[1], 1);
+            s_next = 0;
+        }
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const bool badL = (s_badL != 0) || !(lam > 0.0);
+        const int fa = A.tile_fa[tile];
+        const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
+        const double* Dtg = A.dicT + (size_t)fa * n * m;
+        for (int i = threadIdx.x; i < NCOL * EC_LDD; i += blockDim.x) {
+            const int j = i / EC_LDD, e = i - j * EC_LDD;
+            S[oDt + i] = (j < n && e < m) ? __ldg(Dtg + j * m + e) * S[oIL + j] : 0.0;
+        }
+        __syncthreads();
+
+        while (true) {
+            int it = 0;
+            if (lane == 0) it = atomicAdd(&s_next, 1);
+            it = __shfl_sync(FULL_MASK, it, 0);
+            if (it >= tcnt) break;
+            const long long v = A.perm[tstart + it];
+            unsigned st = load_signal<1>(A.sig, v, m, oM, lane);
+            const int fav = A.fa_index[v];
+            const bool normalise = !(A.cfg.flags & MET2_T2_FLAG_NO_NORMALISE);
+            const double km = normalise ? S[oM] : 1.0;
+            if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
+            if (!st && badL) st = MET2_ST_SKIPPED | MET2_ST_ECHO_BAD_L;
+            double fit = 0.0;
+            if (!st) {
+                __syncwarp();
+                S[oM + lane] = (lane < m) ? S[oM + lane] / km : 0.0;
+                // empty set: M_P = 0, T = I / sqrt(lam)
+                for (int i = lane; i < tri(EC_M); i += 32) {
+                    S[O.Mp + i] = 0.0;
+                    S[W.T + i] = 0.0;
+                }
+                __syncwarp();
+                S[W.T + tri(lane) + lane] = tdiag;
+                __syncwarp();
+                unsigned inP = 0u;
+                double x[NC];
+#pragma unroll
+                for (int s = 0; s < NC; ++s) x[s] = 0.0;
+                int est = 0;
+                echo_nnls<NC>(W, O, n, lam, lane, inP, x, est, false);
+#pragma unroll
+                for (int s = 0; s < NC; ++s) S[oX + lane + 32 * s] = x[s];
+                __syncwarp();
+                (void)echo_fit_sse(oX, O, n, lane, fit);
+                __syncwarp();
+#pragma unroll
+                for (int s = 0; s < NC; ++s) S[oX + lane + 32 * s] = x[s] * S[oIL + lane + 32 * s];
+                __syncwarp();
+                if (est & 1) st |= MET2_ST_ITMAX;
+                if (est & 2) st |= MET2_ST_NOT_PD;
+            }
+            // ---- outputs (motor...:153-155, 443-472)
+            const bool fitted = !(st & MET2_ST_SKIPPED);
+            const double kmo = fitted ? km : 0.0;
+            double xk[NC];
+            double vt = 0.0;
+#pragma unroll
+            for (int s = 0; s < NC; ++s) {
+                const int col = lane + 32 * s;
+                xk[s] = (col < n && fitted) ? S[oX + col] * kmo : 0.0;
+                vt += xk[s];
+                if (col < n) A.fsol[v * n + col] = xk[s];
+            }
+            if (lane < m) A.est[v * m + lane] = fitted ? fit * kmo : 0.0;
+            vt = warp_sum(vt) + 1.0e-16;
+            double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
+#pragma unroll
+            for (int s = 0; s < NC; ++s) {
+                const int col = lane + 32 * s;
+                if (col < n) {
+                    const double xn = xk[s] / vt;
+                    const unsigned char cm = scomp[col];
+                    if (cm & 1) {
+                        sm += xn;
+                        lm += xn * S[oLogT2 + col];
+                    }
+                    if (cm & 2) {
+                        stt += xn;
+                        lt += xn * S[oLogT2 + col];
+                    }
+                    if (cm & 4) sc += xn;
+                }
+            }
+            sm = warp_sum(sm);
+            stt = warp_sum(stt);
+            sc = warp_sum(sc);
+            lm = warp_sum(lm);
+            lt = warp_sum(lt);
+            if (lane == 0) {
+                double* mp = A.maps + v * 6;
+                mp[0] = sm;
+                mp[1] = stt;
+                mp[2] = sc;
+                mp[3] = exp(lm / (sm + 1.0e-16));
+                mp[4] = exp(lt / (stt + 1.0e-16));
+                mp[5] = vt;
+                A.reg[v] = fitted ? lam : 0.0;
+                A.status[v] = st;
+            }
+            __syncwarp();
+        }
+    }
+}
+
 bool t2_echo_eligible(const met2_t2_cfg* cfg) {
-    return cfg->method == MET2_REG_X2 && (cfg->flags & MET2_T2_FLAG_ECHO_SPACE) && cfg->nTE <= EC_M &&
-           cfg->nT2 <= EC_NCOL && !(cfg->flags & MET2_T2_FLAG_COLD_START);
+    if (!(cfg->flags & MET2_T2_FLAG_ECHO_SPACE) || cfg->nTE > EC_M) return false;
+    if (cfg->method == MET2_REG_X2) return cfg->nT2 <= EC_NCOL && !(cfg->flags & MET2_T2_FLAG_COLD_START);
+    if (cfg->method == MET2_REG_T2SPARC) return cfg->nT2 <= 128;
+    return false;
+}
+
+template <int NC>
+static int t2_launch_echo_tik(const T2Args& A, cudaStream_t st) {
+    const size_t tables = sizeof(double) * (size_t)echo_tik_table_doubles<NC>();
+    const size_t per_warp = sizeof(double) * (size_t)echo_tik_warp_doubles<NC>();
+    const size_t budget = 227 * 1024 - 1024;
+    int warps = (int)((budget - tables) / per_warp);
+    if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
+    if (const char* ev = getenv("MET2_T2_WARPS")) {
+        const int w = atoi(ev);
+        if (w >= 1 && w < warps) warps = w;
+    }
+    const size_t smem = tables + per_warp * warps;
+    int sms = sm_count();
+    if (sms <= 0) sms = 148;
+    cudaError_t e = cudaFuncSetAttribute(t2_echo_tik_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_echo_tik attr (%zu B): %s", smem, cudaGetErrorString(e));
+    MET2_LAUNCH(sms, warps * 32, smem, st, t2_echo_tik_kernel<NC>)(A);
+    count_launch();
+    return check_launch("t2_echo_tik_kernel");
 }
 
 int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
     const int n = A.cfg.nT2;
+    if (A.cfg.method == MET2_REG_T2SPARC) {
+        const int nc = (n + 31) / 32;
+        if (nc <= 1) return t2_launch_echo_tik<1>(A, st);
+        if (nc == 2) return t2_launch_echo_tik<2>(A, st);
+        if (nc == 3) return t2_launch_echo_tik<3>(A, st);
+        return t2_launch_echo_tik<4>(A, st);
+    }
     const size_t tables = sizeof(double) * (size_t)echo_table_doubles(n);
     const size_t per_warp = sizeof(double) * (size_t)echo_warp_doubles();
     const size_t budget = 227 * 1024 - 1024;

@@ -284,3 +284,22 @@ def test_whole_chain_against_the_reference_orchestrator_run():
         assert np.max(np.abs(got - ref)) <= 1e-6 * np.abs(ref).max(), k
     s_ref = g["Est_Signal"].reshape(-1, 32)[flat]
     assert np.max(np.abs(out["est_signal"] - s_ref)) <= 1e-6 * np.abs(s_ref).max()
+
+
+@pytest.mark.parametrize("matrix,npc", [("InvT2", 96), ("I", 96), ("InvT2", 60)])
+def test_echo_space_fixed_lambda_kernel(matrix, npc):
+    """t2_echo_tik_kernel (T2SPARC in echo space, experimental): one solve per voxel from the empty set with rank-one
+    updates of the 32 x 32 factor only; the reference's 96-bin grid uses three column slots per lane."""
+    emu.build()
+    gr, Dic, sig, fa = _synthetic(npc, 32, 6, "T2SPARC", matrix)
+    outs = [_run(o, sig, fa, Dic, gr["L"], gr["T2s"], "T2SPARC", echo=True) for o in ORDERS]
+    assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
+    out = outs[0]
+    assert np.all(out["status"] == 0) and np.all(out["reg"] == 1.8)
+    for i in range(len(sig)):
+        f_ref, s_ref, _ = O.t2_fit_voxel(sig[i], np.ascontiguousarray(Dic[:, :, fa[i]]), "T2SPARC", gr["L"],
+                                         gr["lambda_reg"])
+        assert np.array_equal(out["fsol"][i] > 0, f_ref > 0)
+        assert np.max(np.abs(out["fsol"][i] - f_ref)) < 1e-8 * np.abs(f_ref).max()
+        assert np.max(np.abs(out["est_signal"][i] - s_ref)) < 1e-8 * np.abs(s_ref).max()
+        assert abs(out["maps"][i, 0] - f_ref[gr["ind_m"]].sum() / f_ref.sum()) < 1e-8

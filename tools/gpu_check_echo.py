@@ -4,7 +4,8 @@ config-2 volume (supports, spectra, k_est, time).  Run it under `timeout` on the
 
     gpurun --timeout 600 -- 'timeout 300 python tools/gpu_check_echo.py > gpurun_out/echo.log 2>&1'
 
-RM=InvT2 switches the regularisation matrix; SHAPE=48,48,30 shrinks the volume."""
+RM=InvT2 switches the regularisation matrix; SHAPE=48,48,30 shrinks the volume; METHOD=T2SPARC checks the fixed-lambda
+echo-space kernel (t2_echo_tik_kernel; 96 bins) against the default kernel instead (no golden step)."""
 import json
 import os
 import sys
@@ -20,12 +21,13 @@ from multicomponent_t2_toolbox_b200.phantom import make_phantom  # noqa: E402
 
 ECHO = 64
 rm = os.environ.get("RM", "I")
+method = os.environ.get("METHOD", "X2")
 shape = tuple(int(x) for x in os.environ.get("SHAPE", "96,96,60").split(","))
-plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix=rm, FA_method="spline")
-rep = dict(rm=rm)
+plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method="spline")
+rep = dict(rm=rm, method=method)
 
 # ---- 1. golden voxels (20 480, fitted by the unmodified reference with X2-I)
-if rm == "I":
+if rm == "I" and method == "X2":
     g = dict(np.load(os.path.join(ROOT, "tests", "golden", "config2_subset.npz")))
     sup = np.unpackbits(g["support"], axis=1)[:, :60].astype(bool)
     f_ref = np.zeros(sup.shape)
@@ -65,4 +67,4 @@ rep["ab"] = dict(voxels=int(sig.shape[0]), support_mismatch_voxels=int(((d["fsol
                  status_default=int((d["status"] != 0).sum()), status_echo=int((e["status"] != 0).sum()))
 print(json.dumps(rep))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "echo_check_%s.json" % rm), "w"), indent=1)
+json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "echo_check_%s_%s.json" % (method, rm)), "w"), indent=1)
