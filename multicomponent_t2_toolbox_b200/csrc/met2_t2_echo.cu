@@ -28,7 +28,8 @@
 namespace met2 {
 
 constexpr int EC_M = 32;              // echoes (rows of the echo-space system); nTE <= 32, padded with zero rows
-constexpr int EC_LDD = 33;            // row stride of the staged Dt table: conflict-free for lane = row and lane = echo
+constexpr int EC_LDD = 34;            // row stride of the staged Dt table: even (16-byte rows for 128-bit loads with lane =
+                                      // row: a quarter warp covers all 32 banks) and conflict-free for lane = echo
 constexpr int EC_NCOL = 64;           // columns (nT2 <= 64), zero rows beyond nT2
 
 // per-warp shared memory (doubles): Slots<2>(pmax 32) | M_P packed lower (528) | signal (64) | v (32) | d (32) |
@@ -48,10 +49,17 @@ struct EchoOff {
 // v = T (T^T b), g = Dt^T v.  lane = position / echo for the triangular products, lane + 32 s = column for g (NC column
 // slots per lane: nT2 <= 32 NC).
 template <int NC>
-__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[NC]) {
-    double y[1], v[1];
-    tmul_transposed<1>(W.T, O.B, EC_M, lane, y);
-    S[W.rs + lane] = y[0];
+__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[NC], double& y,
+                                           bool& y_ok) {
+    // y = T^T b: fresh after a refactorisation, otherwise carried through the rank-one updates (echo_change)
+    if (!y_ok) {
+        double yy[1];
+        tmul_transposed<1>(W.T, O.B, EC_M, lane, yy);
+        y = yy[0];
+        y_ok = true;
+    }
+    double v[1];
+    S[W.rs + lane] = y;
     __syncwarp();
     tmul<1>(W.T, W.rs, EC_M, lane, v);
     S[O.V + lane] = v[0];
@@ -62,11 +70,14 @@ __device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, 
     const int r0 = O.Dt + lane * EC_LDD;
 #pragma unroll 1
     for (int e = 0; e < EC_M; e += 2) {
-        const double v0 = S[O.V + e], v1 = S[O.V + e + 1];
+        double vv[2];
+        lds_vec<2>(O.V + e, vv);
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
-            g0[s] = fma(S[r0 + 32 * s * EC_LDD + e], v0, g0[s]);
-            g1[s] = fma(S[r0 + 32 * s * EC_LDD + e + 1], v1, g1[s]);
+            double dd[2];
+            lds_vec<2>(r0 + 32 * s * EC_LDD + e, dd);
+            g0[s] = fma(dd[0], vv[0], g0[s]);
+            g1[s] = fma(dd[1], vv[1], g1[s]);
         }
     }
 #pragma unroll
@@ -102,7 +113,8 @@ __device__ __forceinline__ void echo_mp_rank1(const EchoOff& O, int j, double sg
 }
 
 // Column j enters (sgn = +1) or leaves (sgn = -1) the positive set: M_P += sgn d d^T and the matching update of T.
-__device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O, int j, double sgn, double lam, int lane) {
+__device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O, int j, double sgn, double lam, int lane,
+                                            double& y, bool& y_ok) {
     echo_mp_rank1(O, j, sgn, lane);
     // ---- u = T^T d, prefix sums of u^2
     double u[1];
@@ -115,10 +127,18 @@ __device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O,
     const bool okh = (h > 0.0) && (hm1 > 0.0);
     if (!__all_sync(FULL_MASK, okh)) {
         // downdate lost positivity in floating point: refactor from the (already updated) M_P
+        y_ok = false;
         return echo_refactor(W, O, lam, lane);
     }
     const double delta = sqrt(hm1 / h);
     const double q = -sgn * u[0] / (h * delta);
+    if (y_ok) {
+        // y' = Q^T y:  y'_j = delta_j y_j + q_j sum_{i < j} u_i y_i   (one more scan instead of a fresh T'^T b)
+        double e[1] = {u[0] * y};
+        const double own = e[0];
+        warp_scan_positions<1>(e, lane);
+        y = fma(q, e[0] - own, delta * y);
+    }
     S[W.gs + lane] = delta;
     S[W.gs + 32 + lane] = q;
     S[W.rs + lane] = u[0];
@@ -153,11 +173,13 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
     bool secondary_first = __any_sync(FULL_MASK, inP != 0u);
     bool have_g = false;   // g is the solve for the current set (left by an accepted interpolation loop)
     double g[NC];
+    double y = 0.0;        // y = T^T b of the current factor (lane = position), valid when y_ok
+    bool y_ok = false;
     while (true) {
         if (!secondary_first) {
             if ((int)__reduce_add_sync(FULL_MASK, (unsigned)__popc(inP)) >= n) break;
             // ---- entering column: arg-max of the dual w = lam g over the zero set (lam > 0: same order as g)
-            if (!have_g) echo_solve<NC>(W, O, lane, g);
+            if (!have_g) echo_solve<NC>(W, O, lane, g, y, y_ok);
             double bv = 0.0;
             int bj = -1;
 #pragma unroll
@@ -171,7 +193,7 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
             const int j = warp_argmax_pos(bv, bj);
             if (j < 0) break;
             if ((j & 31) == lane) inP |= 1u << (j >> 5);
-            if (!echo_change(W, O, j, 1.0, lam, lane)) status |= 2;
+            if (!echo_change(W, O, j, 1.0, lam, lane, y, y_ok)) status |= 2;
         }
         secondary_first = false;
         have_g = false;
@@ -183,7 +205,7 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
                 stop = true;
                 break;
             }
-            echo_solve<NC>(W, O, lane, g);
+            echo_solve<NC>(W, O, lane, g, y, y_ok);
             const bool drop_now = block_drop;
             block_drop = false;
             unsigned negm = 0u;
@@ -239,7 +261,7 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
                     for (int s = 0; s < NC; ++s)
                         if (s == (k >> 5)) x[s] = 0.0;
                 }
-                if (!echo_change(W, O, k, -1.0, lam, lane)) status |= 2;
+                if (!echo_change(W, O, k, -1.0, lam, lane, y, y_ok)) status |= 2;
             }
         }
         if (stop) break;
