@@ -69,9 +69,11 @@ def test_production_x2_kernel_against_reference(setup):
     """t2_fit_kernel<2,1,X2> (warm starts, full-set start, Brent-best snapshot) vs the unmodified reference."""
     g, gr = setup["g"], setup["gr"]
     sel, sig, fa = _pick(g, 10)
-    outs = [_run(o, sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16) for o in ORDERS]
-    _check(outs[0], g["f"][sel], g["reg"][sel], gr["ind_m"])
-    assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
+    out = _run("forward", sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16)
+    _check(out, g["f"][sel], g["reg"][sel], gr["ind_m"])
+    for o in ORDERS[1:]:                                     # lane-order invariance on the first voxels
+        other = _run(o, sig[:4], fa[:4], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16)
+        assert all(np.array_equal(out[k][:4], other[k]) for k in ("fsol", "est_signal", "reg", "maps", "status"))
     cold = _run("forward", sig[:4], fa[:4], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=4)   # MET2_T2_FLAG_COLD_START
     _check(cold, g["f"][sel[:4]], g["reg"][sel[:4]], gr["ind_m"])
 
@@ -80,9 +82,11 @@ def test_echo_space_x2_kernel_against_reference(setup):
     """The experimental echo-space kernel (met2_t2_echo.cu): same tolerances, both starting strategies."""
     g, gr = setup["g"], setup["gr"]
     sel, sig, fa = _pick(g, 10, offset=7)
-    outs = [_run(o, sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=True) for o in ORDERS]
+    outs = [_run("forward", sig, fa, setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=True)]
     _check(outs[0], g["f"][sel], g["reg"][sel], gr["ind_m"], tol_f=1e-8)
-    assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
+    for o in ORDERS[1:]:
+        other = _run(o, sig[:4], fa[:4], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=True)
+        assert all(np.array_equal(outs[0][k][:4], other[k]) for k in ("fsol", "est_signal", "reg", "maps", "status"))
     # est_signal = D f * km (motor...:155) and the lambda-returning variant
     D = np.transpose(setup["Dic"], (2, 0, 1))[fa]
     assert np.allclose(outs[0]["est_signal"], np.einsum("vec,vc->ve", D, outs[0]["fsol"]), rtol=1e-10, atol=1e-9)
@@ -182,7 +186,7 @@ def test_fa_stage_kernels_against_reference(setup):
     chosen angle) -> reduce_partials_kernel.  Spline method against the FA indices / km the unmodified reference
     produced (fa_estimation.py:35-72); brute force against the oracle (fa_estimation.py:74-112).  Bit-exact indices."""
     g, gr = setup["g"], setup["gr"]
-    sel = np.arange(3, len(g["sig"]), len(g["sig"]) // 12)[:12]
+    sel = np.arange(3, len(g["sig"]), len(g["sig"]) // 8)[:8]
     sig = g["sig"][sel]
     DicLR = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, gr["alpha_spline"], 1000.0)
     outs = []
@@ -202,11 +206,11 @@ def test_fa_stage_kernels_against_reference(setup):
         assert np.allclose(out["fsol_sum"], other["fsol_sum"], rtol=1e-13, atol=0)   # summation order follows the warps
     a91 = np.linspace(90.0, 180.0, 91)
     D91 = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, a91, 1000.0)
-    sig_b = sig[:8].copy()
+    sig_b = sig[:5].copy()
     sig_b[3] = 0.0                                                  # empty voxel: index 0, status skipped
     out = emu.fa_fit(sig_b, D91, a91)
-    FA, idx, KM, F = O.fitting_slice_FA_brute_force((sig_b.sum(1) > 0).astype(float), sig_b, 8, D91, a91)
-    assert list(out["status"]) == [0, 0, 0, 1, 0, 0, 0, 0]
+    FA, idx, KM, F = O.fitting_slice_FA_brute_force((sig_b.sum(1) > 0).astype(float), sig_b, 5, D91, a91)
+    assert list(out["status"]) == [0, 0, 0, 1, 0]
     assert np.array_equal(out["fa_index"], idx.astype(np.int32)) and np.array_equal(out["fa_deg"], FA)
     assert np.max(np.abs(out["km"] - KM)) < 1e-8 * KM.max()
     assert np.max(np.abs(out["fsol_sum"] - F)) < 1e-6 * np.abs(F).max()
@@ -253,7 +257,7 @@ def test_whole_chain_against_the_reference_orchestrator_run():
     """Every kernel of the path in sequence, emulated: EPG dictionary -> NESMA -> Gaussian smoothing -> FA spline search ->
     X2-I fit + maps, against the output volumes of the UNMODIFIED reference's motor_recon_met2 run end to end
     (tests/golden/pipeline_nesma_x2.npz, oracle/make_golden_pipeline.py; denoise=NESMA, FA_smooth=yes).  The two
-    preprocessing stages run on the whole 14x12x10 volume, the fits on every 13th masked voxel."""
+    preprocessing stages run on the whole 14x12x10 volume, the fits on every 19th masked voxel."""
     g = dict(np.load(os.path.join(os.path.dirname(__file__), "golden", "pipeline_nesma_x2.npz")))
     mask = g["mask"].astype(np.int64)
     data = g["data"] * mask[..., None]
@@ -265,8 +269,8 @@ def test_whole_chain_against_the_reference_orchestrator_run():
     Dic, DicLR = np.transpose(dic, (1, 2, 0)), np.transpose(dic_lr, (1, 2, 0))
     den = emu.nesma_filter(data, mask.astype(np.int32))                        # Step 1 (motor...:305-333)
     smooth = emu.gaussian_smooth(den, 2.0)                                     # FA-stage copy (motor...:336-346)
-    flat = np.nonzero(mask.reshape(-1) > 0)[0][::13]
-    assert len(flat) >= 40
+    flat = np.nonzero(mask.reshape(-1) > 0)[0][::19]
+    assert len(flat) >= 30
     sig = den.reshape(-1, 32)[flat]
     sig_fa = smooth.reshape(-1, 32)[flat]
     fa = emu.fa_fit(sig_fa, Dic, gr["alpha_values"], DicLR, gr["alpha_spline"])          # Step 2
