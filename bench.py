@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default=None, help="override volume, e.g. 16,16,4 (debug only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--t2-flags", type=int, default=0,
+                    help="extra MET2_T2_FLAG_* bits for every T2 fit (A/B runs only, e.g. 64 = experimental echo-space "
+                         "kernel); the default 0 is the measured configuration")
     return ap.parse_args()
 
 
@@ -209,7 +212,7 @@ def run_ours(args):
     sig_host = torch.as_tensor(ph["data"].reshape(-1, N_ECHOES)).pin_memory()
     V = sig_host.shape[0]
     plan = batched.Met2Plan(N_ECHOES, TAU, TR, reg_method=REG_METHOD, reg_matrix=REG_MATRIX, FA_method=FA_METHOD,
-                            device=dev)
+                            device=dev, t2_flags=args.t2_flags)
     sig = sig_host.to(dev)
     fa_out = t2_out = None
 
@@ -309,7 +312,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "voxels_per_gpu": V, "l2": "inputs (142 MB) + outputs (0.44 GB) per "
+                "config": {"workload": WORKLOAD, "t2_flags": args.t2_flags, "voxels_per_gpu": V, "l2": "inputs (142 MB) + outputs (0.44 GB) per "
                            "step exceed the 126 MB L2; no explicit flush", "stage_ms": {"fa": fa_ms, "t2": t2_ms}},
                 "clocks": clocks,
                 "e2e": {"value": world * V / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
