@@ -307,3 +307,37 @@ def test_echo_space_fixed_lambda_kernel(matrix, npc):
         assert np.max(np.abs(out["fsol"][i] - f_ref)) < 1e-8 * np.abs(f_ref).max()
         assert np.max(np.abs(out["est_signal"][i] - s_ref)) < 1e-8 * np.abs(s_ref).max()
         assert abs(out["maps"][i, 0] - f_ref[gr["ind_m"]].sum() / f_ref.sum()) < 1e-8
+
+
+def test_gcv_objective_and_grid_modes(setup):
+    """The GCV kernel's objective (algorithms.py:285-296, quirks included) at fixed lambdas (MET2_T2_FLAG_GCV_EVAL) and
+    its lambda-grid mode (MET2_T2_FLAG_GCV_GRID, BASELINE.json configs[2]) against the oracle.  The criterion sits on
+    a truncated pseudo-inverse whose cut-off is at rounding level for some eigenvalues, so the
+    objective is compared statistically like in the GPU test."""
+    g, gr = setup["g"], setup["gr"]
+    sel, sig, fa = _pick(g, 8, offset=13)
+    Dv = [np.ascontiguousarray(setup["Dic"][:, :, a]) for a in fa]
+    d = []
+    for lam in (1e-3, 0.1, 3.8197):
+        out = _run("shuffle", sig, fa, setup["Dic"], gr["L"], gr["T2s"], "GCV", flags=8, lambda_fixed=lam)
+        assert not out["status"].any()
+        for i in range(len(sel)):
+            M = sig[i] / sig[i, 0]
+            with np.errstate(all="ignore"):
+                ref = O.obj_nnls_gcv(lam, Dv[i], gr["L"], np.concatenate((M, np.zeros(60))), 32, np.eye(32))
+            d.append(abs(out["reg"][i] - ref))
+    d = np.array(d)
+    assert np.median(d) < 1e-4 and (d < 1e-2).mean() > 0.9, (np.median(d), d.max())
+    lams = np.ascontiguousarray(gr["lambda_reg"][1:])
+    out = _run("forward", sig, fa, setup["Dic"], gr["L"], gr["T2s"], "GCV", flags=32, lambdas=lams)
+    assert not out["status"].any()
+    gi = np.array([int(np.argmin(np.abs(np.log(lams) - np.log(l)))) for l in out["reg"]])
+    assert np.allclose(lams[gi], out["reg"], rtol=1e-14)                      # a grid value was returned
+    gi_ref = np.zeros(len(sel), dtype=int)
+    for i in range(len(sel)):
+        fr, reg, costs = O.nnls_gcv_grid(Dv[i], sig[i] / sig[i, 0], gr["L"], lams)
+        gi_ref[i] = int(np.argmin(costs))
+        if gi_ref[i] == gi[i]:
+            assert np.array_equal(out["fsol"][i] > 0, fr > 0)
+            assert np.max(np.abs(out["fsol"][i] - fr * sig[i, 0])) < 1e-6 * np.abs(fr * sig[i, 0]).max()
+    assert (np.abs(gi - gi_ref) <= 1).mean() >= 0.75, (gi, gi_ref)
