@@ -176,15 +176,15 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
         cfg.brent_lo, cfg.brent_hi, cfg.maxfun = 1e-8, 2.0, 200
         with np.errstate(divide="ignore"):
             cfg.log_det_L = float(np.log(np.linalg.det(np.asarray(L, dtype=np.float64))))
-    out = dict(fsol=np.zeros((V, n)), est_signal=np.zeros((V, m)), reg=np.zeros(V), maps=np.zeros((V, 6)),
-               status=np.zeros(V, dtype=np.uint32))
+    out = dict(fsol=np.full((V, n), np.nan), est_signal=np.full((V, m), np.nan), reg=np.full(V, np.nan),
+               maps=np.full((V, 6), np.nan), status=np.full(V, 0xFFFFFFFF, dtype=np.uint32))   # every output must be written
     old = os.environ.get("MET2_T2_WARPS")
     os.environ["MET2_T2_WARPS"] = str(warps)
     try:
         nbytes = lib().met2_t2_workspace_bytes(V, ctypes.byref(cfg))
         if nbytes < 0:
             raise RuntimeError("met2_t2_workspace_bytes: " + lib().met2_last_error().decode())
-        ws = np.zeros(int(nbytes) + 512, dtype=np.uint8)
+        ws = np.full(int(nbytes) + 512, 0xA5, dtype=np.uint8)   # poisoned like a fresh torch.empty
         fn = lib().met2_t2_fit
         fn.argtypes = [P, P, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [P] * 14
         _check(fn(_ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(kband),
@@ -216,12 +216,12 @@ def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None):
         knots = np.ascontiguousarray(alpha_values_spline, dtype=np.float64)
     cfg = FaCfg(method=1 if spline else 0, nTE=m, nT2=n, nA=nA, nKnots=(len(knots) if spline else 0), final_solve=1,
                 brent_lo=90.0, brent_hi=180.0, brent_xatol=1e-5, brent_maxfun=500, reserved=0)
-    out = dict(fa_index=np.zeros(V, dtype=np.int32), fa_deg=np.zeros(V), km=np.zeros(V), fsol_sum=np.zeros(n),
-               status=np.zeros(V, dtype=np.uint32))
+    out = dict(fa_index=np.full(V, -7, dtype=np.int32), fa_deg=np.full(V, np.nan), km=np.full(V, np.nan),
+               fsol_sum=np.full(n, np.nan), status=np.full(V, 0xFFFFFFFF, dtype=np.uint32))    # every output must be written
     nbytes = lib().met2_fa_workspace_bytes(V, ctypes.byref(cfg))
     if nbytes < 0:
         raise RuntimeError("met2_fa_workspace_bytes: " + lib().met2_last_error().decode())
-    ws = np.zeros(int(nbytes) + 512, dtype=np.uint8)
+    ws = np.full(int(nbytes) + 512, 0xA5, dtype=np.uint8)   # poisoned like a fresh torch.empty
     fn = lib().met2_fa_fit
     fn.argtypes = [P, ctypes.c_int64, ctypes.POINTER(FaCfg)] + [P] * 15
     _check(fn(_ptr(sig), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(alphas), _ptr(dic_s), _ptr(dicT_s),
@@ -267,7 +267,7 @@ def segment_means(sig, fa_index, label, nSeg, dic):
     V, m = sig.shape
     nA, _, n = dic.shape
     ms, mk, cnt = np.zeros((nSeg, m)), np.zeros((nSeg, m, n)), np.zeros(nSeg, dtype=np.int32)
-    ws = np.zeros(int(lib().met2_segment_workspace_bytes(nSeg, nA)) + 512, dtype=np.uint8)
+    ws = np.full(int(lib().met2_segment_workspace_bytes(nSeg, nA)) + 512, 0xA5, dtype=np.uint8)
     fn = lib().met2_segment_means
     fn.argtypes = [P, P, P, ctypes.c_int64] + [ctypes.c_int] * 4 + [P] * 6
     _check(fn(_ptr(sig), _ptr(fa_index), _ptr(label), V, m, n, nA, nSeg, _ptr(dic), _ptr(ms), _ptr(mk), _ptr(cnt),

@@ -292,8 +292,12 @@ struct Launch {
         const int nthreads = (int)(block.x * block.y * block.z);
         g_shared.size = (long)(smem / sizeof(double));
         ++n_launches;
-        for (unsigned b = 0; b < grid.x; ++b)
+        for (unsigned b = 0; b < grid.x; ++b) {
+            // a block starts with its dynamic shared memory POISONED (NaN): a kernel that reads a shared location
+            // before writing it shows up as NaN / wrong outputs instead of silently using the previous block's data
+            for (long i = 0; i < g_shared.size; ++i) g_shared.data[i] = NAN;
             n_collectives += run_block(nthreads, (int)b, (int)grid.x, [&]() { kern(args...); }, block);
+        }
     }
 };
 template <class... P>
