@@ -94,6 +94,31 @@ def _check(rc, what):
         raise RuntimeError("%s failed (%d): %s" % (what, rc, lib().met2_last_error().decode()))
 
 
+_GUARD = 512      # bytes of canary either side of every output / workspace array
+
+
+class _Guarded:
+    """Output arrays carved out of byte buffers with canaries either side: a kernel writing just outside one of its
+    output or workspace arrays is caught by `check()` after the call."""
+
+    def __init__(self):
+        self.bufs = []
+
+    def array(self, shape, dtype, fill):
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        raw = np.full(n + 2 * _GUARD, 0xC3, dtype=np.uint8)
+        view = raw[_GUARD:_GUARD + n].view(dtype).reshape(shape)
+        view[...] = fill
+        self.bufs.append((raw, n))
+        return view
+
+    def check(self, what):
+        for raw, n in self.bufs:
+            if not (np.all(raw[:_GUARD] == 0xC3) and np.all(raw[_GUARD + n:] == 0xC3)):
+                raise AssertionError("%s wrote outside one of its output / workspace arrays" % what)
+
+
 def counters(reset_only=False):
     """Work since the last call: per-THREAD counts of fma(), shared-memory accesses, __syncwarp, warp collectives
     (divide by 32 for warp level) and the number of kernel launches."""
@@ -176,20 +201,23 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
         cfg.brent_lo, cfg.brent_hi, cfg.maxfun = 1e-8, 2.0, 200
         with np.errstate(divide="ignore"):
             cfg.log_det_L = float(np.log(np.linalg.det(np.asarray(L, dtype=np.float64))))
-    out = dict(fsol=np.full((V, n), np.nan), est_signal=np.full((V, m), np.nan), reg=np.full(V, np.nan),
-               maps=np.full((V, 6), np.nan), status=np.full(V, 0xFFFFFFFF, dtype=np.uint32))   # every output must be written
+    gd = _Guarded()      # poisoned, canary-guarded outputs: every element must be written, nothing beyond
+    out = dict(fsol=gd.array((V, n), np.float64, np.nan), est_signal=gd.array((V, m), np.float64, np.nan),
+               reg=gd.array(V, np.float64, np.nan), maps=gd.array((V, 6), np.float64, np.nan),
+               status=gd.array(V, np.uint32, 0xFFFFFFFF))
     old = os.environ.get("MET2_T2_WARPS")
     os.environ["MET2_T2_WARPS"] = str(warps)
     try:
         nbytes = lib().met2_t2_workspace_bytes(V, ctypes.byref(cfg))
         if nbytes < 0:
             raise RuntimeError("met2_t2_workspace_bytes: " + lib().met2_last_error().decode())
-        ws = np.full(int(nbytes) + 512, 0xA5, dtype=np.uint8)   # poisoned like a fresh torch.empty
+        ws = gd.array(int(nbytes), np.uint8, 0xA5)               # poisoned like a fresh torch.empty
         fn = lib().met2_t2_fit
         fn.argtypes = [P, P, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [P] * 14
         _check(fn(_ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(kband),
                   _ptr(lam), _ptr(logT2), _ptr(comp), _ptr(out["fsol"]), _ptr(out["est_signal"]), _ptr(out["reg"]),
                   _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), None), "met2_t2_fit")
+        gd.check("met2_t2_fit")
     finally:
         if old is None:
             del os.environ["MET2_T2_WARPS"]
@@ -216,17 +244,19 @@ def fa_fit(sig, Dic_3D, alpha_values, Dic_3D_LR=None, alpha_values_spline=None):
         knots = np.ascontiguousarray(alpha_values_spline, dtype=np.float64)
     cfg = FaCfg(method=1 if spline else 0, nTE=m, nT2=n, nA=nA, nKnots=(len(knots) if spline else 0), final_solve=1,
                 brent_lo=90.0, brent_hi=180.0, brent_xatol=1e-5, brent_maxfun=500, reserved=0)
-    out = dict(fa_index=np.full(V, -7, dtype=np.int32), fa_deg=np.full(V, np.nan), km=np.full(V, np.nan),
-               fsol_sum=np.full(n, np.nan), status=np.full(V, 0xFFFFFFFF, dtype=np.uint32))    # every output must be written
+    gd = _Guarded()
+    out = dict(fa_index=gd.array(V, np.int32, -7), fa_deg=gd.array(V, np.float64, np.nan), km=gd.array(V, np.float64, np.nan),
+               fsol_sum=gd.array(n, np.float64, np.nan), status=gd.array(V, np.uint32, 0xFFFFFFFF))
     nbytes = lib().met2_fa_workspace_bytes(V, ctypes.byref(cfg))
     if nbytes < 0:
         raise RuntimeError("met2_fa_workspace_bytes: " + lib().met2_last_error().decode())
-    ws = np.full(int(nbytes) + 512, 0xA5, dtype=np.uint8)   # poisoned like a fresh torch.empty
+    ws = gd.array(int(nbytes), np.uint8, 0xA5)
     fn = lib().met2_fa_fit
     fn.argtypes = [P, ctypes.c_int64, ctypes.POINTER(FaCfg)] + [P] * 15
     _check(fn(_ptr(sig), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(alphas), _ptr(dic_s), _ptr(dicT_s),
               _ptr(G_s), _ptr(knots), _ptr(out["fa_index"]), _ptr(out["fa_deg"]), _ptr(out["km"]), _ptr(out["fsol_sum"]),
               _ptr(out["status"]), _ptr(ws), None), "met2_fa_fit")
+    gd.check("met2_fa_fit")
     out["counters"] = counters()
     return out
 
