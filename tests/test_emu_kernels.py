@@ -341,3 +341,32 @@ def test_gcv_objective_and_grid_modes(setup):
             assert np.array_equal(out["fsol"][i] > 0, fr > 0)
             assert np.max(np.abs(out["fsol"][i] - fr * sig[i, 0])) < 1e-6 * np.abs(fr * sig[i, 0]).max()
     assert (np.abs(gi - gi_ref) <= 1).mean() >= 0.75, (gi, gi_ref)
+
+
+def test_odd_sizes_and_tile_scheduling():
+    """Sizes off the beaten path through the real host code: 24 echoes, 50 bins (neither a multiple of 32 nor even rows
+    of the Gram table), three flip angles, 301 voxels (ragged last tile, tiles of 32 forced through MET2_T2_TILE so that
+    one flip angle spans several tiles), two emulated SMs pulling tiles from the shared counter."""
+    emu.build()
+    gr, Dic, sig, fa = _synthetic(50, 24, 301, "T2SPARC", "L1", seed=9)
+    fa = (fa % 3).astype(np.int32)
+    Dic = np.ascontiguousarray(Dic[:, :, :3])
+    old = os.environ.get("MET2_T2_TILE")
+    os.environ["MET2_T2_TILE"] = "32"
+    try:
+        outs = {m: emu.t2_fit(sig, fa, Dic, gr["L"], gr["T2s"], m, warps=3) for m in ("NNLS", "T2SPARC")}
+    finally:
+        if old is None:
+            del os.environ["MET2_T2_TILE"]
+        else:
+            os.environ["MET2_T2_TILE"] = old
+    for method, out in outs.items():
+        assert not out["status"].any()
+        for i in range(0, len(sig), 7):
+            f_ref, s_ref, reg_ref = O.t2_fit_voxel(sig[i], np.ascontiguousarray(Dic[:, :, fa[i]]), method, gr["L"],
+                                                   gr["lambda_reg"])
+            assert np.array_equal(out["fsol"][i] > 0, f_ref > 0), (method, i)
+            assert np.max(np.abs(out["fsol"][i] - f_ref)) < 1e-6 * np.abs(f_ref).max(), (method, i)
+            assert np.max(np.abs(out["est_signal"][i] - s_ref)) < 1e-6 * np.abs(s_ref).max()
+        # every voxel was fitted exactly once: no voxel left at its poison value, TWC > 0 everywhere
+        assert np.isfinite(out["fsol"]).all() and (out["maps"][:, 5] > 0).all()
