@@ -29,7 +29,15 @@ namespace met2 {
 
 #ifdef MET2_HOST_EMU
 static simt::Shared& S = simt::g_shared;
+// decision trace of the active-set solver for the CPU emulation build (MET2_EMU_TRACE=1); compiles to nothing in CUDA
+#define MET2_TRACE(lane, ...)                                              \
+    do {                                                                   \
+        if ((lane) == 0 && getenv("MET2_EMU_TRACE")) fprintf(stderr, __VA_ARGS__); \
+    } while (0)
 #else
+#define MET2_TRACE(lane, ...) \
+    do {                      \
+    } while (0)
 extern __shared__ __align__(16) double S[];   // the dynamic shared memory of every met2 kernel
 #endif
 
@@ -641,6 +649,8 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         // nnls.f: reject if the column is numerically dependent on P (unorm + |a_new|*0.01 == unorm, i.e.
         // rho < ~1e-14 unorm) or if its new coefficient ("ztest") is not positive
         const bool ok = (rho2 > 0.0) && (rho2 > 1.2e-28 * s1) && (!need_positive || ynew > 0.0);
+        MET2_TRACE(lane, "  append j=%d p=%d gjj=%.17g rho2=%.17g ynew=%.17g -> %s\n", j, p, gjj, rho2, ynew,
+                   ok ? "accepted" : "rejected");
         __syncwarp();
         if (!ok) return false;
         double acc[NS];
@@ -933,6 +943,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             int k = jb;
             while (true) {
                 int colk = SI(W.ix, k);
+                MET2_TRACE(lane, "  remove col=%d (position %d of %d) alpha=%.17g\n", colk, k, p, alpha);
                 if (colk / NS == lane) inP &= ~(1u << (colk % NS));
                 if (lane == 0) S[W.xc + colk] = 0.0;
                 __syncwarp();
