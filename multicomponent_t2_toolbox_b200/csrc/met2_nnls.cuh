@@ -592,7 +592,15 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
 template <int NS, bool GSH>
 __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
                                          bool reg, double lam, int n, int mrows, int lane, int& status, int p0 = 0,
-                                         bool t_ready = false) {
+                                         bool t_ready = false
+#ifdef MET2_DSPACE_RESCUE
+                                         // EXPERIMENT (not compiled into libmet2.so; DESIGN.md §5, 96-bin finding): the
+                                         // transposed dictionary [n][mrows] and the signal offset, for the D-space
+                                         // evaluation of a nearly dependent candidate's rho^2
+                                         ,
+                                         const double* __restrict__ DtR = nullptr, int oMR = 0
+#endif
+) {
     const int itmax = 3 * n;
     auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * ldg + c] : __ldg(Gg + r * ldg + c); };
     const int col0 = NS * lane;
@@ -642,10 +650,42 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             }
         }
         warp_sum2(s1, s2);
+#ifndef MET2_DSPACE_RESCUE
         const double rho2 = gjj - s1;
         const double cj = S[W.cc + j];
         const double rinv = rsqrt_fast(rho2);
         const double ynew = (cj - s2) * rinv;
+#else
+        double rho2 = gjj - s1;
+        const double cj = S[W.cc + j];
+        double rinv = rsqrt_fast(rho2);
+        double ynew = (cj - s2) * rinv;
+        if (!reg && DtR && p > 0 && rho2 < 1e-10 * gjj) {
+            // rho^2 = G_jj - r.r is below the rounding of its terms: take the candidate's orthogonal residual in D-space,
+            // q = d_j - D_P a with a = T r, rho^2 = q.q, y_new = (q.b) / rho  (q is orthogonal to the columns of P)
+            __syncwarp();
+            double a[NS];
+            tmul<NS>(W.T, W.rs, p, lane, a);
+#pragma unroll
+            for (int t = 0; t < NS; ++t) {
+                int k = lane + 32 * t;
+                if (k < p) S[W.gs + k] = a[t];
+            }
+            __syncwarp();
+            double qq = 0.0, qb = 0.0;
+            for (int e = lane; e < mrows; e += 32) {
+                double qe = __ldg(DtR + j * mrows + e);
+                for (int k = 0; k < p; ++k) qe = fma(-S[W.gs + k], __ldg(DtR + SI(W.ix, k) * mrows + e), qe);
+                qq = fma(qe, qe, qq);
+                qb = fma(qe, S[oMR + e], qb);
+            }
+            warp_sum2(qq, qb);
+            MET2_TRACE(lane, "  rescue j=%d: Gram rho2=%.3e -> D-space rho2=%.17g, y_new numerator %.17g\n", j, rho2, qq, qb);
+            rho2 = qq;
+            rinv = rsqrt_fast(rho2);
+            ynew = qb * rinv;
+        }
+#endif
         // nnls.f: reject if the column is numerically dependent on P (unorm + |a_new|*0.01 == unorm, i.e.
         // rho < ~1e-14 unorm) or if its new coefficient ("ztest") is not positive
         const bool ok = (rho2 > 0.0) && (rho2 > 1.2e-28 * s1) && (!need_positive || ynew > 0.0);

@@ -690,7 +690,12 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
-                                            warm ? p : 0, t_ready);
+                                            warm ? p : 0, t_ready
+#ifdef MET2_DSPACE_RESCUE
+                                            ,
+                                            Dt, oM
+#endif
+                    );
                     t_ready = false;
                     if (method == MET2_REG_NNLS && nst == 0 && p > 0) refine_plain<NS, ME>(W, Dt, oM, oLx, m, p, lane);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);

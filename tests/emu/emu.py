@@ -51,7 +51,7 @@ def build(force=False):
         return LIB
     os.makedirs(BUILD, exist_ok=True)
     flags = ["-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-DMET2_HOST_EMU=1", "-x", "c++", "-I", HERE, "-I", CSRC,
-             "-I", os.path.join(ROOT, "include")]
+             "-I", os.path.join(ROOT, "include")] + os.environ.get("EMU_EXTRA_DEFS", "").split()   # experiments only
 
     def compile_one(src):
         obj = os.path.join(BUILD, os.path.basename(src) + ".o")
