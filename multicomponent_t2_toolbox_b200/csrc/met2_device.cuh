@@ -268,29 +268,38 @@ __device__ __forceinline__ double fit_and_sse(const Slots<NS>& W, const double* 
     return warp_sum(s);
 }
 
-// One step of iterative refinement of a PLAIN (unregularised) least-squares solution on its final positive set, with
-// the residual evaluated in D-space ("corrected semi-normal equations"): r = M - D_P x, x += T T^T (D_P^T r).
+// One step of iterative refinement of a least-squares solution on its final positive set, with the residual evaluated
+// in D-space ("corrected semi-normal equations"):  r = M - D_P x,  g = D_P^T r - lam (K x)_P,  x += T T^T g.
 // The Gram-domain solve squares the condition number of D_P (up to ~1e5 for 4-6 EPG columns), which leaves ~1e-6
-// relative error in the worst voxels — the size of the parity tolerance; the reference's QR-based Lawson-Hanson does not
-// have that loss.  One refinement step brings the solution to the D-space accuracy.  The step is skipped if it would
-// make a coefficient non-positive (the active set is the solver's decision, not the refinement's).
-// oR: scratch of m doubles in shared memory.
+// (plain) / ~1e-9 (Tikhonov) relative error in the worst voxels; the reference's QR-based Lawson-Hanson does not have
+// that loss.  One refinement step brings the solution to the D-space accuracy (~1e-12).  Used for plain NNLS outputs
+// (the 1e-6 spectrum tolerance had no margin without it) and for every BayesReg evaluation: the evidence depends on f
+// to first order (sum log(1 + erf(U f / sqrt 2))) and its curve is flat enough for a 1e-9 error of f to move Brent's
+// lambda by more than 1e-6 in a quarter of the config-4 voxels.  The step is skipped if it would make a
+// coefficient non-positive (the active set is the solver's decision, not the refinement's).
+// reg: Tikhonov term lam * K with K in 5-band form at S[oKb + d*n + c] = K[c+d-2][c]; S[W.xc..] must hold x in column
+// space (zeros outside P), as nnls_gram leaves it.  Scratch: S[W.rs..] (m <= 32 NS doubles), S[W.gs..].
 template <int NS, int ME>
-__device__ __forceinline__ void refine_plain(const Slots<NS>& W, const double* __restrict__ Dt, int oM, int oR, int m,
-                                             int p, int lane) {
+__device__ __forceinline__ void refine_on_support(const Slots<NS>& W, const double* __restrict__ Dt, int oM, int m, int p,
+                                                  int lane, bool reg, double lam, int oKb, int n) {
+    static_assert(ME <= NS, "the residual is staged in a position-space slot");
     double fit[ME];
     (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
+    const int oR = W.rs;
 #pragma unroll
     for (int u = 0; u < ME; ++u) {
         const int e = lane + 32 * u;
         if (e < m) S[oR + e] = S[oM + e] - fit[u];
     }
     __syncwarp();
+    double gv[NS];
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
         const int i = lane + 32 * t;
+        gv[t] = 0.0;
         if (i < p) {
-            const double* d = Dt + SI(W.ix, i) * m;
+            const int col = SI(W.ix, i);
+            const double* d = Dt + col * m;
             double a0 = 0.0, a1 = 0.0;
             int e = 0;
 #pragma unroll 1
@@ -299,8 +308,23 @@ __device__ __forceinline__ void refine_plain(const Slots<NS>& W, const double* _
                 a1 = fma(__ldg(d + e + 1), S[oR + e + 1], a1);
             }
             if (e < m) a0 = fma(__ldg(d + e), S[oR + e], a0);
-            S[W.gs + i] = a0 + a1;
+            double gi = a0 + a1;
+            if (reg) {
+                double kx = 0.0;
+#pragma unroll
+                for (int dd = 0; dd < 5; ++dd) {
+                    const int c2 = col + dd - 2;
+                    if (c2 >= 0 && c2 < n) kx = fma(S[oKb + dd * n + col], S[W.xc + c2], kx);
+                }
+                gi = fma(-lam, kx, gi);
+            }
+            gv[t] = gi;
         }
+    }
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        const int i = lane + 32 * t;
+        if (i < p) S[W.gs + i] = gv[t];
     }
     __syncwarp();
     double y[NS], dz[NS];

@@ -280,6 +280,76 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 #endif
 }
 
+// Symmetric Gaussian elimination on the augmented 8 x 8 block [S | I] held as accumulator fragments (s0, s1) =
+// S[g][2q], S[g][2q + 1] (g = lane / 4, q = lane % 4): afterwards the 8 x 16 array FR = S[W.gs .. W.gs + 128) (row stride
+// 16; spans gs and, for NS = 2, rs) holds D L1^T in its left half (S = L1 D L1^T, pivots d_r = FR[17 r]) and M = L1^-1 in
+// its right half, so that chol(S) = R = D^1/2 L1^T (R[r][c] = FR[16 r + c] / sqrt(d_r), c >= r) and
+// R^-1[r][c] = M[c][r] / sqrt(d_c) = FR[16 c + 8 + r] / sqrt(d_c) for r < c, 1 / sqrt(d_c) on the diagonal.
+// The 36 upper-triangular entries of the left half and the 28 strictly-lower entries of M are exactly two per lane and
+// stay in REGISTERS; a row is published to FR once, when it becomes the pivot row.  One __syncwarp and one fast
+// reciprocal per step on the dependency chain.  nv = live rows (the rest are virtual identity rows of a partial block).
+// (First version: an 8-step Cholesky with three barriers per step plus a serial triangular inverse on 8 lanes, ~20 % of
+// the kernel's stall samples in profiles/r01_t2_fit_v8_ncu_summary.txt; second: the same elimination with every entry
+// updated in shared memory, 16 % of the executed instructions in the v11 capture.)
+template <int NS>
+__device__ __forceinline__ void ldl_8x8(const Slots<NS>& W, double s0, double s1, int nv, int lane, bool& ok) {
+    const int g = lane >> 2, q = lane & 3;
+    const int oFR = W.gs;
+    S[oFR + g * 16 + 2 * q] = s0;
+    S[oFR + g * 16 + 2 * q + 1] = s1;
+    S[oFR + g * 16 + 8 + 2 * q] = (2 * q == g) ? 1.0 : 0.0;
+    S[oFR + g * 16 + 8 + 2 * q + 1] = (2 * q + 1 == g) ? 1.0 : 0.0;
+    __syncwarp();
+    // entry e = lane + 32 s: e < 36 -> (r, c) of the upper triangle, row-major; e >= 36 -> (r, 8 + c') with c' < r
+    int er[2], ec[2];
+    double ev[2];
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int e = lane + 32 * sl;
+        int rr, cc;
+        if (e < 36) {
+            rr = 0;
+            int rem = e;
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+                if (rem >= 8 - rr) {
+                    rem -= 8 - rr;
+                    ++rr;
+                }
+            cc = rr + rem;
+        } else {
+            const int f = e - 36;
+            rr = 1;
+#pragma unroll
+            for (int t = 0; t < 6; ++t)
+                if (f >= (rr * (rr + 1)) / 2) ++rr;
+            cc = 8 + f - (rr * (rr - 1)) / 2;
+        }
+        er[sl] = rr;
+        ec[sl] = cc;
+        ev[sl] = S[oFR + rr * 16 + cc];
+    }
+#pragma unroll 1
+    for (int k = 0; k < nv - 1; ++k) {
+        const double d = S[oFR + k * 17];
+        if (!(d > 0.0)) ok = false;
+        const double inv = rcp_fast(d);
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+            if (er[sl] > k && (ec[sl] < 8 || ec[sl] - 8 <= k)) {
+                const double m = S[oFR + k * 16 + er[sl]] * inv;
+                ev[sl] = fma(-m, S[oFR + k * 16 + ec[sl]], ev[sl]);
+            }
+        }
+        // row k+1 is final now: publish it (this step only read row k, so one barrier per step is enough)
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl)
+            if (er[sl] == k + 1) S[oFR + er[sl] * 16 + ec[sl]] = ev[sl];
+        __syncwarp();
+    }
+    if (!(S[oFR + (nv - 1) * 17] > 0.0)) ok = false;
+}
+
 // Blocked rebuild of the inverse Cholesky factor T for a GIVEN positive set (warm start): A = (G + lam K)_PP = R^T R,
 // T = R^-1, processed in column blocks J of 8 with the 8x8x4 FP64 MMA:
 //     R_top = T_old^T A[P_old, J]           (tiles of 8 rows; staged where the new columns of T will live)
@@ -353,61 +423,9 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
         //      in shared memory, 16 % of the executed instructions in the v11 capture.)
         {
             const int oFR = W.gs;
-            S[oFR + g * 16 + 2 * q] = s0;
-            S[oFR + g * 16 + 2 * q + 1] = s1;
-            S[oFR + g * 16 + 8 + 2 * q] = (2 * q == g) ? 1.0 : 0.0;
-            S[oFR + g * 16 + 8 + 2 * q + 1] = (2 * q + 1 == g) ? 1.0 : 0.0;
-            __syncwarp();
-            // entry e = lane + 32 s: e < 36 -> (r, c) of the upper triangle, row-major; e >= 36 -> (r, 8 + c') with c' < r
-            int er[2], ec[2];
-            double ev[2];
-#pragma unroll
-            for (int sl = 0; sl < 2; ++sl) {
-                const int e = lane + 32 * sl;
-                int rr, cc;
-                if (e < 36) {
-                    rr = 0;
-                    int rem = e;
-#pragma unroll
-                    for (int t = 0; t < 7; ++t)
-                        if (rem >= 8 - rr) {
-                            rem -= 8 - rr;
-                            ++rr;
-                        }
-                    cc = rr + rem;
-                } else {
-                    const int f = e - 36;
-                    rr = 1;
-#pragma unroll
-                    for (int t = 0; t < 6; ++t)
-                        if (f >= (rr * (rr + 1)) / 2) ++rr;
-                    cc = 8 + f - (rr * (rr - 1)) / 2;
-                }
-                er[sl] = rr;
-                ec[sl] = cc;
-                ev[sl] = S[oFR + rr * 16 + cc];
-            }
             // rows beyond the set (virtual identity rows of a partial last block) need no elimination
             const int nv = (p - c0 < 8) ? (p - c0) : 8;
-#pragma unroll 1
-            for (int k = 0; k < nv - 1; ++k) {
-                const double d = S[oFR + k * 17];
-                if (!(d > 0.0)) ok = false;
-                const double inv = rcp_fast(d);
-#pragma unroll
-                for (int sl = 0; sl < 2; ++sl) {
-                    if (er[sl] > k && (ec[sl] < 8 || ec[sl] - 8 <= k)) {
-                        const double m = S[oFR + k * 16 + er[sl]] * inv;
-                        ev[sl] = fma(-m, S[oFR + k * 16 + ec[sl]], ev[sl]);
-                    }
-                }
-                // row k+1 is final now: publish it (this step only read row k, so one barrier per step is enough)
-#pragma unroll
-                for (int sl = 0; sl < 2; ++sl)
-                    if (er[sl] == k + 1) S[oFR + er[sl] * 16 + ec[sl]] = ev[sl];
-                __syncwarp();
-            }
-            if (!(S[oFR + (nv - 1) * 17] > 0.0)) ok = false;
+            ldl_8x8<NS>(W, s0, s1, nv, lane, ok);
             // T_JJ (row-major 8 x 8) -> S[W.rs ..]; FR overlaps rs, so gather into registers first
             const int c = lane & 7;
             const double ric = rsqrt_fast(S[oFR + c * 17]);
@@ -459,6 +477,118 @@ __device__ __forceinline__ bool rebuild_T_blocked(const Slots<NS>& W, AENT&& Aen
         for (int pass = 0; pass < 2; ++pass) {
             const int rr = pass * 4 + (lane >> 3), c = lane & 7;
             if (rr <= c && c0 + c < p) S[oT + tri(c0 + c) + c0 + rr] = S[W.rs + rr * 8 + c];
+        }
+        __syncwarp();
+    }
+    return ok;
+}
+
+// Blocked Cholesky factorisation A = U^T U of the n x n matrix Aent(r, c) (natural order, all n columns): U upper
+// triangular, packed column-major in the T region (U(k, j) at S[W.T + tri(j) + k], k <= j), by block rows of 8 on the
+// FP64 tensor cores (up-looking):
+//     W_IJ = A_IJ - sum_{K < I} U_KI^T U_KJ        (J >= I; DMMA 8x8x4, two block columns in flight)
+//     U_II = chol(W_II), Tinv = U_II^-1             (ldl_8x8: elimination on [W_II | I])
+//     U_IJ = Tinv^T W_IJ                            (J > I; W_IJ staged at U_IJ's own place)
+// This is the factor the BayesReg evidence needs (bayesian_interpolation.py:113-119: U = cholesky(A), log prod diag U,
+// U f): round 1 took it from the INVERSE factor (U f = T^T (A f), log det = -sum log T_kk), which costs 1.5x the
+// flops and loses sqrt(cond A) ~ 1e4 ulps in the small entries of U f — enough, on the flat evidence curve of
+// BayesReg + InvT2, to move Brent's lambda by more than the reference moves under a 1e-13 perturbation of its input
+// (DESIGN.md §5).  Rows / columns >= n of the last block are virtual identity rows.  Returns false if a pivot is not
+// positive.  Uses S[W.gs .. W.gs + 128) and S[W.rs .. W.rs + 64) as scratch.
+template <int NS, class AENT>
+__device__ __forceinline__ bool chol_upper_blocked(const Slots<NS>& W, AENT&& Aent, int n, int lane) {
+    const int oT = W.T;
+    const int g = lane >> 2, q = lane & 3;
+    const int nb = (n + 7) >> 3;
+    bool ok = true;
+#pragma unroll 1
+    for (int I = 0; I < nb; ++I) {
+        const int r0 = 8 * I;
+        const int rg = r0 + g;                      // accumulator row / column of U^T read as the A fragment
+        const bool rlive = rg < n;
+        const int colrg = oT + tri(rg);
+        // ---- diagonal block: W_II = A_II - sum_K U_KI^T U_KI, then U_II and Tinv = U_II^-1
+        {
+            const int ca = r0 + 2 * q, cb = ca + 1;
+            double s0 = (rlive && ca < n) ? Aent(rg, ca) : ((rg == ca) ? 1.0 : 0.0);
+            double s1 = (rlive && cb < n) ? Aent(rg, cb) : ((rg == cb) ? 1.0 : 0.0);
+#pragma unroll 1
+            for (int ks = 0; ks < 2 * I; ++ks) {
+                const double v = rlive ? S[colrg + 4 * ks + q] : 0.0;
+                dmma884(s0, s1, -v, v);
+            }
+            const int nv = (n - r0 < 8) ? (n - r0) : 8;
+            ldl_8x8<NS>(W, s0, s1, nv, lane, ok);
+            const int oFR = W.gs;
+            const int c = lane & 7;
+            const double ric = rsqrt_fast(S[oFR + c * 17]);
+            double tv[2], uv[2];
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int rr = pass * 4 + (lane >> 3);
+                tv[pass] = (rr < c) ? S[oFR + c * 16 + 8 + rr] * ric : ((rr == c) ? ric : 0.0);      // Tinv[rr][c]
+                uv[pass] = (rr <= c) ? S[oFR + rr * 16 + c] * rsqrt_fast(S[oFR + rr * 17]) : 0.0;     // U_II[rr][c]
+            }
+            __syncwarp();
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int rr = pass * 4 + (lane >> 3);
+                S[W.rs + rr * 8 + c] = tv[pass];
+                if (rr <= c && r0 + c < n) S[oT + tri(r0 + c) + r0 + rr] = uv[pass];
+            }
+            __syncwarp();
+        }
+        // ---- block row: U_IJ for J > I, two block columns at a time (independent accumulators hide the DMMA latency)
+        const double ti0 = S[W.rs + q * 8 + g], ti1 = S[W.rs + (4 + q) * 8 + g];   // A fragments of Tinv^T: Tinv[k][g]
+#pragma unroll 1
+        for (int J = I + 1; J < nb; J += 2) {
+            double d0[2], d1[2];
+            int colg[2], cola[2], colb[2];
+            bool glive[2], alive[2], blive[2];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c0 = 8 * (J + h);
+                const bool on = (J + h) < nb;
+                glive[h] = on && (c0 + g < n);
+                alive[h] = on && (c0 + 2 * q < n);
+                blive[h] = on && (c0 + 2 * q + 1 < n);
+                colg[h] = oT + tri(c0 + g);
+                cola[h] = oT + tri(c0 + 2 * q);
+                colb[h] = oT + tri(c0 + 2 * q + 1);
+                d0[h] = (rlive && alive[h]) ? Aent(rg, c0 + 2 * q) : 0.0;
+                d1[h] = (rlive && blive[h]) ? Aent(rg, c0 + 2 * q + 1) : 0.0;
+            }
+#pragma unroll 1
+            for (int ks = 0; ks < 2 * I; ++ks) {
+                const int kk = 4 * ks + q;
+                const double a = rlive ? -S[colrg + kk] : 0.0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double bf = glive[h] ? S[colg[h] + kk] : 0.0;
+                    dmma884(d0[h], d1[h], a, bf);
+                }
+            }
+            // stage W_IJ at U_IJ's own place (rows r0 .. r0 + 7 of the block's columns)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (rlive && alive[h]) S[cola[h] + rg] = d0[h];
+                if (rlive && blive[h]) S[colb[h] + rg] = d1[h];
+            }
+            __syncwarp();
+            double e0[2] = {0.0, 0.0}, e1[2] = {0.0, 0.0};
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double b0 = (glive[h] && r0 + q < n) ? S[colg[h] + r0 + q] : 0.0;
+                const double b1 = (glive[h] && r0 + 4 + q < n) ? S[colg[h] + r0 + 4 + q] : 0.0;
+                dmma884(e0[h], e1[h], ti0, b0);
+                dmma884(e0[h], e1[h], ti1, b1);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (rlive && alive[h]) S[cola[h] + rg] = e0[h];
+                if (rlive && blive[h]) S[colb[h] + rg] = e1[h];
+            }
         }
         __syncwarp();
     }
@@ -577,6 +707,37 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
     __syncwarp();
 }
 
+// D-space evaluation of a candidate column j that the Gram-domain test finds (nearly) dependent on the positive set:
+// the candidate's orthogonal residual q = d_j - D_P a with a = T r (r = T^T g_Pj is in S[W.rs..]), rho^2 = q.q and the
+// numerator of its entering coefficient q.b — m p FMAs, errors of `a` enter quadratically.  Plain NNLS only (lam = 0).
+// without it Lawson-Hanson stopped one exchange short in 1 of 1 500 voxels on the 96-bin grid
+// (rho^2 = G_jj - r.r = -1.2e-13 for a column SciPy's QR-based test accepts).  Leaves a in S[W.gs..].
+// Everything is passed and returned BY VALUE: a reference argument would force the caller's Slots / rho^2 / y_new into
+// local memory on the hot path (measured with the first, by-reference version: T2 stage +3.3 %, FA stage +3 %).
+template <int NS>
+__device__ __noinline__ double2 dspace_candidate(int oT, int oGs, int oRs, int oIx, const double* __restrict__ DtR,
+                                                 int oMR, int mrows, int j, int p, int lane) {
+    double a[NS];
+    tmul<NS>(oT, oRs, p, lane, a);
+#pragma unroll
+    for (int t = 0; t < NS; ++t) {
+        int k = lane + 32 * t;
+        if (k < p) S[oGs + k] = a[t];
+    }
+    __syncwarp();
+    double qq = 0.0, qb = 0.0;
+    for (int e = lane; e < mrows; e += 32) {
+        double qe = __ldg(DtR + j * mrows + e);
+        for (int k = 0; k < p; ++k) qe = fma(-S[oGs + k], __ldg(DtR + SI(oIx, k) * mrows + e), qe);
+        qq = fma(qe, qe, qq);
+        qb = fma(qe, S[oMR + e], qb);
+    }
+    warp_sum2(qq, qb);
+    MET2_TRACE(lane, "  rescue j=%d: D-space rho2=%.17g, y_new numerator %.17g\n", j, qq, qb);
+    __syncwarp();
+    return make_double2(qq, qb);
+}
+
 // Gram-domain Lawson-Hanson.  On entry S[W.cc + 0..n) holds c = A^T b (visible to the whole warp).
 // G: n x n row-major Gram matrix of the unregularised dictionary — in shared memory at offset oG (GSH) or in global
 // memory at Gg.  reg: add lam * K, K given in 5-band form at S[oKb + d*n + c] = K[c+d-2][c].
@@ -592,15 +753,10 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
 template <int NS, bool GSH>
 __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
                                          bool reg, double lam, int n, int mrows, int lane, int& status, int p0 = 0,
-                                         bool t_ready = false
-#ifdef MET2_DSPACE_RESCUE
-                                         // EXPERIMENT (not compiled into libmet2.so; DESIGN.md §5, 96-bin finding): the
-                                         // transposed dictionary [n][mrows] and the signal offset, for the D-space
-                                         // evaluation of a nearly dependent candidate's rho^2
-                                         ,
-                                         const double* __restrict__ DtR = nullptr, int oMR = 0
-#endif
-) {
+                                         bool t_ready = false,
+                                         // the transposed dictionary [n][mrows] (global) and the signal offset in S: the
+                                         // D-space evaluation of a nearly dependent candidate (dspace_candidate)
+                                         const double* __restrict__ DtR = nullptr, int oMR = 0) {
     const int itmax = 3 * n;
     auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * ldg + c] : __ldg(Gg + r * ldg + c); };
     const int col0 = NS * lane;
@@ -650,40 +806,19 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             }
         }
         warp_sum2(s1, s2);
-#ifndef MET2_DSPACE_RESCUE
-        const double rho2 = gjj - s1;
-        const double cj = S[W.cc + j];
-        const double rinv = rsqrt_fast(rho2);
-        const double ynew = (cj - s2) * rinv;
-#else
         double rho2 = gjj - s1;
         const double cj = S[W.cc + j];
         double rinv = rsqrt_fast(rho2);
         double ynew = (cj - s2) * rinv;
+#ifndef MET2_NO_DSPACE_RESCUE   // A/B timing switch only (libmet2_norescue.so); the product library always has the rescue
         if (!reg && DtR && p > 0 && rho2 < 1e-10 * gjj) {
-            // rho^2 = G_jj - r.r is below the rounding of its terms: take the candidate's orthogonal residual in D-space,
-            // q = d_j - D_P a with a = T r, rho^2 = q.q, y_new = (q.b) / rho  (q is orthogonal to the columns of P)
+            // rho^2 = G_jj - r.r is below the rounding of its terms (nearly collinear long-T2 columns of the 96/100-bin
+            // grids): the Gram form resolves rho^2/G_jj to ~1e-16, nnls.f accepts down to ~5e-27.  Rare, so out of line.
             __syncwarp();
-            double a[NS];
-            tmul<NS>(W.T, W.rs, p, lane, a);
-#pragma unroll
-            for (int t = 0; t < NS; ++t) {
-                int k = lane + 32 * t;
-                if (k < p) S[W.gs + k] = a[t];
-            }
-            __syncwarp();
-            double qq = 0.0, qb = 0.0;
-            for (int e = lane; e < mrows; e += 32) {
-                double qe = __ldg(DtR + j * mrows + e);
-                for (int k = 0; k < p; ++k) qe = fma(-S[W.gs + k], __ldg(DtR + SI(W.ix, k) * mrows + e), qe);
-                qq = fma(qe, qe, qq);
-                qb = fma(qe, S[oMR + e], qb);
-            }
-            warp_sum2(qq, qb);
-            MET2_TRACE(lane, "  rescue j=%d: Gram rho2=%.3e -> D-space rho2=%.17g, y_new numerator %.17g\n", j, rho2, qq, qb);
-            rho2 = qq;
+            const double2 qd = dspace_candidate<NS>(W.T, W.gs, W.rs, W.ix, DtR, oMR, mrows, j, p, lane);
+            rho2 = qd.x;
             rinv = rsqrt_fast(rho2);
-            ynew = qb * rinv;
+            ynew = qd.y * rinv;
         }
 #endif
         // nnls.f: reject if the column is numerically dependent on P (unorm + |a_new|*0.01 == unorm, i.e.

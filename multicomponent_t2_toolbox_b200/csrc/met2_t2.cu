@@ -91,7 +91,8 @@ static int t2_launch_full_factors(const T2Args& A, int ntab, const double* G, co
     cudaError_t e = cudaFuncSetAttribute(t2_full_factors_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_full_factors attr: %s", cudaGetErrorString(e));
     MET2_LAUNCH(ntab * A.cfg.nA, 32, smem, st, t2_full_factors_kernel<NS>)(G, kband, n, A.cfg.nA, A.cfg.brent_lo, A.cfg.brent_hi,
-                                                                     A.cfg.brent_xatol, A.cfg.maxfun, tfull, lam_tab);
+                                                                     A.cfg.brent_xatol, A.cfg.maxfun,
+                                                                     A.cfg.method == MET2_REG_BAYESREG ? 1 : 0, tfull, lam_tab);
     count_launch();
     return check_launch("t2_full_factors_kernel");
 }

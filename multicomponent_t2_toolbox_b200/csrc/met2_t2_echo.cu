@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                 // ---- plain NNLS in the Gram domain -> SSE (algorithms.py:213-214)
                 compute_c<2>(W, D, oM, m, n, lane);
                 int nst = 0;
-                int p = nnls_gram<2, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, 0, false);
+                int p = nnls_gram<2, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, 0, false, Dtg, oM);
                 double fit1[1];
                 const double SSE = fit_and_sse<2, 1>(W, Dtg, oM, m, p, lane, fit1);
                 if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;

@@ -37,7 +37,8 @@ struct T2Args {
     // shared full-set factor tables (X2 with MET2_T2_FLAG_FULL_START): the first T2_NTAB abscissae of bounded Brent do
     // not depend on the voxel, so the inverse Cholesky factor of the FULL column set, (G_a + lam_j K)^-1 = T T^T, is
     // built once per (flip angle, abscissa) by t2_full_factors_kernel and copied instead of being re-derived per voxel
-    const double* tfull;     // [ntab][nA][tri(nT2)], first entry NaN if not positive definite
+    const double* tfull;     // [ntab][nA][tri(nT2)], first entry NaN if not positive definite.  X2: inverse Cholesky
+                             // factors T; BayesReg: the Cholesky factors U themselves (evidence)
     const double* lam_tab;   // [ntab]
     int ntab;                // tables built
     int ntab_use;            // how many of them the NNLS full-set starts consult
@@ -116,25 +117,27 @@ __device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int 
 // column space (S[W.xc..]):  A = beta*B + (beta*x)*K, U = chol(A) (upper), and
 //   cost = beta*ED + beta*x*EW + log(prod diag U) - (n/2) log(pi/2) - sum log(1 + erf(U f / sqrt 2))
 //        + (m/2) log(2 pi) - (m/2) log(beta) + (n/2) log(pi) - (n/2) log(2 beta x) - log(det L).
-// The n x n INVERSE factor T = U^-1 is built in the warp's T region (free between NNLS solves) by the same blocked
-// FP64-tensor-core factorisation that warm starts use (rebuild_T_blocked); log det U = -sum log T_kk and
-// U f = T^T (A f), so U itself is never needed.
+// U itself (n x n, natural column order) is built in the warp's T region (free between NNLS solves) by the blocked
+// FP64-tensor-core Cholesky chol_upper_blocked; log det U = log prod U_kk and U f is one triangular mat-vec — the same
+// quantities, formed the same way, as the reference's.  (Round 1 used the inverse factor: U f = T^T (A f).  Together
+// with the ~1e-9 relative error of the Gram-domain NNLS solution that put 25 % of the config-4 voxels more than 1e-6
+// away from the reference's lambda, where the reference's own reproducibility under a 1e-13 perturbation is 5 %.)
 template <int NS>
 __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg, int oKb, int n, int m, int lane,
                                              double x, double beta, double sse, double nrm, double log_det_L,
-                                             unsigned& st, int p, const double* __restrict__ ttab) {
+                                             unsigned& st, const double* __restrict__ utab) {
     const int oT = W.T;
     const double bx = beta * x;
-    // T = U^-1 with A = beta*B + (beta*x)*K = U^T U, all n columns in natural order.  While Brent is still on its
-    // voxel-independent golden chain (the first T2_NTAB_BAYES abscissae, bracket wider than ~1e-2), the factor T0 of
-    // B + x K comes from the shared tables (ttab) and T = T0 / sqrt(beta); afterwards A is factored here, with beta
-    // inside the matrix like the reference's cholesky(beta*B + beta*x*K).  The two differ by rounding only, which is why
-    // the tables stop before the convergence phase: there Brent compares nearly equal evidences and a 1e-16 change of
-    // the objective can move lambda by 1e-3 relative (measured with 16 tables: 2 of 2 048 voxels; with 9: none).
+    // While Brent is still on its voxel-independent golden chain (the first T2_NTAB_BAYES abscissae, bracket wider than
+    // ~1e-2), the factor U0 of B + x K comes from the shared tables (utab) and U = sqrt(beta) U0; afterwards A is
+    // factored here, with beta inside the matrix like the reference's cholesky(beta*B + beta*x*K).  The two differ by
+    // rounding only, which is why the tables stop before the convergence phase: there Brent compares nearly equal
+    // evidences and a 1e-16 change of the objective can move lambda by 1e-3 relative (measured with 16 tables: 2 of
+    // 2 048 voxels; with 9: none).
     bool pd = true;
-    if (ttab) {
-        const double rsb = 1.0 / sqrt(beta);
-        for (int i = lane; i < tri(n); i += 32) S[oT + i] = __ldg(ttab + i) * rsb;
+    if (utab) {
+        const double sb = sqrt(beta);
+        for (int i = lane; i < tri(n); i += 32) S[oT + i] = __ldg(utab + i) * sb;
         __syncwarp();
     } else {
         auto Aent = [&](int r, int c) -> double {
@@ -143,46 +146,15 @@ __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg
             if (d >= 0 && d <= 4) a = a + bx * S[oKb + d * n + c];
             return a;
         };
-        pd = rebuild_T_blocked<NS>(W, Aent, n, lane);
+        pd = chol_upper_blocked<NS>(W, Aent, n, lane);
     }
     if (!pd) st |= MET2_ST_NOT_PD;
-    // det_U = prod(diag(U)) = prod 1 / T_kk  (np.prod order)
+    // det_U = prod(diag(U))  (np.prod order)
     double det_u = 1.0;
-    for (int k = 0; k < n; ++k) det_u *= 1.0 / S[oT + tri(k) + k];
-    // U f = U^-T (U^T U f) = T^T (A f);  v = A f in column space, f = S[W.xc ..] (support W.ix / W.xs, size p)
-    {
-        const int col0 = NS * lane;
-        double v[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) v[s] = 0.0;
-        if (col0 < n) {
-            for (int k = 0; k < p; ++k) {
-                const int r0 = oG + SI(W.ix, k) * ldg + col0;
-                const double xk = S[W.xs + k];
-                double g0[NS];
-                lds_vec<NS>(r0, g0);
-#pragma unroll
-                for (int s = 0; s < NS; ++s) v[s] = fma(xk, g0[s], v[s]);
-            }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int col = col0 + s;
-            if (col < n) {
-                double kf = 0.0;
-#pragma unroll
-                for (int d = 0; d < 5; ++d) {
-                    const int c2 = col + d - 2;
-                    if (c2 >= 0 && c2 < n) kf = fma(S[oKb + d * n + col], S[W.xc + c2], kf);
-                }
-                S[W.gs + col] = beta * v[s] + bx * kf;
-            }
-        }
-        __syncwarp();
-    }
+    for (int k = 0; k < n; ++k) det_u *= S[oT + tri(k) + k];
+    // U f: row k of U times f (natural order; f = S[W.xc ..], zeros outside the support)
     double uf[NS];
-    tmul_transposed<NS>(oT, W.gs, n, lane, uf);
+    tmul<NS>(oT, W.xc, n, lane, uf);
     double series = 0.0;
 #pragma unroll
     for (int t = 0; t < NS; ++t) {
@@ -454,7 +426,7 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
 template <int NS>
 __global__ void __launch_bounds__(32) t2_full_factors_kernel(const double* __restrict__ G, const double* __restrict__ kband,
                                                              int n, int nA, double lo, double hi, double xatol,
-                                                             int maxfun, double* __restrict__ tfull,
+                                                             int maxfun, int upper, double* __restrict__ tfull,
                                                              double* __restrict__ lam_tab) {
     const int lane = threadIdx.x;
     const int a = blockIdx.x % nA, j = blockIdx.x / nA;
@@ -476,7 +448,8 @@ __global__ void __launch_bounds__(32) t2_full_factors_kernel(const double* __res
         if (d >= 0 && d <= 4) v = fma(lj, __ldg(kband + d * n + c), v);
         return v;
     };
-    const bool pd = (lj == lj) && rebuild_T_blocked<NS>(W, Aent, n, lane);
+    // upper: the Cholesky factor U itself (BayesReg evidence); otherwise the inverse factor T (X2 full-set starts)
+    const bool pd = (lj == lj) && (upper ? chol_upper_blocked<NS>(W, Aent, n, lane) : rebuild_T_blocked<NS>(W, Aent, n, lane));
     double* out = tfull + ((size_t)j * nA + a) * tri(n);
     for (int i = lane; i < tri(n); i += 32) out[i] = S[W.T + i];
     __syncwarp();
@@ -690,14 +663,12 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
-                                            warm ? p : 0, t_ready
-#ifdef MET2_DSPACE_RESCUE
-                                            ,
-                                            Dt, oM
-#endif
-                    );
+                                            warm ? p : 0, t_ready, Dt, oM);
                     t_ready = false;
-                    if (method == MET2_REG_NNLS && nst == 0 && p > 0) refine_plain<NS, ME>(W, Dt, oM, oLx, m, p, lane);
+                    if (method == MET2_REG_NNLS && nst == 0 && p > 0)
+                        refine_on_support<NS, ME>(W, Dt, oM, m, p, lane, false, 0.0, oKb, n);
+                    if (method == MET2_REG_BAYESREG && reg && nst == 0 && p > 0)
+                        refine_on_support<NS, ME>(W, Dt, oM, m, p, lane, true, lam, oKb, n);
                     const double sse = fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                     if (stage == ST_FINAL) {
                         if (method == MET2_REG_GCV && (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL)) {
@@ -767,7 +738,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                                 if (ttab && !(__ldg(ttab) == __ldg(ttab))) ttab = nullptr;   // not positive definite
                             }
                             const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
-                                                               A.cfg.log_det_L, st, p, ttab);
+                                                               A.cfg.log_det_L, st, ttab);
                             const double lam_eval = lam;
                             const bool more = B.feed(cost, lam);
                             if (warm && B.xf == lam_eval) snapshot(sse);

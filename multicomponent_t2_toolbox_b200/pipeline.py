@@ -33,15 +33,17 @@ def cyclic_slab(n_voxels, rank, world_size, chunk=2048):
     return idx[(idx // int(chunk)) % int(world_size) == rank]
 
 
-def masked_voxel_list(data, mask):
-    """Apply the mask and the negative clamp like motor...:178-180,279 and return (flat voxel indices, signals[V,nTE])
-    of the voxels with mask > 0, in C order of (x, y, z)."""
+def masked_voxel_list(data, mask, premasked=False):
+    """Return (flat voxel indices, signals[V,nTE]) of the voxels with mask > 0, in C order of (x, y, z).  Unless
+    `premasked` (the motor entry points have already done it, motor...:178-180,279 — applying a label mask twice would
+    scale the data by mask squared), the mask multiplication and the negative clamp are applied here."""
     nx, ny, nz, nt = data.shape
     m = np.asarray(mask).reshape(-1)
     flat = np.nonzero(m > 0)[0]
     sig = np.ascontiguousarray(data.reshape(-1, nt)[flat], dtype=np.float64)
-    sig = sig * m[flat][:, None]
-    sig[sig < 0.0] = 0.0
+    if not premasked:
+        sig = sig * m[flat][:, None]
+        sig[sig < 0.0] = 0.0
     return flat, sig
 
 
@@ -84,7 +86,8 @@ def fit_voxels(plan, sig, sig_fa=None, pinned_out=None, in_mask=None, roi=None):
 
 
 def recon_arrays(data, mask, TE_array, TR, reg_method, reg_matrix, FA_method, myelin_T2=40.0, data_fa=None, plan=None,
-                 npc=None, n_alphas=None, device=None, rank=0, world_size=1, diagnostics=False, rois=None):
+                 npc=None, n_alphas=None, device=None, rank=0, world_size=1, diagnostics=False, rois=None,
+                 premasked=False, fa_only=False):
     """Steps 2-4 of motor_recon_met2 on in-memory arrays.  Returns the ten output volumes (plus FA_index) as numpy.
 
     With world_size > 1 only this rank's slab of the masked voxels is fitted and the other voxels are left zero; the
@@ -97,17 +100,19 @@ def recon_arrays(data, mask, TE_array, TR, reg_method, reg_matrix, FA_method, my
         plan = batched.Met2Plan(TE_array.shape[0], TE_array[1] - TE_array[0], TR, reg_method=reg_method,
                                 reg_matrix=reg_matrix, FA_method=FA_method, myelin_T2=myelin_T2, npc=npc,
                                 n_alphas=n_alphas, device=device)
-    flat, sig = masked_voxel_list(data, mask)
+    flat, sig = masked_voxel_list(data, mask, premasked)
     lo, hi = slab_bounds(len(flat), rank, world_size)
     sig_fa = None
     if data_fa is not None:
         if isinstance(data_fa, torch.Tensor):
             # smoothed volume already on the GPU (batched.gaussian_smooth): gather the slab's voxels there
             idx = torch.as_tensor(flat[lo:hi]).to(data_fa.device)
-            m = torch.as_tensor(np.asarray(mask).reshape(-1)[flat[lo:hi]].astype(np.float64)).to(data_fa.device)
-            sig_fa = (data_fa.reshape(-1, nt).index_select(0, idx) * m[:, None]).clamp_min(0.0)
+            sig_fa = data_fa.reshape(-1, nt).index_select(0, idx)
+            if not premasked:
+                m = torch.as_tensor(np.asarray(mask).reshape(-1)[flat[lo:hi]].astype(np.float64)).to(data_fa.device)
+                sig_fa = (sig_fa * m[:, None]).clamp_min(0.0)
         else:
-            _, sig_fa_all = masked_voxel_list(np.asarray(data_fa, dtype=np.float64), mask)
+            _, sig_fa_all = masked_voxel_list(np.asarray(data_fa, dtype=np.float64), mask, premasked)
             sig_fa = sig_fa_all[lo:hi]
     if (diagnostics or rois is not None) and world_size != 1:
         raise ValueError("mean-spectrum diagnostics / ROI estimates are whole-volume reductions: run them unsharded")

@@ -53,3 +53,33 @@ def golden_methods(golden_config2):
         return f
     g["spectrum"] = spectrum
     return g
+
+
+def _unpack(g, key, npc):
+    import numpy as np
+    sup = np.unpackbits(g[key + "_support"], axis=1)[:, :npc].astype(bool)
+    f = np.zeros(sup.shape)
+    f[sup] = g[key + "_fnz"]
+    return f
+
+
+@pytest.fixture(scope="session")
+def golden_plain_wide(golden_config2):
+    """Plain NNLS of the 20 480 config-2 voxels on the 60-, 96- and 100-bin grids + the 96-bin spline FA search, all by the
+    unmodified reference (oracle/make_golden_r2.py)."""
+    import numpy as np
+    g = dict(np.load(os.path.join(GOLDEN, "plain_nnls_wide.npz")))
+    return dict(sig=golden_config2["sig"], fa_idx=golden_config2["fa_idx"].astype(np.int32),
+                f60=_unpack(g, "nnls60", 60), f96=_unpack(g, "nnls96", 96), f100=_unpack(g, "nnls100", 100),
+                fa96_idx=g["fa96_idx"].astype(np.int32), fa96_km=g["fa96_km"])
+
+
+@pytest.fixture(scope="session")
+def golden_config4():
+    """2 048 voxels at BASELINE.json configs[3] sizes (nTE 48, 100 bins, brute-force FA, BayesReg + InvT2) fitted by the
+    unmodified reference, plus the same fit of the 1e-13-perturbed signals (oracle/make_golden_r2.py)."""
+    import numpy as np
+    g = dict(np.load(os.path.join(GOLDEN, "config4_subset.npz")))
+    for key in ("nnls", "bayes", "bayesp"):
+        g["f_" + key] = _unpack(g, key, 100)
+    return g

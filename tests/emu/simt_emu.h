@@ -26,6 +26,7 @@
 #define __device__
 #define __global__
 #define __forceinline__ inline __attribute__((always_inline))
+#define __noinline__ __attribute__((noinline))
 #define __restrict__
 #define __launch_bounds__(...)
 #define __shared__ static
@@ -35,6 +36,7 @@ typedef void* cudaStream_t;
 struct double2 {
     double x, y;
 };
+static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}

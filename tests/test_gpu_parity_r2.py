@@ -1,0 +1,183 @@
+"""Round-2 parity tests on the device, all against fixtures written by the UNMODIFIED reference
+(oracle/make_golden_r2.py, oracle/make_golden_config2.py, oracle/make_golden_methods.py):
+
+  * plain Lawson-Hanson NNLS on the 60 / 96 / 100-bin grids, 20 480 voxels each (algorithms.py:55-82) and the 96-bin
+    spline FA search (fa_estimation.py:35-70) — the wide grids have nearly collinear long-T2 columns;
+  * BASELINE.json configs[3] sizes (nTE 48, 100 bins): brute-force FA, plain NNLS and BayesReg + InvT2
+    (bayesian_interpolation.py:84-126) on 2 048 voxels, bounded by the reference's own reproducibility under a 1e-13
+    relative perturbation of the signal;
+  * the echo-space kernels (MET2_T2_FLAG_ECHO_SPACE) for X2-I, X2-InvT2 and T2SPARC (96 bins).
+
+Every test writes its measured rates to gpurun_out/parity_r2_*.json (copied to profiles/ after a run)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import met2_oracle as O
+from multicomponent_t2_toolbox_b200 import batched
+
+pytestmark = pytest.mark.gpu
+
+REL_SPECTRUM = 1e-6
+ABS_MAPS = 1e-4
+ECHO = 64
+OUTDIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
+def _rel_err(f, f_ref):
+    scale = np.abs(f_ref).max(axis=1)
+    scale[scale == 0] = 1.0
+    return np.abs(f - f_ref).max(axis=1) / scale
+
+
+def _record(name, rec):
+    os.makedirs(OUTDIR, exist_ok=True)
+    with open(os.path.join(OUTDIR, name), "w") as fh:
+        json.dump(rec, fh, indent=1)
+
+
+def _mwf(f, plan):
+    return f[:, plan.ind_m].sum(1) / (f.sum(1) + 1e-16)
+
+
+def test_plain_nnls_wide_grids_vs_reference(golden_plain_wide):
+    """North-star bar "active sets bit-exact" for the plain solver on every grid the reference uses: 0 disagreements
+    expected (the Gram-domain dependence test alone left 1 in 1 500 at 96 bins: dspace_candidate, met2_nnls.cuh)."""
+    g = golden_plain_wide
+    sig = g["sig"]
+    V = sig.shape[0]
+    rec = {}
+    for npc in (60, 96, 100):
+        plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="NNLS", reg_matrix="I", FA_method="spline", npc=npc)
+        out = plan.t2_fit(sig, g["fa_idx"])
+        f, f_ref = out["fsol"].cpu().numpy(), g["f%d" % npc]
+        bad = np.any((f > 0) != (f_ref > 0), axis=1)
+        rel = _rel_err(f, f_ref)
+        dmwf = np.abs(_mwf(f, plan) - _mwf(f_ref, plan))
+        r = dict(voxels=int(V), active_set_disagreements=int(bad.sum()), disagreement_rate=float(bad.mean()),
+                 spectrum_rel_err_max_agreeing=float(rel[~bad].max()), spectrum_rel_err_max_all=float(rel.max()),
+                 max_abs_dMWF_all=float(dmwf.max()), status_nonzero=int((out["status"] != 0).sum()))
+        if npc == 96:
+            fa = plan.fa_fit(sig)
+            r["fa_spline_index_mismatches"] = int((fa["fa_index"].cpu().numpy() != g["fa96_idx"]).sum())
+            r["fa_km_rel_err_max"] = float(np.max(np.abs(fa["km"].cpu().numpy() - g["fa96_km"]) / g["fa96_km"]))
+        rec["nnls_%d_bins" % npc] = r
+    _record("parity_r2_plain_nnls_wide.json", rec)
+    for key, r in rec.items():
+        assert r["active_set_disagreements"] == 0, (key, r)
+        assert r["spectrum_rel_err_max_all"] < REL_SPECTRUM and r["max_abs_dMWF_all"] < ABS_MAPS, (key, r)
+        assert r["status_nonzero"] == 0, (key, r)
+    assert rec["nnls_96_bins"]["fa_spline_index_mismatches"] == 0, rec
+    assert rec["nnls_96_bins"]["fa_km_rel_err_max"] < 1e-6, rec
+
+
+def test_config4_subset_vs_reference(golden_config4):
+    """configs[3] sizes against 2 048 reference-fitted voxels.  FA index and plain NNLS at full tolerance.  BayesReg +
+    InvT2: the reference does not reproduce ITSELF to 1e-6 there — the fixture holds its fit of the same signals
+    perturbed by 1e-13 (relative), and the evidence is flat enough for that to move lambda by up to 3e-4 and the
+    spectrum by up to 1e-4 in ~5 % of the voxels.  Our result is held to that reproducibility: no more voxels beyond
+    1e-6 than twice the reference's own count (+ 1 % of the voxels; measured under the SIMT emulator on 256 voxels:
+    ours 20, the reference against itself 13), a median within 3x of the reference's, active sets within 2 voxels of
+    its own disagreement count and maps at full tolerance."""
+    g = golden_config4
+    sig = g["sig"]
+    V = sig.shape[0]
+    plan = batched.Met2Plan(48, 8.0, 1000.0, reg_method="BayesReg", reg_matrix="InvT2", FA_method="brute-force", npc=100)
+    fa = plan.fa_fit(sig)
+    idx_ref = g["fa_idx"].astype(np.int32)
+    fa_bad = fa["fa_index"].cpu().numpy() != idx_ref
+    nn = plan.t2_fit(sig, idx_ref, reg_method="NNLS")
+    fn, fn_ref = nn["fsol"].cpu().numpy(), g["f_nnls"]
+    nn_bad = np.any((fn > 0) != (fn_ref > 0), axis=1)
+    t2 = plan.t2_fit(sig, idx_ref)
+    f, f_ref, f_p = t2["fsol"].cpu().numpy(), g["f_bayes"], g["f_bayesp"]
+    reg = t2["reg"].cpu().numpy()
+    sup_bad = np.any((f > 0) != (f_ref > 0), axis=1)
+    sup_self = np.any((f_p > 0) != (f_ref > 0), axis=1)
+    d_ours, d_self = _rel_err(f, f_ref), _rel_err(f_p, f_ref)
+    l_ours = np.abs(reg - g["bayes_reg"]) / g["bayes_reg"]
+    l_self = np.abs(g["bayesp_reg"] - g["bayes_reg"]) / g["bayes_reg"]
+    dmwf = np.abs(_mwf(f, plan) - _mwf(f_ref, plan))
+    dmwf_self = np.abs(_mwf(f_p, plan) - _mwf(f_ref, plan))
+    rec = dict(voxels=int(V), fa_index_mismatches=int(fa_bad.sum()),
+               nnls_active_set_disagreements=int(nn_bad.sum()), nnls_spectrum_rel_err_max=float(_rel_err(fn, fn_ref).max()),
+               bayes=dict(active_set_disagreements=int(sup_bad.sum()), reference_self_disagreements=int(sup_self.sum()),
+                          spectrum_rel_over_1e6=int((d_ours > 1e-6).sum()), reference_self_over_1e6=int((d_self > 1e-6).sum()),
+                          spectrum_rel_median=float(np.median(d_ours)), reference_self_median=float(np.median(d_self)),
+                          spectrum_rel_max=float(d_ours.max()), reference_self_max=float(d_self.max()),
+                          lambda_rel_over_1e6=int((l_ours > 1e-6).sum()), reference_self_lambda_over_1e6=int((l_self > 1e-6).sum()),
+                          lambda_rel_max=float(l_ours.max()), reference_self_lambda_max=float(l_self.max()),
+                          max_abs_dMWF=float(dmwf.max()), reference_self_max_abs_dMWF=float(dmwf_self.max()),
+                          status_nonzero=int((t2["status"] != 0).sum())))
+    _record("parity_r2_config4_subset.json", rec)
+    b = rec["bayes"]
+    assert rec["fa_index_mismatches"] == 0 and rec["nnls_active_set_disagreements"] == 0, rec
+    assert rec["nnls_spectrum_rel_err_max"] < REL_SPECTRUM, rec
+    assert b["status_nonzero"] == 0, rec
+    assert b["active_set_disagreements"] <= b["reference_self_disagreements"] + 2, rec
+    slack = int(0.01 * V)
+    assert b["spectrum_rel_over_1e6"] <= 2 * b["reference_self_over_1e6"] + slack, rec
+    assert b["lambda_rel_over_1e6"] <= 2 * b["reference_self_lambda_over_1e6"] + slack, rec
+    assert b["spectrum_rel_median"] <= 3.0 * b["reference_self_median"] + 1e-9, rec
+    assert b["spectrum_rel_max"] <= 10.0 * b["reference_self_max"], rec
+    assert b["max_abs_dMWF"] < ABS_MAPS, rec
+
+
+def test_echo_space_kernels_vs_reference(golden_config2, golden_methods):
+    """MET2_T2_FLAG_ECHO_SPACE (csrc/met2_t2_echo.cu) on the device: X2-I against the 20 480 reference-fitted voxels,
+    X2-InvT2 against the oracle (160 voxels) and the default kernel (20 480), T2SPARC (96 bins) against the 2 048
+    reference-fitted voxels."""
+    g = golden_config2
+    sig, idx = g["sig"], g["fa_idx"].astype(np.int32)
+    rec = {}
+    plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="I", FA_method="spline")
+    out = plan.t2_fit(sig, idx, flags=ECHO)
+    f, f_ref = out["fsol"].cpu().numpy(), g["f"]
+    bad = np.any((f > 0) != (f_ref > 0), axis=1)
+    rel = _rel_err(f, f_ref)
+    dreg = np.abs(out["reg"].cpu().numpy() - g["reg"]) / np.abs(g["reg"])
+    rec["X2_I"] = dict(voxels=int(len(f)), active_set_disagreements=int(bad.sum()),
+                       spectrum_rel_err_max_agreeing=float(rel[~bad].max()), k_est_rel_err_max_agreeing=float(dreg[~bad].max()),
+                       max_abs_dMWF_agreeing=float(np.abs(_mwf(f, plan) - _mwf(f_ref, plan))[~bad].max()),
+                       status_nonzero=int((out["status"] != 0).sum()))
+    pi = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="InvT2", FA_method="spline")
+    e = pi.t2_fit(sig, idx, flags=ECHO)
+    d = pi.t2_fit(sig, idx)
+    fe, fd = e["fsol"].cpu().numpy(), d["fsol"].cpu().numpy()
+    bad_ab = np.any((fe > 0) != (fd > 0), axis=1)
+    n_or = 160
+    Dic = pi.dict_hr.to_reference_layout()
+    f_or, _, reg_or = O.fitting_slice_T2(np.ones(n_or), sig[:n_or], idx[:n_or], n_or, Dic, pi.lambda_reg, 60, 32, "X2",
+                                         pi.Laplac)
+    rec["X2_InvT2"] = dict(voxels=int(len(fe)), active_set_disagreements_vs_default=int(bad_ab.sum()),
+                           spectrum_rel_err_over_1e6_vs_default=int((_rel_err(fe, fd) > REL_SPECTRUM).sum()),
+                           oracle_voxels=n_or,
+                           active_set_disagreements_vs_oracle=int(np.any((fe[:n_or] > 0) != (f_or > 0), axis=1).sum()),
+                           spectrum_rel_err_max_vs_oracle=float(_rel_err(fe[:n_or], f_or).max()),
+                           status_nonzero=int((e["status"] != 0).sum()))
+    gm = golden_methods
+    pt = batched.Met2Plan(32, 10.0, 1000.0, reg_method="T2SPARC", reg_matrix="InvT2", FA_method="spline", npc=96)
+    idx96 = gm["fa_spline_96"].astype(np.int32)
+    t = pt.t2_fit(gm["sig"], idx96, flags=ECHO)
+    ft, ft_ref = t["fsol"].cpu().numpy(), gm["spectrum"]("T2SPARC_InvT2", 96)
+    bad_t = np.any((ft > 0) != (ft_ref > 0), axis=1)
+    rec["T2SPARC_InvT2_96"] = dict(voxels=int(len(ft)), active_set_disagreements=int(bad_t.sum()),
+                                   spectrum_rel_err_max_agreeing=float(_rel_err(ft, ft_ref)[~bad_t].max()),
+                                   max_abs_dMWF=float(np.abs(_mwf(ft, pt) - _mwf(ft_ref, pt)).max()),
+                                   status_nonzero=int((t["status"] != 0).sum()))
+    _record("parity_r2_echo_space.json", rec)
+    r = rec["X2_I"]
+    assert r["status_nonzero"] == 0 and r["active_set_disagreements"] <= 4, rec      # Brent branch points, see config-2 test
+    assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF_agreeing"] < ABS_MAPS, rec
+    r = rec["X2_InvT2"]
+    assert r["status_nonzero"] == 0 and r["active_set_disagreements_vs_oracle"] == 0, rec
+    assert r["spectrum_rel_err_max_vs_oracle"] < REL_SPECTRUM, rec
+    # Brent branch points (absolute xtol 1e-5 on lambda): two exact solvers part ways on ~4 voxels in 10^4, like the
+    # reference against itself (config-2 test above; warm/cold A/B of round 1: 15 of 552 960)
+    assert r["active_set_disagreements_vs_default"] <= 4 and r["spectrum_rel_err_over_1e6_vs_default"] <= 12, rec
+    r = rec["T2SPARC_InvT2_96"]
+    assert r["status_nonzero"] == 0 and r["active_set_disagreements"] == 0, rec
+    assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF"] < ABS_MAPS, rec
