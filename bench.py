@@ -52,6 +52,8 @@ def parse_args():
     ap.add_argument("--t2-flags", type=int, default=0,
                     help="extra MET2_T2_FLAG_* bits for every T2 fit (A/B runs only, e.g. 64 = experimental echo-space "
                          "kernel); the default 0 is the measured configuration")
+    ap.add_argument("--gram", action="store_true",
+                    help="A/B runs only: Gram-domain T2 kernel instead of the default reduced-echo-space kernel")
     return ap.parse_args()
 
 
@@ -212,7 +214,7 @@ def run_ours(args):
     sig_host = torch.as_tensor(ph["data"].reshape(-1, N_ECHOES)).pin_memory()
     V = sig_host.shape[0]
     plan = batched.Met2Plan(N_ECHOES, TAU, TR, reg_method=REG_METHOD, reg_matrix=REG_MATRIX, FA_method=FA_METHOD,
-                            device=dev, t2_flags=args.t2_flags)
+                            device=dev, t2_flags=args.t2_flags, echo_space=not args.gram)
     sig = sig_host.to(dev)
     fa_out = t2_out = None
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MET2_VERSION 100 /* 0.1.0 */
+#define MET2_VERSION 110 /* 0.1.1: met2_echo_basis, met2_t2_fit_echo */
 
 /* error codes */
 #define MET2_OK 0
@@ -38,6 +38,7 @@ extern "C" {
 #define MET2_MAX_NTE 64  /* echoes (reference data: 32; config 4 uses 48) */
 #define MET2_MAX_KNOTS 32
 #define MET2_MAX_LAMBDAS 64
+#define MET2_ECHO_RANK 24 /* rows of the reduced echo space (met2_echo_basis, met2_t2_fit_echo) */
 
 /* per-voxel status bits */
 #define MET2_ST_SKIPPED 1u      /* sum(M) <= 0 or M[0] <= 0: voxel not fitted (fa_estimation.py:100, motor...:124,131) */
@@ -81,11 +82,13 @@ typedef struct met2_fa_cfg {
 #define MET2_T2_FLAG_FULL_START 16    /* X2: start the solves at Brent's first (voxel-independent) abscissae from the full
                                         column set, with inverse-Cholesky factors shared per flip angle
                                         (worth it when L = I; same minimiser) */
-#define MET2_T2_FLAG_ECHO_SPACE 64    /* EXPERIMENTAL, off by default: X2 (nT2 <= 64) and T2SPARC (nT2 <= 128) with
-                                        nTE <= 32 and a DIAGONAL L (I, InvT2; asserted by the caller): Tikhonov solves
-                                        in echo space (32 x 32 factor per voxel, csrc/met2_t2_echo.cu).  A non-diagonal
-                                        L skips every voxel with MET2_ST_ECHO_BAD_L.  Same minimiser as the default
-                                        path; validated on the CPU emulator only so far */
+#define MET2_T2_FLAG_ECHO_SPACE 64    /* X2 (nT2 <= 64) and T2SPARC (nT2 <= 128) with a DIAGONAL L (I, InvT2; asserted by
+                                        the caller): Tikhonov solves in the reduced echo space (24 x 24 factor per
+                                        voxel, csrc/met2_t2_echo.cu) instead of the Gram domain (nT2 x nT2).  Needs
+                                        the tables of met2_echo_basis -> call met2_t2_fit_echo.  A non-diagonal L
+                                        skips every voxel with MET2_ST_ECHO_BAD_L.  Same minimiser as the Gram-domain
+                                        path; measured faster for X2-I and T2SPARC (profiles/r02_ab_*), which is why
+                                        batched.Met2Plan sets it for those by default */
 #define MET2_T2_FLAG_COLD_START 4    /* start every NNLS of a lambda search from the empty set like the reference,
                                         instead of warm-starting from the previous solution (same minimiser) */
 
@@ -145,6 +148,23 @@ int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met
                 const double* dicT, const double* G, const double* kband, const double* lambdas, const double* logT2,
                 const uint8_t* comp, double* fsol, double* est_signal, double* reg, double* maps, uint32_t* status,
                 void* workspace, void* stream);
+
+/* Reduced echo basis of the dictionary (once per reconstruction).  The EPG decay curves of one flip angle are
+ * numerically of rank ~20 whatever nTE is: D_a = U_a C_a to the rounding of D_a's own entries, with U_a [nTE][R]
+ * orthonormal and C_a = U_a^T D_a (column-pivoted Gram-Schmidt, csrc/met2_basis.cu).
+ * basis [nA][nTE][R], coef [nA][nT2][R] (C_a[e][j] stored at [j][e]), tail [nA] = max_j |d_j - U C_j| / max_j |d_j|
+ * per angle (may be NULL): the measured residual of the reduction, which the caller checks against its tolerance
+ * (batched.Dictionary: 1e-15) before using the echo-space kernels.  R must be MET2_ECHO_RANK for met2_t2_fit_echo. */
+int met2_echo_basis(const double* dic, int nA, int nTE, int nT2, int R, double* basis, double* coef, double* tail,
+                    void* stream);
+
+/* met2_t2_fit with the tables of met2_echo_basis: required when cfg->flags has MET2_T2_FLAG_ECHO_SPACE (the X2 / T2SPARC
+ * Tikhonov solves then run in the reduced echo space); otherwise identical to met2_t2_fit. */
+int met2_t2_fit_echo(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg, const double* dic,
+                     const double* dicT, const double* G, const double* kband, const double* lambdas,
+                     const double* logT2, const uint8_t* comp, const double* red_basis, const double* red_coef,
+                     double* fsol, double* est_signal, double* reg, double* maps, uint32_t* status, void* workspace,
+                     void* stream);
 
 /* FA-stage preprocessing: replaces `filt.gaussian_filter(data[:, :, :, c], 2.0, 0)` per echo (motor...:336-346;
  * scipy.ndimage semantics: mode 'reflect', symmetric kernel `weights[2*radius+1]`, radius = int(4 sigma + 0.5)).

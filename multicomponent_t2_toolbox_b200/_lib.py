@@ -37,6 +37,9 @@ SIGNATURES = {
     "met2_fa_fit": (ctypes.c_int, [c_void_p, ctypes.c_int64, ctypes.POINTER(FaCfg)] + [c_void_p] * 15),
     "met2_t2_workspace_bytes": (ctypes.c_int64, [ctypes.c_int64, ctypes.POINTER(T2Cfg)]),
     "met2_t2_fit": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [c_void_p] * 14),
+    "met2_t2_fit_echo": (ctypes.c_int, [c_void_p, c_void_p, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [c_void_p] * 16),
+    "met2_echo_basis": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p]),
     "met2_gaussian_smooth": (ctypes.c_int, [c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_void_p,
                                             ctypes.c_int, c_void_p, c_void_p, c_void_p]),
     "met2_segment_workspace_bytes": (ctypes.c_int64, [ctypes.c_int, ctypes.c_int]),

@@ -20,7 +20,9 @@ FA_METHOD_CODE = {"brute-force": 0, "spline": 1}
 REG_METHOD_CODE = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3, "GCV": 4, "BayesReg": 5}
 
 ST_SKIPPED, ST_NONFINITE, ST_ITMAX, ST_SSE_ZERO, ST_NOT_PD = 1, 2, 4, 8, 16
-REG_IS_LAMBDA, NO_NORMALISE, COLD_START, GCV_EVAL, FULL_START, GCV_GRID = 1, 2, 4, 8, 16, 32   # MET2_T2_FLAG_*
+REG_IS_LAMBDA, NO_NORMALISE, COLD_START, GCV_EVAL, FULL_START, GCV_GRID, ECHO_SPACE = 1, 2, 4, 8, 16, 32, 64   # MET2_T2_FLAG_*
+ECHO_RANK = 24          # MET2_ECHO_RANK
+ECHO_TAIL_MAX = 1e-15   # largest sigma_{R+1} / sigma_1 for which the reduced echo space is taken as exact
 
 
 def _require_cuda(device):
@@ -175,6 +177,23 @@ class Dictionary:
                                             _stream()), "met2_gram_tables")
         return self
 
+    def echo_basis(self):
+        """Reduced echo basis of this dictionary (met2_echo_basis, built on first use): (basis [nA, nTE, R],
+        coef [nA, nT2, R]) or None when the dictionary is not numerically of rank <= R (then the echo-space kernels are
+        not used and the Gram-domain kernels run)."""
+        if not hasattr(self, "_echo"):
+            lib = _lib.load()
+            dev = self.dic.device
+            basis = torch.empty((self.nA, self.nTE, ECHO_RANK), dtype=torch.float64, device=dev)
+            coef = torch.empty((self.nA, self.nT2, ECHO_RANK), dtype=torch.float64, device=dev)
+            tail = torch.empty(self.nA, dtype=torch.float64, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(lib.met2_echo_basis(_ptr(self.dic), self.nA, self.nTE, self.nT2, ECHO_RANK, _ptr(basis),
+                                               _ptr(coef), _ptr(tail), _stream()), "met2_echo_basis")
+            self.echo_tail = float(tail.max())
+            self._echo = (basis, coef) if self.echo_tail <= ECHO_TAIL_MAX else None
+        return self._echo
+
     def to_reference_layout(self):
         """Host copy in the reference's layout Dic_3D[nTE, nT2, nA] (epg/epg.py:155-162)."""
         return np.ascontiguousarray(self.dic.permute(1, 2, 0).cpu().numpy())
@@ -183,7 +202,7 @@ class Dictionary:
 class Met2Plan:
     def __init__(self, n_echoes, tau, TR, reg_method="X2", reg_matrix="I", FA_method="spline", myelin_T2=40.0,
                  npc=None, n_alphas=None, T1=1000.0, device=None, lambda_reg=None, Laplac=None, Dic_3D=None,
-                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None, t2_flags=0):
+                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None, t2_flags=0, echo_space=True):
         """Tables for one reconstruction set-up.  By default everything is built like motor...:204-277 (EPG dictionary
         on the GPU); `Dic_3D` (+ `Dic_3D_LR`, `alpha_values`, `alpha_values_spline`, `T2s`, `Laplac`) lets a caller bring
         its own dictionary in the reference layout [nTE, nT2, nA] — used by the drop-in row workers and per-voxel API."""
@@ -195,6 +214,9 @@ class Met2Plan:
         self.lib = _lib.load()
         self.reg_method, self.reg_matrix, self.FA_method = reg_method, reg_matrix, FA_method
         self.t2_flags = int(t2_flags)    # MET2_T2_FLAG_* applied to every t2_fit of this plan (e.g. GCV_GRID)
+        # reduced-echo-space kernels for the configurations where they measured faster than the Gram-domain ones
+        # (X2 with the identity matrix, T2SPARC; profiles/r02_ab_*); echo_space=False keeps the Gram-domain kernels
+        self.echo_space = bool(echo_space)
         self.nTE, self.tau, self.TR = int(n_echoes), float(tau), float(TR)
         if Dic_3D is not None:
             Dic_3D = np.asarray(Dic_3D, dtype=np.float64)
@@ -268,10 +290,18 @@ class Met2Plan:
             with np.errstate(divide="ignore"):
                 cfg.log_det_L = float(np.log(np.linalg.det(self.Laplac)))
         if method == "X2" and np.array_equal(self.Laplac, np.eye(self.npc)):
-            cfg.flags |= 16   # MET2_T2_FLAG_FULL_START
+            cfg.flags |= FULL_START
+            if self.echo_space and self.npc <= 64 and not (cfg.flags & COLD_START):
+                cfg.flags |= ECHO_SPACE
+        if method == "T2SPARC" and self.echo_space and self.npc <= 128 and self._diagonal_L():
+            cfg.flags |= ECHO_SPACE
         for k, v in overrides.items():   # e.g. factor=..., lambda_fixed=..., maxfun=...
             setattr(cfg, k, v)
         return cfg
+
+    def _diagonal_L(self):
+        L = self.Laplac
+        return bool(np.all(L[~np.eye(self.npc, dtype=bool)] == 0.0) and np.all(np.diag(L) > 0.0))
 
     def _workspace(self, key, nbytes):
         ws = self._ws.get(key)
@@ -347,16 +377,24 @@ class Met2Plan:
         if cfg.flags & GCV_GRID:    # GCV over the positive part of the L-curve grid (lambda_reg[1:]; lambda_reg[0] = 0)
             lambdas = self.lambdas[1:].contiguous()
             cfg.nLambda = lambdas.numel()
+        red = None
+        if cfg.flags & ECHO_SPACE:
+            if not self._diagonal_L():
+                raise ValueError("MET2_T2_FLAG_ECHO_SPACE needs a diagonal regularisation matrix (I, InvT2)")
+            red = hr.echo_basis()
+            if red is None:      # dictionary not of numerical rank <= 24: Gram-domain kernels
+                cfg.flags &= ~ECHO_SPACE
         with torch.cuda.device(dev):
             nbytes = self.lib.met2_t2_workspace_bytes(V, ctypes.byref(cfg))
             if nbytes < 0:
                 _lib.check(-1, "met2_t2_workspace_bytes")
             ws = self._workspace("t2", nbytes)
-            _lib.check(self.lib.met2_t2_fit(
+            _lib.check(self.lib.met2_t2_fit_echo(
                 _ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(hr.dic), _ptr(hr.dicT), _ptr(hr.G),
-                _ptr(self.kband), _ptr(lambdas), _ptr(self.logT2), _ptr(self.comp), _ptr(out["fsol"]),
+                _ptr(self.kband), _ptr(lambdas), _ptr(self.logT2), _ptr(self.comp),
+                _ptr(red[0]) if red else None, _ptr(red[1]) if red else None, _ptr(out["fsol"]),
                 _ptr(out["est_signal"]), _ptr(out["reg"]), _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), _stream()),
-                "met2_t2_fit")
+                "met2_t2_fit_echo")
         return out
 
     def fit(self, sig, sig_fa=None):

@@ -115,6 +115,7 @@ __global__ void band_kernel(const double* __restrict__ L, int n, double* __restr
     }
 }
 
+
 }  // namespace met2
 
 using namespace met2;

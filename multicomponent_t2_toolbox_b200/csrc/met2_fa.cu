@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(FA_SEARCH_WARPS * 32, 1) fa_search_kernel(FaAr
                 __syncwarp();
             }
             int nst = 0;
-            int p = nnls_gram<NS, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, p0, false,
-                                        A.dicT_s + (size_t)a * n * m, oM);
+            set_dspace<NS>(W, A.dicT_s + (size_t)a * n * m, oM, lane);
+            int p = nnls_gram<NS, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, p0);
             if (a + 1 < A.nS) {
                 const bool keep = (p <= FA_CARRY);
                 if (keep && lane < p) {
@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_select_kernel(FaArgs A) {
             const double* G = A.G + (size_t)index * n * n;
             compute_c<NS>(W, D, oM, m, n, lane);
             int nst = 0;
-            (void)nnls_gram<NS, false>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst, 0, false,
-                                       A.dicT + (size_t)index * n * m, oM);
+            set_dspace<NS>(W, A.dicT + (size_t)index * n * m, oM, lane);
+            (void)nnls_gram<NS, false>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst);
             if (nst && lane == 0) A.status[v] |= MET2_ST_ITMAX;
             // nnls_gram leaves the solution in column space in S[W.xc..]; km = sum(f)
             double part = 0.0;

@@ -111,11 +111,14 @@ __device__ __forceinline__ int warp_argmin_nonneg(double v, int index, double& v
 //   cc : c = A^T b in column space
 //   xc : x in column space (zeros outside P)
 //   ix : position -> column (ints, stored in the space of LEN/2 doubles)
+//   aux: two doubles after ix — [0] the pointer to the transposed dictionary [n][m] of the solve in flight (global
+//        memory), [1] (as int) the offset of its right-hand side in S; read only by the rare D-space evaluation of a
+//        nearly dependent candidate (dspace_candidate), kept here rather than in registers (see set_dspace)
 template <int NS>
 struct Slots {
     int T, gs, rs, xs, cc, xc, ix;
     static constexpr int LEN = 32 * NS;
-    __host__ __device__ static int doubles(int pmax) { return tri(pmax) + 5 * LEN + LEN / 2; }
+    __host__ __device__ static int doubles(int pmax) { return tri(pmax) + 5 * LEN + LEN / 2 + 2; }
     __device__ __forceinline__ void carve(int base, int pmax) {
         T = base;
         gs = T + tri(pmax);
@@ -125,9 +128,23 @@ struct Slots {
         xc = cc + LEN;
         ix = xc + LEN;
     }
+    __device__ __forceinline__ int aux() const { return ix + LEN / 2; }
 };
 
 __device__ __forceinline__ int& SI(int off, int k) { return reinterpret_cast<int*>(S + off)[k]; }
+
+// Tell the plain solves of this warp where the transposed dictionary [n][m] (global memory) and the right-hand side
+// (offset in S) are, for the D-space evaluation of nearly dependent candidates.  Dt = nullptr switches it off.
+// Two shared-memory words per warp instead of three kernel-lifetime registers per thread: with the pointer as an
+// argument of nnls_gram the 80-register FA select kernel spilled (FA stage +6 %).
+template <int NS>
+__device__ __forceinline__ void set_dspace(const Slots<NS>& W, const double* Dt, int oM, int lane) {
+    if (lane == 0) {
+        *reinterpret_cast<const double**>(S + W.aux()) = Dt;
+        SI(W.aux() + 1, 0) = oM;
+    }
+    __syncwarp();
+}
 
 // Column space: lane owns columns NS*lane + s (s < NS) so that its NS values are contiguous (128-bit LDS for NS = 2, 4).
 // Position space: lane owns positions lane + 32 t, so that sets with p <= 32 only touch slot 0.
@@ -714,8 +731,13 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
 // (rho^2 = G_jj - r.r = -1.2e-13 for a column SciPy's QR-based test accepts).  Leaves a in S[W.gs..].
 // Everything is passed and returned BY VALUE: a reference argument would force the caller's Slots / rho^2 / y_new into
 // local memory on the hot path (measured with the first, by-reference version: T2 stage +3.3 %, FA stage +3 %).
+#ifndef MET2_DSPACE_INLINE          // A/B switch (libmet2_inl.so): out of line (default) or inlined into the solver
+#define MET2_DSPACE_FN __noinline__
+#else
+#define MET2_DSPACE_FN __forceinline__
+#endif
 template <int NS>
-__device__ __noinline__ double2 dspace_candidate(int oT, int oGs, int oRs, int oIx, const double* __restrict__ DtR,
+__device__ MET2_DSPACE_FN double2 dspace_candidate(int oT, int oGs, int oRs, int oIx, const double* __restrict__ DtR,
                                                  int oMR, int mrows, int j, int p, int lane) {
     double a[NS];
     tmul<NS>(oT, oRs, p, lane, a);
@@ -753,10 +775,7 @@ __device__ __noinline__ double2 dspace_candidate(int oT, int oGs, int oRs, int o
 template <int NS, bool GSH>
 __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
                                          bool reg, double lam, int n, int mrows, int lane, int& status, int p0 = 0,
-                                         bool t_ready = false,
-                                         // the transposed dictionary [n][mrows] (global) and the signal offset in S: the
-                                         // D-space evaluation of a nearly dependent candidate (dspace_candidate)
-                                         const double* __restrict__ DtR = nullptr, int oMR = 0) {
+                                         bool t_ready = false) {
     const int itmax = 3 * n;
     auto Gat = [&](int r, int c) -> double { return GSH ? S[oG + r * ldg + c] : __ldg(Gg + r * ldg + c); };
     const int col0 = NS * lane;
@@ -811,14 +830,17 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         double rinv = rsqrt_fast(rho2);
         double ynew = (cj - s2) * rinv;
 #ifndef MET2_NO_DSPACE_RESCUE   // A/B timing switch only (libmet2_norescue.so); the product library always has the rescue
-        if (!reg && DtR && p > 0 && rho2 < 1e-10 * gjj) {
+        if (!reg && p > 0 && rho2 < 1e-10 * gjj) {
             // rho^2 = G_jj - r.r is below the rounding of its terms (nearly collinear long-T2 columns of the 96/100-bin
             // grids): the Gram form resolves rho^2/G_jj to ~1e-16, nnls.f accepts down to ~5e-27.  Rare, so out of line.
             __syncwarp();
-            const double2 qd = dspace_candidate<NS>(W.T, W.gs, W.rs, W.ix, DtR, oMR, mrows, j, p, lane);
-            rho2 = qd.x;
-            rinv = rsqrt_fast(rho2);
-            ynew = qd.y * rinv;
+            const double* DtR = *reinterpret_cast<const double* const*>(S + W.aux());
+            if (DtR) {
+                const double2 qd = dspace_candidate<NS>(W.T, W.gs, W.rs, W.ix, DtR, SI(W.aux() + 1, 0), mrows, j, p, lane);
+                rho2 = qd.x;
+                rinv = rsqrt_fast(rho2);
+                ynew = qd.y * rinv;
+            }
         }
 #endif
         // nnls.f: reject if the column is numerically dependent on P (unorm + |a_new|*0.01 == unorm, i.e.

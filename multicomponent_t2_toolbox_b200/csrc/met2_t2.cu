@@ -71,6 +71,10 @@ static int t2_check_cfg(const met2_t2_cfg* cfg) {
         return set_error(MET2_ERR_ARG, "met2_t2: unknown method %d", cfg->method);
     if (cfg->method == MET2_REG_LCURVE && (cfg->nLambda < 3 || cfg->nLambda > MET2_MAX_LAMBDAS))
         return set_error(MET2_ERR_ARG, "met2_t2: L-curve needs 3..%d lambdas", MET2_MAX_LAMBDAS);
+    // the kernel stages MET2_MAX_LAMBDAS grid values in shared memory and walks gi < nLambda
+    if (cfg->method == MET2_REG_GCV && (cfg->flags & MET2_T2_FLAG_GCV_GRID) &&
+        (cfg->nLambda < 1 || cfg->nLambda > MET2_MAX_LAMBDAS))
+        return set_error(MET2_ERR_ARG, "met2_t2: GCV grid needs 1..%d lambdas, got %d", MET2_MAX_LAMBDAS, cfg->nLambda);
     return MET2_OK;
 }
 
@@ -112,11 +116,11 @@ extern "C" int64_t met2_t2_workspace_bytes(int64_t V, const met2_t2_cfg* cfg) {
     return (int64_t)b + 256;
 }
 
-extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg,
-                           const double* dic, const double* dicT, const double* G, const double* kband,
-                           const double* lambdas, const double* logT2, const uint8_t* comp, double* fsol,
-                           double* est_signal, double* reg, double* maps, uint32_t* status, void* workspace,
-                           void* stream) {
+static int t2_fit_impl(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg,
+                       const double* dic, const double* dicT, const double* G, const double* kband,
+                       const double* lambdas, const double* logT2, const uint8_t* comp, const double* red_basis,
+                       const double* red_coef, double* fsol, double* est_signal, double* reg, double* maps,
+                       uint32_t* status, void* workspace, void* stream) {
     int rc = t2_check_cfg(cfg);
     if (rc) return rc;
     if (V < 0 || !sig || !fa_index || !dic || !dicT || !G || !logT2 || !comp || !fsol || !est_signal || !reg || !maps ||
@@ -125,6 +129,8 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     if (cfg->method != MET2_REG_NNLS && !kband)
         return set_error(MET2_ERR_ARG, "met2_t2_fit: regularised methods need kband (met2_gram_tables)");
     if (cfg->method == MET2_REG_LCURVE && !lambdas) return set_error(MET2_ERR_ARG, "met2_t2_fit: L-curve needs lambdas");
+    if (cfg->method == MET2_REG_GCV && (cfg->flags & MET2_T2_FLAG_GCV_GRID) && !lambdas)
+        return set_error(MET2_ERR_ARG, "met2_t2_fit: the GCV grid mode needs lambdas");
     if (V == 0) return MET2_OK;
     if (V > 0x7fffffffLL) return set_error(MET2_ERR_ARG, "met2_t2_fit: V too large for one call");
     cudaStream_t st = (cudaStream_t)stream;
@@ -133,6 +139,7 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
     A.sig = sig; A.fa_index = fa_index; A.V = V; A.cfg = *cfg;
     A.dic = dic; A.dicT = dicT; A.G = G; A.kband = kband; A.lambdas = lambdas; A.logT2 = logT2; A.comp = comp;
     A.fsol = fsol; A.est = est_signal; A.reg = reg; A.maps = maps; A.status = status;
+    A.red_basis = red_basis; A.red_coef = red_coef;
     unsigned char* w = reinterpret_cast<unsigned char*>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     A.hist = reinterpret_cast<int*>(w);        w += align256(sizeof(int) * (size_t)cfg->nA);
     A.cursor = reinterpret_cast<int*>(w);      w += align256(sizeof(int) * (size_t)cfg->nA);
@@ -190,4 +197,22 @@ extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V
         case MET2_REG_GCV: return t2_launch_gcv(A, g, st);
         default: return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit: method %d not implemented", cfg->method);
     }
+}
+
+extern "C" int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg,
+                           const double* dic, const double* dicT, const double* G, const double* kband,
+                           const double* lambdas, const double* logT2, const uint8_t* comp, double* fsol,
+                           double* est_signal, double* reg, double* maps, uint32_t* status, void* workspace,
+                           void* stream) {
+    return t2_fit_impl(sig, fa_index, V, cfg, dic, dicT, G, kband, lambdas, logT2, comp, nullptr, nullptr, fsol,
+                       est_signal, reg, maps, status, workspace, stream);
+}
+
+extern "C" int met2_t2_fit_echo(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg,
+                                const double* dic, const double* dicT, const double* G, const double* kband,
+                                const double* lambdas, const double* logT2, const uint8_t* comp,
+                                const double* red_basis, const double* red_coef, double* fsol, double* est_signal,
+                                double* reg, double* maps, uint32_t* status, void* workspace, void* stream) {
+    return t2_fit_impl(sig, fa_index, V, cfg, dic, dicT, G, kband, lambdas, logT2, comp, red_basis, red_coef, fsol,
+                       est_signal, reg, maps, status, workspace, stream);
 }

@@ -1,18 +1,26 @@
-// met2_t2_echo.cu — EXPERIMENTAL (opt-in, MET2_T2_FLAG_ECHO_SPACE): the X2 fit with its Tikhonov solves carried out in
-// ECHO SPACE.  Not on any default path; not yet run on a GPU (written at the end of round 1 with the GPU budget spent —
-// DESIGN.md §8 item 0).  Design evidence: tools/proto_dual_nnls.py / profiles/r01_proto_echo_space.txt (CPU): 0 of 2 000
-// support disagreements and spectra within 2.6e-11 of the unmodified reference inside the X2 search.
+// met2_t2_echo.cu — Tikhonov NNLS in REDUCED ECHO SPACE for a diagonal regularisation matrix (reg_matrix I and InvT2):
+// the X2 search (algorithms.py:211-233) and the fixed-lambda solve of T2SPARC (algorithms.py:262-269, motor...:138).
+// Selected with MET2_T2_FLAG_ECHO_SPACE; batched.Met2Plan sets the flag whenever the configuration is eligible.
 //
-// For a DIAGONAL regularisation matrix L = diag(l) (reg_matrix I and InvT2) and lam > 0 the Tikhonov problem
+// For L = diag(l) and lam > 0 the Tikhonov problem
 //     min_{x >= 0} |D x - b|^2 + lam |L x|^2,      Dt = D diag(1/l),  xt = l * x  (same sign pattern)
 // has, on a positive set P, the stationary point (push-through identity)
-//     v = (lam I_m + M_P)^-1 b,   M_P = sum_{j in P} dt_j dt_j^T   (m x m, independent of lam)
-//     zt_P = Dt_P^T v,            w_Z = lam Dt_Z^T v               (r = b - Dt_P zt_P = lam v)
+//     v = (lam I + M_P)^-1 b,   M_P = sum_{j in P} dt_j dt_j^T   (independent of lam)
+//     zt_P = Dt_P^T v,          w_Z = lam Dt_Z^T v               (r = b - Dt_P zt_P = lam v)
 // so ONE product g = Dt^T v gives the coefficients on P and the dual on Z, a column entering / leaving P is a rank-one
-// change of M_P, and a new lambda costs one m x m factorisation (m = 32: tri(32) = 528 doubles per warp instead of
-// tri(60) = 1 830, which pins t2_fit_kernel at 10 warps per SM).  With lam > 0 both acceptance tests of nnls.f pass
-// identically (a regularised column is never dependent; its entering coefficient is w_j / (lam (1 + dt_j^T A^-1 dt_j))
-// > 0), so the control flow is the main loop + the interpolation loop of Lawson-Hanson (algorithms.py:55-82 -> nnls.f).
+// change of M_P, and a new lambda costs one factorisation of an echo-space matrix instead of a p x p one (p up to 60).
+// With lam > 0 both acceptance tests of nnls.f pass identically (a regularised column is never dependent; its entering
+// coefficient is w_j / (lam (1 + dt_j^T A^-1 dt_j)) > 0), so the control flow is the main loop + the interpolation loop
+// of Lawson-Hanson (algorithms.py:55-82 -> nnls.f).
+//
+// REDUCED: the dictionary of one flip angle is numerically of rank ~20 (met2_basis.cu): D = U C with U: nTE x RD
+// orthonormal, C = U^T D: RD x nT2 (RD = 24), exact to the rounding of D's own entries.  Every quantity above then
+// lives in RD dimensions — b -> bt = U^T b, Dt -> Ct = C diag(1/l), M_P = Ct_P Ct_P^T (24 x 24) — and the part of b
+// outside range(U) only adds the constant |b - U bt|^2 to every residual.  Against the unreduced echo-space kernel of
+// round 2's first GPU call (32 x 32 factors): tri(24) = 300 instead of 528 doubles per factor, 3 instead of 4 diagonal
+// blocks per refactorisation, 24- instead of 32-step triangular products, and nTE no longer limited to 32.  CPU
+// prototype against voxels fitted by the unmodified reference (tools/proto_reduced_echo.py): 0 of 300 support
+// disagreements, spectra within 1.1e-12 (RD = 24 and 20; the Gram-domain kernel: 1.4e-9).
 //
 // The factor is the upper-triangular inverse Cholesky factor T, A^-1 = T T^T, A = lam I + M_P:
 //   new lambda     : rebuild_T_blocked (the FP64-tensor-core blocked factorisation of met2_nnls.cuh) on M_P + lam I
@@ -22,56 +30,44 @@
 //                    T' = T Q is a running sum along each ROW of T (one row per lane):
 //                        T'[r][j] = delta_j T[r][j] + q_j acc,   acc += T[r][j] u_j
 //                    (s = +1: h >= 1, no cancellation; s = -1: h_k >= 1 - u.u > 0, rebuilt from M_P if that fails).
-// Plain NNLS (lam = 0: the SSE of algorithms.py:213-214) stays in the Gram domain (nnls_gram).
+// The plain NNLS of X2 (lam = 0: the SSE of algorithms.py:213-214) stays in the Gram domain (nnls_gram), with its
+// right-hand side, residual and D-space candidate test taken in the same reduced space.
 #include "met2_t2_impl.cuh"
 
 namespace met2 {
 
-constexpr int EC_M = 32;              // echoes (rows of the echo-space system); nTE <= 32, padded with zero rows
-constexpr int EC_LDD = 34;            // row stride of the staged Dt table: even (16-byte rows for 128-bit loads with lane =
-                                      // row: a quarter warp covers all 32 banks) and conflict-free for lane = echo
-constexpr int EC_NCOL = 64;           // columns (nT2 <= 64), zero rows beyond nT2
-
-// per-warp shared memory (doubles): Slots<2>(pmax 32) | M_P packed lower (528) | signal (64) | v (32) | d (32) |
-// Brent-best snapshot of xt (64)
-__host__ __device__ __forceinline__ int echo_warp_doubles() {
-    return (Slots<2>::doubles(EC_M) + tri(EC_M) + 64 + 32 + 32 + 64 + 31) & ~31;
-}
-// CTA tables (doubles): G [n][ldg] | Dt [64][33] | M_full packed (528) | l (64) | 1/l (64) | logT2 (64) | comp (8)
-__host__ __device__ __forceinline__ int echo_table_doubles(int n) {
-    return (n * t2_ldg(n) + EC_NCOL * EC_LDD + tri(EC_M) + 3 * 64 + 8 + 31) & ~31;
-}
+constexpr int RD = MET2_ECHO_RANK;    // rows of the reduced system (3 DMMA blocks of 8)
+constexpr int EC_LDD = RD + 2;        // row stride of the staged Ct table [column][row]: even (16-byte rows for 128-bit
+                                      // loads with lane = column: a quarter warp covers all 32 banks) and conflict-free
+                                      // for lane = row
+constexpr int EC_NCOL = 64;           // columns of the X2 kernel (nT2 <= 64), zero rows beyond nT2
 
 struct EchoOff {
-    int Dt, Mp, B, V, D;   // offsets into S
+    int Ct, Mp, B, V, D;   // offsets into S: staged Ct table; per warp: M_P packed lower, bt (RD), v (RD), d (RD)
 };
 
-// v = T (T^T b), g = Dt^T v.  lane = position / echo for the triangular products, lane + 32 s = column for g (NC column
-// slots per lane: nT2 <= 32 NC).
+// per-warp shared memory of the X2 kernel (doubles): Slots<2>(pmax RD) | M_P packed lower tri(RD) | raw signal (64) |
+// bt (32) | v (32) | d (32) | Brent-best snapshot of xt (64)
+__host__ __device__ __forceinline__ int echo_warp_doubles() {
+    return (Slots<2>::doubles(RD) + tri(RD) + 64 + 32 + 32 + 32 + 64 + 31) & ~31;
+}
+// CTA tables (doubles): G [n][ldg] | Ct [64][EC_LDD] | U [m][RD] | M_full packed tri(RD) | l (64) | 1/l (64) | logT2 (64) |
+// comp (8)
+__host__ __device__ __forceinline__ int echo_table_doubles(int n, int m) {
+    return (n * t2_ldg(n) + EC_NCOL * EC_LDD + m * RD + tri(RD) + 3 * 64 + 8 + 31) & ~31;
+}
+
+// g = Ct^T v for v at S[oV .. oV + RD): lane + 32 s = column (NC column slots per lane: nT2 <= 32 NC).
 template <int NC>
-__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[NC], double& y,
-                                           bool& y_ok) {
-    // y = T^T b: fresh after a refactorisation, otherwise carried through the rank-one updates (echo_change)
-    if (!y_ok) {
-        double yy[1];
-        tmul_transposed<1>(W.T, O.B, EC_M, lane, yy);
-        y = yy[0];
-        y_ok = true;
-    }
-    double v[1];
-    S[W.rs + lane] = y;
-    __syncwarp();
-    tmul<1>(W.T, W.rs, EC_M, lane, v);
-    S[O.V + lane] = v[0];
-    __syncwarp();
+__device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, double (&g)[NC]) {
     double g0[NC], g1[NC];
 #pragma unroll
     for (int s = 0; s < NC; ++s) g0[s] = g1[s] = 0.0;
-    const int r0 = O.Dt + lane * EC_LDD;
+    const int r0 = O.Ct + lane * EC_LDD;
 #pragma unroll 1
-    for (int e = 0; e < EC_M; e += 2) {
+    for (int e = 0; e < RD; e += 2) {
         double vv[2];
-        lds_vec<2>(O.V + e, vv);
+        lds_vec<2>(oV + e, vv);
 #pragma unroll
         for (int s = 0; s < NC; ++s) {
             double dd[2];
@@ -82,6 +78,26 @@ __device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, 
     }
 #pragma unroll
     for (int s = 0; s < NC; ++s) g[s] = g0[s] + g1[s];
+}
+
+// v = T (T^T bt), g = Ct^T v.  lane = position / row for the triangular products.
+template <int NC>
+__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[NC], double& y,
+                                           bool& y_ok) {
+    // y = T^T bt: fresh after a refactorisation, otherwise carried through the rank-one updates (echo_change)
+    if (!y_ok) {
+        double yy[1];
+        tmul_transposed<1>(W.T, O.B, RD, lane, yy);
+        y = yy[0];
+        y_ok = true;
+    }
+    double v[1];
+    if (lane < RD) S[W.rs + lane] = y;
+    __syncwarp();
+    tmul<1>(W.T, W.rs, RD, lane, v);
+    if (lane < RD) S[O.V + lane] = v[0];
+    __syncwarp();
+    echo_gprod<NC>(O, O.V, lane, g);
     __syncwarp();
 }
 
@@ -94,20 +110,20 @@ __device__ __forceinline__ bool echo_refactor(const Slots<2>& W, const EchoOff& 
         return a;
     };
     __syncwarp();
-    return rebuild_T_blocked<2>(W, Aent, EC_M, lane);
+    return rebuild_T_blocked<2>(W, Aent, RD, lane);
 }
 
-// M_P += sgn d d^T on the packed lower triangle (row = lane), d = column j of the staged Dt table; leaves d in S[O.D..].
+// M_P += sgn d d^T on the packed lower triangle (row = lane), d = column j of the staged Ct table; leaves d in S[O.D..].
 __device__ __forceinline__ void echo_mp_rank1(const EchoOff& O, int j, double sgn, int lane) {
-    const double d = S[O.Dt + j * EC_LDD + lane];
+    const double d = (lane < RD) ? S[O.Ct + j * EC_LDD + lane] : 0.0;
     __syncwarp();
-    S[O.D + lane] = d;
+    if (lane < RD) S[O.D + lane] = d;
     __syncwarp();
-    const int row = O.Mp + tri(lane);
-    const double sd = sgn * d;
+    if (lane < RD) {
+        const int row = O.Mp + tri(lane);
+        const double sd = sgn * d;
 #pragma unroll 1
-    for (int c = 0; c < EC_M; ++c) {
-        if (c <= lane) S[row + c] = fma(sd, S[O.D + c], S[row + c]);
+        for (int c = 0; c <= lane; ++c) S[row + c] = fma(sd, S[O.D + c], S[row + c]);
     }
     __syncwarp();
 }
@@ -118,7 +134,7 @@ __device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O,
     echo_mp_rank1(O, j, sgn, lane);
     // ---- u = T^T d, prefix sums of u^2
     double u[1];
-    tmul_transposed<1>(W.T, O.D, EC_M, lane, u);
+    tmul_transposed<1>(W.T, O.D, RD, lane, u);
     double tau[1] = {u[0] * u[0]};
     warp_scan_positions<1>(tau, lane);
     const double h = fma(sgn, tau[0], 1.0);
@@ -139,21 +155,21 @@ __device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O,
         warp_scan_positions<1>(e, lane);
         y = fma(q, e[0] - own, delta * y);
     }
-    S[W.gs + lane] = delta;
-    S[W.gs + 32 + lane] = q;
-    S[W.rs + lane] = u[0];
+    if (lane < RD) {
+        S[W.gs + lane] = delta;
+        S[W.gs + 32 + lane] = q;
+        S[W.rs + lane] = u[0];
+    }
     __syncwarp();
     // ---- T' = T Q, one row of T per lane (row r has entries in columns j >= r)
-    {
+    if (lane < RD) {
         double acc = 0.0;
 #pragma unroll 1
-        for (int c = 0; c < EC_M; ++c) {
-            if (c >= lane) {
-                const int a = W.T + tri(c) + lane;
-                const double t = S[a];
-                S[a] = fma(S[W.gs + c], t, S[W.gs + 32 + c] * acc);
-                acc = fma(t, S[W.rs + c], acc);
-            }
+        for (int c = lane; c < RD; ++c) {
+            const int a = W.T + tri(c) + lane;
+            const double t = S[a];
+            S[a] = fma(S[W.gs + c], t, S[W.gs + 32 + c] * acc);
+            acc = fma(t, S[W.rs + c], acc);
         }
     }
     __syncwarp();
@@ -173,7 +189,7 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
     bool secondary_first = __any_sync(FULL_MASK, inP != 0u);
     bool have_g = false;   // g is the solve for the current set (left by an accepted interpolation loop)
     double g[NC];
-    double y = 0.0;        // y = T^T b of the current factor (lane = position), valid when y_ok
+    double y = 0.0;        // y = T^T bt of the current factor (lane = position), valid when y_ok
     bool y_ok = false;
     while (true) {
         if (!secondary_first) {
@@ -268,64 +284,187 @@ __device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, i
     }
 }
 
-// fit = Dt xt (= D x) with lane = echo, SSE = sum (fit - b)^2.  xt is read from S[oX + 0..n) (column space).
-__device__ __forceinline__ double echo_fit_sse(int oX, const EchoOff& O, int n, int lane, double& fit) {
+// ft = Ct xt (reduced fit, lane = row; left in S[oF .. oF + RD) when oF >= 0) and |ft - bt|^2.  xt is read from
+// S[oX + 0..n) (column space).
+__device__ __forceinline__ double echo_fit_sse(int oX, const EchoOff& O, int n, int lane, int oF) {
     double f0 = 0.0, f1 = 0.0;
-    int j = 0;
+    if (lane < RD) {
+        int j = 0;
 #pragma unroll 1
-    for (; j + 1 < n; j += 2) {
-        f0 = fma(S[O.Dt + j * EC_LDD + lane], S[oX + j], f0);
-        f1 = fma(S[O.Dt + (j + 1) * EC_LDD + lane], S[oX + j + 1], f1);
+        for (; j + 1 < n; j += 2) {
+            f0 = fma(S[O.Ct + j * EC_LDD + lane], S[oX + j], f0);
+            f1 = fma(S[O.Ct + (j + 1) * EC_LDD + lane], S[oX + j + 1], f1);
+        }
+        if (j < n) f0 = fma(S[O.Ct + j * EC_LDD + lane], S[oX + j], f0);
     }
-    if (j < n) f0 = fma(S[O.Dt + j * EC_LDD + lane], S[oX + j], f0);
-    fit = f0 + f1;
-    const double dd = fit - S[O.B + lane];
+    const double ft = f0 + f1;
+    if (oF >= 0 && lane < RD) S[oF + lane] = ft;
+    const double dd = (lane < RD) ? ft - S[O.B + lane] : 0.0;
     return warp_sum(dd * dd);
 }
 
-constexpr int ECHO_MAX_THREADS = 416;   // 13 warps: (227 KB - 52 KB of tables) / 12.8 KB per warp at nT2 = 60
+// Project the normalised signal S[oM .. oM + m) onto the reduced basis U ([m][RD] at S[oU..]): bt -> S[oB .. oB + RD),
+// and return |b - U bt|^2, the part of every residual that no spectrum can reach.
+template <int ME>
+__device__ __forceinline__ double echo_project(int oU, int oM, int oB, int m, int lane) {
+    double b0 = 0.0, b1 = 0.0;
+    if (lane < RD) {
+        int k = 0;
+#pragma unroll 1
+        for (; k + 1 < m; k += 2) {
+            b0 = fma(S[oU + k * RD + lane], S[oM + k], b0);
+            b1 = fma(S[oU + (k + 1) * RD + lane], S[oM + k + 1], b1);
+        }
+        if (k < m) b0 = fma(S[oU + k * RD + lane], S[oM + k], b0);
+        S[oB + lane] = b0 + b1;
+    }
+    __syncwarp();
+    double perp = 0.0;
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        const int k = lane + 32 * u;
+        if (k < m) {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll 1
+            for (int e = 0; e < RD; e += 2) {
+                a0 = fma(S[oU + k * RD + e], S[oB + e], a0);
+                a1 = fma(S[oU + k * RD + e + 1], S[oB + e + 1], a1);
+            }
+            const double r = S[oM + k] - (a0 + a1);
+            perp = fma(r, r, perp);
+        }
+    }
+    return warp_sum(perp);
+}
 
-__global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args A) {
-    __shared__ int s_tile, s_next, s_badL;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n = A.cfg.nT2, m = A.cfg.nTE;
-    const int ldg = t2_ldg(n);
-    const int oG = 0;
-    const int oDt = oG + n * ldg;
-    const int oMf = oDt + EC_NCOL * EC_LDD;
-    const int oL = oMf + tri(EC_M);
-    const int oIL = oL + 64;
-    const int oLogT2 = oIL + 64;
-    unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + 64);
-    const int wbase = echo_table_doubles(n) + warp * echo_warp_doubles();
-    Slots<2> W;
-    W.carve(wbase, EC_M);
-    EchoOff O;
-    O.Dt = oDt;
-    O.Mp = wbase + Slots<2>::doubles(EC_M);
-    const int oM = O.Mp + tri(EC_M);
-    O.B = oM;
-    O.V = oM + 64;
-    O.D = O.V + 32;
-    const int oSnap = O.D + 32;
+// fit[u] (echo k = lane + 32 u) = sum_e U[k][e] ft[e] for ft at S[oF .. oF + RD): the fitted signal D x in echo space.
+template <int ME>
+__device__ __forceinline__ void echo_expand(int oU, int oF, int m, int lane, double (&fit)[ME]) {
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        const int k = lane + 32 * u;
+        double a0 = 0.0, a1 = 0.0;
+        if (k < m) {
+#pragma unroll 1
+            for (int e = 0; e < RD; e += 2) {
+                a0 = fma(S[oU + k * RD + e], S[oF + e], a0);
+                a1 = fma(S[oU + k * RD + e + 1], S[oF + e + 1], a1);
+            }
+        }
+        fit[u] = a0 + a1;
+    }
+}
 
-    if (threadIdx.x == 0) s_badL = 0;
-    __syncthreads();
-    // l = diag(L) from the row-band form (kband rows 5..9: kband[5 + d][r] = L[r][r + d - 2]); every other band must be 0
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) {
+// Outputs of one voxel (motor...:153-155, 443-472): fsol = x km, Est_Signal = (D x) km, reg, maps.  x in column space at
+// S[oX .. oX + n), column = lane + 32 s.
+template <int NC, int ME>
+__device__ __forceinline__ void echo_outputs(const T2Args& A, long long v, int oX, int oLogT2, const unsigned char* scomp,
+                                             int n, int m, int lane, unsigned st, double km, double regv,
+                                             const double (&fit)[ME]) {
+    const bool fitted = !(st & MET2_ST_SKIPPED);
+    const double kmo = fitted ? km : 0.0;
+    double xk[NC];
+    double vt = 0.0;
+#pragma unroll
+    for (int s = 0; s < NC; ++s) {
+        const int col = lane + 32 * s;
+        xk[s] = (col < n && fitted) ? S[oX + col] * kmo : 0.0;
+        vt += xk[s];
+        if (col < n) A.fsol[v * n + col] = xk[s];
+    }
+#pragma unroll
+    for (int u = 0; u < ME; ++u) {
+        const int e = lane + 32 * u;
+        if (e < m) A.est[v * m + e] = fitted ? fit[u] * kmo : 0.0;
+    }
+    vt = warp_sum(vt) + 1.0e-16;
+    double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
+#pragma unroll
+    for (int s = 0; s < NC; ++s) {
+        const int col = lane + 32 * s;
+        if (col < n) {
+            const double xn = xk[s] / vt;
+            const unsigned char cm = scomp[col];
+            if (cm & 1) {
+                sm += xn;
+                lm += xn * S[oLogT2 + col];
+            }
+            if (cm & 2) {
+                stt += xn;
+                lt += xn * S[oLogT2 + col];
+            }
+            if (cm & 4) sc += xn;
+        }
+    }
+    sm = warp_sum(sm);
+    stt = warp_sum(stt);
+    sc = warp_sum(sc);
+    lm = warp_sum(lm);
+    lt = warp_sum(lt);
+    if (lane == 0) {
+        double* mp = A.maps + v * 6;
+        mp[0] = sm;
+        mp[1] = stt;
+        mp[2] = sc;
+        mp[3] = exp(lm / (sm + 1.0e-16));
+        mp[4] = exp(lt / (stt + 1.0e-16));
+        mp[5] = vt;
+        A.reg[v] = fitted ? regv : 0.0;
+        A.status[v] = st;
+    }
+    __syncwarp();
+}
+
+// l = diag(L) from the row-band form (kband rows 5..9: kband[5 + d][r] = L[r][r + d - 2]); every other band must be 0.
+__device__ __forceinline__ void echo_stage_diag(const T2Args& A, int ncol, int n, int oL, int oIL, int oLogT2,
+                                                unsigned char* scomp, int* s_badL) {
+    for (int i = threadIdx.x; i < ncol; i += blockDim.x) {
         double l = 1.0;
         if (i < n) {
             l = A.kband[7 * n + i];
             bool bad = !(l > 0.0) || !(l < 1e300);
             for (int d = 0; d < 5; ++d)
                 if (d != 2 && A.kband[(5 + d) * n + i] != 0.0) bad = true;
-            if (bad) atomicOr(&s_badL, 1);
+            if (bad) atomicOr(s_badL, 1);
         }
         S[oL + i] = l;
         S[oIL + i] = 1.0 / l;
         S[oLogT2 + i] = (i < n) ? A.logT2[i] : 0.0;
         if (i < n) scomp[i] = A.comp[i];
     }
+}
+
+constexpr int ECHO_MAX_THREADS = 512;   // 16 warps at 128 registers
+
+template <int ME>
+__global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args A) {
+    __shared__ int s_tile, s_next, s_badL;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = A.cfg.nT2, m = A.cfg.nTE;
+    const int ldg = t2_ldg(n);
+    const int oG = 0;
+    const int oCt = oG + n * ldg;
+    const int oU = oCt + EC_NCOL * EC_LDD;
+    const int oMf = oU + m * RD;
+    const int oL = oMf + tri(RD);
+    const int oIL = oL + 64;
+    const int oLogT2 = oIL + 64;
+    unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + 64);
+    const int wbase = echo_table_doubles(n, m) + warp * echo_warp_doubles();
+    Slots<2> W;
+    W.carve(wbase, RD);
+    EchoOff O;
+    O.Ct = oCt;
+    O.Mp = wbase + Slots<2>::doubles(RD);
+    const int oM = O.Mp + tri(RD);
+    O.B = oM + 64;
+    O.V = O.B + 32;
+    O.D = O.V + 32;
+    const int oSnap = O.D + 32;
+
+    if (threadIdx.x == 0) s_badL = 0;
+    __syncthreads();
+    echo_stage_diag(A, 64, n, oL, oIL, oLogT2, scomp, &s_badL);
     const int ntiles = A.counters[0];
 
     while (true) {
@@ -340,33 +479,34 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
         const bool badL = (s_badL != 0);
         const int fa = A.tile_fa[tile];
         const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
-        const double* D = A.dic + (size_t)fa * m * n;
-        const double* Dtg = A.dicT + (size_t)fa * n * m;
+        const double* Cg = A.red_coef + (size_t)fa * n * RD;     // [n][RD]: C[e][j] at [j][e]
         {
             const double* Gg = A.G + (size_t)fa * n * n;
             for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
                 const int r = i / n;
                 S[oG + r * ldg + (i - r * n)] = __ldg(Gg + i);
             }
-            // Dt[j][e] = D[e][j] / l_j, zero rows / echoes beyond (n, m)
+            // Ct[j][e] = C[e][j] / l_j, zero rows beyond n and in the two pad columns
             for (int i = threadIdx.x; i < EC_NCOL * EC_LDD; i += blockDim.x) {
                 const int j = i / EC_LDD, e = i - j * EC_LDD;
-                S[oDt + i] = (j < n && e < m) ? __ldg(Dtg + j * m + e) * S[oIL + j] : 0.0;
+                S[oCt + i] = (j < n && e < RD) ? __ldg(Cg + j * RD + e) * S[oIL + j] : 0.0;
             }
+            const double* Ug = A.red_basis + (size_t)fa * m * RD;
+            for (int i = threadIdx.x; i < m * RD; i += blockDim.x) S[oU + i] = __ldg(Ug + i);
         }
         __syncthreads();
-        // M_full = Dt^T-table product over ALL columns, packed lower triangle
-        for (int i = threadIdx.x; i < tri(EC_M); i += blockDim.x) {
+        // M_full = Ct-table product over ALL columns, packed lower triangle
+        for (int i = threadIdx.x; i < tri(RD); i += blockDim.x) {
             int r = 0;
             while (tri(r + 1) <= i) ++r;
             const int c = i - tri(r);
             double a0 = 0.0, a1 = 0.0;
             int j = 0;
             for (; j + 1 < n; j += 2) {
-                a0 = fma(S[oDt + j * EC_LDD + r], S[oDt + j * EC_LDD + c], a0);
-                a1 = fma(S[oDt + (j + 1) * EC_LDD + r], S[oDt + (j + 1) * EC_LDD + c], a1);
+                a0 = fma(S[oCt + j * EC_LDD + r], S[oCt + j * EC_LDD + c], a0);
+                a1 = fma(S[oCt + (j + 1) * EC_LDD + r], S[oCt + (j + 1) * EC_LDD + c], a1);
             }
-            if (j < n) a0 = fma(S[oDt + j * EC_LDD + r], S[oDt + j * EC_LDD + c], a0);
+            if (j < n) a0 = fma(S[oCt + j * EC_LDD + r], S[oCt + j * EC_LDD + c], a0);
             S[oMf + i] = a0 + a1;
         }
         __syncthreads();
@@ -377,23 +517,47 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
             it = __shfl_sync(FULL_MASK, it, 0);
             if (it >= tcnt) break;
             const long long v = A.perm[tstart + it];
-            unsigned st = load_signal<1>(A.sig, v, m, oM, lane);
+            unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             const int fav = A.fa_index[v];
             const bool normalise = !(A.cfg.flags & MET2_T2_FLAG_NO_NORMALISE);
             const double km = normalise ? S[oM] : 1.0;
             if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
             if (!st && badL) st = MET2_ST_SKIPPED | MET2_ST_ECHO_BAD_L;
-            double regv = 0.0, fit = 0.0;
+            double regv = 0.0;
+            double fit[ME];
+#pragma unroll
+            for (int u = 0; u < ME; ++u) fit[u] = 0.0;
             if (!st) {
                 __syncwarp();
-                S[oM + lane] = (lane < m) ? S[oM + lane] / km : 0.0;
+#pragma unroll
+                for (int u = 0; u < ME; ++u) {
+                    const int e = lane + 32 * u;
+                    if (e < m) S[oM + e] = S[oM + e] / km;
+                }
                 __syncwarp();
-                // ---- plain NNLS in the Gram domain -> SSE (algorithms.py:213-214)
-                compute_c<2>(W, D, oM, m, n, lane);
+                const double perp = echo_project<ME>(oU, oM, O.B, m, lane);
+                // ---- plain NNLS in the Gram domain -> SSE (algorithms.py:213-214): c = D^T b = l * (Ct^T bt)
+                {
+                    double g[2];
+                    echo_gprod<2>(O, O.B, lane, g);
+#pragma unroll
+                    for (int s = 0; s < 2; ++s) {
+                        const int j = lane + 32 * s;
+                        if (j < n) S[W.cc + j] = g[s] * S[oL + j];
+                    }
+                    __syncwarp();
+                }
+                set_dspace<2>(W, Cg, O.B, lane);     // candidate test in the reduced space: rows of C, right-hand side bt
                 int nst = 0;
-                int p = nnls_gram<2, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, 0, false, Dtg, oM);
-                double fit1[1];
-                const double SSE = fit_and_sse<2, 1>(W, Dtg, oM, m, p, lane, fit1);
+                (void)nnls_gram<2, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, RD, lane, nst, 0, false);
+                // xt0 = l * x0 -> column space; SSE = |Ct xt0 - bt|^2 + |b_perp|^2
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int j = lane + 32 * s;
+                    S[oSnap + j] = (j < n) ? S[W.xc + j] * S[oL + j] : 0.0;
+                }
+                __syncwarp();
+                const double SSE = echo_fit_sse(oSnap, O, n, lane, -1) + perp;
                 if (SSE == 0.0) st |= MET2_ST_SSE_ZERO;
                 // ---- starting set of the first Tikhonov solve
                 Brent B;
@@ -413,18 +577,18 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                             inP |= 1u << s;
                         }
                     }
-                    for (int i = lane; i < tri(EC_M); i += 32) S[O.Mp + i] = S[oMf + i];
+                    for (int i = lane; i < tri(RD); i += 32) S[O.Mp + i] = S[oMf + i];
                     block_drop = true;
                 } else {
                     // the plain solution's support and coefficients (scaled); M_P by rank-one terms
-                    for (int i = lane; i < tri(EC_M); i += 32) S[O.Mp + i] = 0.0;
+                    for (int i = lane; i < tri(RD); i += 32) S[O.Mp + i] = 0.0;
                     __syncwarp();
 #pragma unroll
                     for (int s = 0; s < 2; ++s) {
                         const int j = lane + 32 * s;
-                        const double xv = (j < n) ? S[W.xc + j] : 0.0;
+                        const double xv = (j < n) ? S[oSnap + j] : 0.0;
                         if (xv > 0.0) {
-                            x[s] = xv * S[oL + j];
+                            x[s] = xv;
                             inP |= 1u << s;
                         }
                     }
@@ -444,7 +608,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
 #pragma unroll
                     for (int s = 0; s < 2; ++s) S[W.xc + lane + 32 * s] = x[s];
                     __syncwarp();
-                    const double sse = echo_fit_sse(W.xc, O, n, lane, fit);
+                    const double sse = echo_fit_sse(W.xc, O, n, lane, -1) + perp;
                     const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
                     const double lam_eval = lam;
                     const bool more = B.feed(cost, lam);
@@ -458,16 +622,11 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                     if (!more) break;
                 }
                 lam = B.xf;
-                // ---- hand out the best solution: x = xt / l
+                // ---- hand out the best solution: fitted signal U (Ct xt), x = xt / l
                 __syncwarp();
-#pragma unroll
-                for (int s = 0; s < 2; ++s) {
-                    const int j = lane + 32 * s;
-                    S[W.xc + j] = S[oSnap + j];
-                }
+                (void)echo_fit_sse(oSnap, O, n, lane, O.V);
                 __syncwarp();
-                (void)echo_fit_sse(W.xc, O, n, lane, fit);
-                __syncwarp();
+                echo_expand<ME>(oU, O.V, m, lane, fit);
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     const int j = lane + 32 * s;
@@ -478,95 +637,49 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                 if (nst || (est & 1)) st |= MET2_ST_ITMAX;
                 if (est & 2) st |= MET2_ST_NOT_PD;
             }
-            // ---- outputs: fsol = x*km, Est_Signal = (D x)*km, reg, maps (motor...:153-155, 443-472)
-            const bool fitted = !(st & MET2_ST_SKIPPED);
-            const double kmo = fitted ? km : 0.0;
-            double xk[2];
-            double vt = 0.0;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int col = 2 * lane + s;
-                xk[s] = (col < n && fitted) ? S[W.xc + col] * kmo : 0.0;
-                vt += xk[s];
-                if (col < n) A.fsol[v * n + col] = xk[s];
-            }
-            if (lane < m) A.est[v * m + lane] = fitted ? fit * kmo : 0.0;
-            vt = warp_sum(vt) + 1.0e-16;
-            double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int col = 2 * lane + s;
-                if (col < n) {
-                    const double xn = xk[s] / vt;
-                    const unsigned char cm = scomp[col];
-                    if (cm & 1) {
-                        sm += xn;
-                        lm += xn * S[oLogT2 + col];
-                    }
-                    if (cm & 2) {
-                        stt += xn;
-                        lt += xn * S[oLogT2 + col];
-                    }
-                    if (cm & 4) sc += xn;
-                }
-            }
-            sm = warp_sum(sm);
-            stt = warp_sum(stt);
-            sc = warp_sum(sc);
-            lm = warp_sum(lm);
-            lt = warp_sum(lt);
-            if (lane == 0) {
-                double* mp = A.maps + v * 6;
-                mp[0] = sm;
-                mp[1] = stt;
-                mp[2] = sc;
-                mp[3] = exp(lm / (sm + 1.0e-16));
-                mp[4] = exp(lt / (stt + 1.0e-16));
-                mp[5] = vt;
-                A.reg[v] = fitted ? regv : 0.0;
-                A.status[v] = st;
-            }
-            __syncwarp();
+            echo_outputs<2, ME>(A, v, W.xc, oLogT2, scomp, n, m, lane, st, km, regv, fit);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------- fixed-lambda Tikhonov
-// T2SPARC (algorithms.py:262-269 with reg = 1.8, motor...:138) in echo space, nT2 <= 32 NC (the reference's 96 bins:
-// NC = 3).  One solve per voxel from the empty set: the factor of lam I is T = I / sqrt(lam), every entering / leaving
-// column is one rank-one update of the 32 x 32 factor — no Gram matrix, no n x n factor (the Gram-domain kernel keeps
-// tri(96) = 4 656 doubles per voxel and runs at three warps per SM).
-// per-warp shared memory (doubles): Slots<2>(pmax 32) | M_P (528) | signal (64) | v (32) | d (32) | x column space (32 NC)
+// T2SPARC (algorithms.py:262-269 with reg = 1.8, motor...:138) in reduced echo space, nT2 <= 32 NC (the reference's 96
+// bins: NC = 3).  One solve per voxel from the empty set: the factor of lam I is T = I / sqrt(lam), every entering /
+// leaving column is one rank-one update of the RD x RD factor — no Gram matrix, no n x n factor (the Gram-domain
+// kernel keeps tri(96) = 4 656 doubles per voxel and runs at three warps per SM).
+// per-warp shared memory (doubles): Slots<2>(pmax RD) | M_P tri(RD) | raw signal (64) | bt (32) | v (32) | d (32) |
+// x column space (32 NC)
 template <int NC>
 __host__ __device__ __forceinline__ int echo_tik_warp_doubles() {
-    return (Slots<2>::doubles(EC_M) + tri(EC_M) + 64 + 32 + 32 + 32 * NC + 31) & ~31;
+    return (Slots<2>::doubles(RD) + tri(RD) + 64 + 32 + 32 + 32 + 32 * NC + 31) & ~31;
 }
-// CTA tables (doubles): Dt [32 NC][33] | l | 1/l | logT2 (32 NC each) | comp
+// CTA tables (doubles): Ct [32 NC][EC_LDD] | U [m][RD] | l | 1/l | logT2 (32 NC each) | comp
 template <int NC>
-__host__ __device__ __forceinline__ int echo_tik_table_doubles() {
-    return (32 * NC * EC_LDD + 3 * 32 * NC + (32 * NC + 7) / 8 + 31) & ~31;
+__host__ __device__ __forceinline__ int echo_tik_table_doubles(int m) {
+    return (32 * NC * EC_LDD + m * RD + 3 * 32 * NC + (32 * NC + 7) / 8 + 31) & ~31;
 }
 
-template <int NC>
+template <int NC, int ME>
 __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args A) {
     __shared__ int s_tile, s_next, s_badL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
     constexpr int NCOL = 32 * NC;
-    const int oDt = 0;
-    const int oL = oDt + NCOL * EC_LDD;
+    const int oCt = 0;
+    const int oU = oCt + NCOL * EC_LDD;
+    const int oL = oU + m * RD;
     const int oIL = oL + NCOL;
     const int oLogT2 = oIL + NCOL;
     unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + NCOL);
-    const int wbase = echo_tik_table_doubles<NC>() + warp * echo_tik_warp_doubles<NC>();
+    const int wbase = echo_tik_table_doubles<NC>(m) + warp * echo_tik_warp_doubles<NC>();
     Slots<2> W;
-    W.carve(wbase, EC_M);
+    W.carve(wbase, RD);
     EchoOff O;
-    O.Dt = oDt;
-    O.Mp = wbase + Slots<2>::doubles(EC_M);
-    const int oM = O.Mp + tri(EC_M);
-    O.B = oM;
-    O.V = oM + 64;
+    O.Ct = oCt;
+    O.Mp = wbase + Slots<2>::doubles(RD);
+    const int oM = O.Mp + tri(RD);
+    O.B = oM + 64;
+    O.V = O.B + 32;
     O.D = O.V + 32;
     const int oX = O.D + 32;
     const double lam = A.cfg.lambda_fixed;
@@ -574,20 +687,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
 
     if (threadIdx.x == 0) s_badL = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < NCOL; i += blockDim.x) {
-        double l = 1.0;
-        if (i < n) {
-            l = A.kband[7 * n + i];
-            bool bad = !(l > 0.0) || !(l < 1e300);
-            for (int d = 0; d < 5; ++d)
-                if (d != 2 && A.kband[(5 + d) * n + i] != 0.0) bad = true;
-            if (bad) atomicOr(&s_badL, 1);
-        }
-        S[oL + i] = l;
-        S[oIL + i] = 1.0 / l;
-        S[oLogT2 + i] = (i < n) ? A.logT2[i] : 0.0;
-        if (i < n) scomp[i] = A.comp[i];
-    }
+    echo_stage_diag(A, NCOL, n, oL, oIL, oLogT2, scomp, &s_badL);
     const int ntiles = A.counters[0];
 
     while (true) {
@@ -602,11 +702,13 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
         const bool badL = (s_badL != 0) || !(lam > 0.0);
         const int fa = A.tile_fa[tile];
         const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
-        const double* Dtg = A.dicT + (size_t)fa * n * m;
+        const double* Cg = A.red_coef + (size_t)fa * n * RD;
         for (int i = threadIdx.x; i < NCOL * EC_LDD; i += blockDim.x) {
             const int j = i / EC_LDD, e = i - j * EC_LDD;
-            S[oDt + i] = (j < n && e < m) ? __ldg(Dtg + j * m + e) * S[oIL + j] : 0.0;
+            S[oCt + i] = (j < n && e < RD) ? __ldg(Cg + j * RD + e) * S[oIL + j] : 0.0;
         }
+        const double* Ug = A.red_basis + (size_t)fa * m * RD;
+        for (int i = threadIdx.x; i < m * RD; i += blockDim.x) S[oU + i] = __ldg(Ug + i);
         __syncthreads();
 
         while (true) {
@@ -615,23 +717,30 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
             it = __shfl_sync(FULL_MASK, it, 0);
             if (it >= tcnt) break;
             const long long v = A.perm[tstart + it];
-            unsigned st = load_signal<1>(A.sig, v, m, oM, lane);
+            unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             const int fav = A.fa_index[v];
             const bool normalise = !(A.cfg.flags & MET2_T2_FLAG_NO_NORMALISE);
             const double km = normalise ? S[oM] : 1.0;
             if (!st && (!(km > 0.0) || fav < 0 || fav >= A.cfg.nA)) st = MET2_ST_SKIPPED;
             if (!st && badL) st = MET2_ST_SKIPPED | MET2_ST_ECHO_BAD_L;
-            double fit = 0.0;
+            double fit[ME];
+#pragma unroll
+            for (int u = 0; u < ME; ++u) fit[u] = 0.0;
             if (!st) {
                 __syncwarp();
-                S[oM + lane] = (lane < m) ? S[oM + lane] / km : 0.0;
+#pragma unroll
+                for (int u = 0; u < ME; ++u) {
+                    const int e = lane + 32 * u;
+                    if (e < m) S[oM + e] = S[oM + e] / km;
+                }
                 // empty set: M_P = 0, T = I / sqrt(lam)
-                for (int i = lane; i < tri(EC_M); i += 32) {
+                for (int i = lane; i < tri(RD); i += 32) {
                     S[O.Mp + i] = 0.0;
                     S[W.T + i] = 0.0;
                 }
                 __syncwarp();
-                S[W.T + tri(lane) + lane] = tdiag;
+                if (lane < RD) S[W.T + tri(lane) + lane] = tdiag;
+                (void)echo_project<ME>(oU, oM, O.B, m, lane);
                 __syncwarp();
                 unsigned inP = 0u;
                 double x[NC];
@@ -642,122 +751,83 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
 #pragma unroll
                 for (int s = 0; s < NC; ++s) S[oX + lane + 32 * s] = x[s];
                 __syncwarp();
-                (void)echo_fit_sse(oX, O, n, lane, fit);
+                (void)echo_fit_sse(oX, O, n, lane, O.V);
                 __syncwarp();
+                echo_expand<ME>(oU, O.V, m, lane, fit);
 #pragma unroll
                 for (int s = 0; s < NC; ++s) S[oX + lane + 32 * s] = x[s] * S[oIL + lane + 32 * s];
                 __syncwarp();
                 if (est & 1) st |= MET2_ST_ITMAX;
                 if (est & 2) st |= MET2_ST_NOT_PD;
             }
-            // ---- outputs (motor...:153-155, 443-472)
-            const bool fitted = !(st & MET2_ST_SKIPPED);
-            const double kmo = fitted ? km : 0.0;
-            double xk[NC];
-            double vt = 0.0;
-#pragma unroll
-            for (int s = 0; s < NC; ++s) {
-                const int col = lane + 32 * s;
-                xk[s] = (col < n && fitted) ? S[oX + col] * kmo : 0.0;
-                vt += xk[s];
-                if (col < n) A.fsol[v * n + col] = xk[s];
-            }
-            if (lane < m) A.est[v * m + lane] = fitted ? fit * kmo : 0.0;
-            vt = warp_sum(vt) + 1.0e-16;
-            double sm = 0.0, stt = 0.0, sc = 0.0, lm = 0.0, lt = 0.0;
-#pragma unroll
-            for (int s = 0; s < NC; ++s) {
-                const int col = lane + 32 * s;
-                if (col < n) {
-                    const double xn = xk[s] / vt;
-                    const unsigned char cm = scomp[col];
-                    if (cm & 1) {
-                        sm += xn;
-                        lm += xn * S[oLogT2 + col];
-                    }
-                    if (cm & 2) {
-                        stt += xn;
-                        lt += xn * S[oLogT2 + col];
-                    }
-                    if (cm & 4) sc += xn;
-                }
-            }
-            sm = warp_sum(sm);
-            stt = warp_sum(stt);
-            sc = warp_sum(sc);
-            lm = warp_sum(lm);
-            lt = warp_sum(lt);
-            if (lane == 0) {
-                double* mp = A.maps + v * 6;
-                mp[0] = sm;
-                mp[1] = stt;
-                mp[2] = sc;
-                mp[3] = exp(lm / (sm + 1.0e-16));
-                mp[4] = exp(lt / (stt + 1.0e-16));
-                mp[5] = vt;
-                A.reg[v] = fitted ? lam : 0.0;
-                A.status[v] = st;
-            }
-            __syncwarp();
+            echo_outputs<NC, ME>(A, v, oX, oLogT2, scomp, n, m, lane, st, km, lam, fit);
         }
     }
 }
 
 bool t2_echo_eligible(const met2_t2_cfg* cfg) {
-    if (!(cfg->flags & MET2_T2_FLAG_ECHO_SPACE) || cfg->nTE > EC_M) return false;
+    if (!(cfg->flags & MET2_T2_FLAG_ECHO_SPACE)) return false;
     if (cfg->method == MET2_REG_X2) return cfg->nT2 <= EC_NCOL && !(cfg->flags & MET2_T2_FLAG_COLD_START);
     if (cfg->method == MET2_REG_T2SPARC) return cfg->nT2 <= 128;
     return false;
 }
 
-template <int NC>
-static int t2_launch_echo_tik(const T2Args& A, cudaStream_t st) {
-    const size_t tables = sizeof(double) * (size_t)echo_tik_table_doubles<NC>();
-    const size_t per_warp = sizeof(double) * (size_t)echo_tik_warp_doubles<NC>();
+static int echo_warps(size_t tables, size_t per_warp) {
     const size_t budget = 227 * 1024 - 1024;
-    int warps = (int)((budget - tables) / per_warp);
+    int warps = tables < budget ? (int)((budget - tables) / per_warp) : 0;
     if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
     if (const char* ev = getenv("MET2_T2_WARPS")) {
         const int w = atoi(ev);
         if (w >= 1 && w < warps) warps = w;
     }
+    return warps;
+}
+
+template <int NC, int ME>
+static int t2_launch_echo_tik(const T2Args& A, cudaStream_t st) {
+    const size_t tables = sizeof(double) * (size_t)echo_tik_table_doubles<NC>(A.cfg.nTE);
+    const size_t per_warp = sizeof(double) * (size_t)echo_tik_warp_doubles<NC>();
+    const int warps = echo_warps(tables, per_warp);
+    if (warps < 1) return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit (echo space): tables do not fit in shared memory");
     const size_t smem = tables + per_warp * warps;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    cudaError_t e = cudaFuncSetAttribute(t2_echo_tik_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(t2_echo_tik_kernel<NC, ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_echo_tik attr (%zu B): %s", smem, cudaGetErrorString(e));
-    MET2_LAUNCH(sms, warps * 32, smem, st, t2_echo_tik_kernel<NC>)(A);
+    MET2_LAUNCH(sms, warps * 32, smem, st, t2_echo_tik_kernel<NC, ME>)(A);
     count_launch();
     return check_launch("t2_echo_tik_kernel");
 }
 
-int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
+template <int ME>
+static int t2_launch_echo_me(const T2Args& A, cudaStream_t st) {
     const int n = A.cfg.nT2;
     if (A.cfg.method == MET2_REG_T2SPARC) {
         const int nc = (n + 31) / 32;
-        if (nc <= 1) return t2_launch_echo_tik<1>(A, st);
-        if (nc == 2) return t2_launch_echo_tik<2>(A, st);
-        if (nc == 3) return t2_launch_echo_tik<3>(A, st);
-        return t2_launch_echo_tik<4>(A, st);
+        if (nc <= 1) return t2_launch_echo_tik<1, ME>(A, st);
+        if (nc == 2) return t2_launch_echo_tik<2, ME>(A, st);
+        if (nc == 3) return t2_launch_echo_tik<3, ME>(A, st);
+        return t2_launch_echo_tik<4, ME>(A, st);
     }
-    const size_t tables = sizeof(double) * (size_t)echo_table_doubles(n);
+    const size_t tables = sizeof(double) * (size_t)echo_table_doubles(n, A.cfg.nTE);
     const size_t per_warp = sizeof(double) * (size_t)echo_warp_doubles();
-    const size_t budget = 227 * 1024 - 1024;
-    int warps = (int)((budget - tables) / per_warp);
-    if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
+    const int warps = echo_warps(tables, per_warp);
     if (warps < 1) return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit (echo space): tables do not fit in shared memory");
-    if (const char* ev = getenv("MET2_T2_WARPS")) {
-        const int w = atoi(ev);
-        if (w >= 1 && w < warps) warps = w;
-    }
     const size_t smem = tables + per_warp * warps;
     int sms = sm_count();
     if (sms <= 0) sms = 148;
-    cudaError_t e = cudaFuncSetAttribute(t2_echo_x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(t2_echo_x2_kernel<ME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_error(MET2_ERR_CUDA, "t2_echo attr (%zu B): %s", smem, cudaGetErrorString(e));
-    MET2_LAUNCH(sms, warps * 32, smem, st, t2_echo_x2_kernel)(A);
+    MET2_LAUNCH(sms, warps * 32, smem, st, t2_echo_x2_kernel<ME>)(A);
     count_launch();
     return check_launch("t2_echo_x2_kernel");
+}
+
+int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
+    if (!A.red_basis || !A.red_coef)
+        return set_error(MET2_ERR_ARG, "met2_t2_fit: MET2_T2_FLAG_ECHO_SPACE needs the reduced echo basis (met2_echo_basis)");
+    if (A.cfg.nTE <= 32) return t2_launch_echo_me<1>(A, st);
+    return t2_launch_echo_me<2>(A, st);
 }
 
 }  // namespace met2

@@ -21,6 +21,8 @@ struct T2Args {
     met2_t2_cfg cfg;
     const double *dic, *dicT, *G, *kband, *lambdas, *logT2;
     const unsigned char* comp;
+    const double *red_basis, *red_coef;   // reduced echo basis U [nA][nTE][RD] and coefficients C [nA][nT2][RD]
+                                          // (met2_echo_basis); only the echo-space kernels read them
     double *fsol, *est, *reg, *maps;
     unsigned* status;
     // workspace
@@ -549,6 +551,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 }
                 __syncwarp();
                 compute_c<NS>(W, D, oM, m, n, lane);
+                set_dspace<NS>(W, Dt, oM, lane);
                 // ---- lambda-search driver: a small state machine around ONE inlined NNLS call site.
                 //   NNLS     : plain solve                                                    (algorithms.py:55)
                 //   T2SPARC  : one Tikhonov solve at lambda_fixed                             (algorithms.py:262)
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
                     p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
-                                            warm ? p : 0, t_ready, Dt, oM);
+                                            warm ? p : 0, t_ready);
                     t_ready = false;
                     if (method == MET2_REG_NNLS && nst == 0 && p > 0)
                         refine_on_support<NS, ME>(W, Dt, oM, m, p, lane, false, 0.0, oKb, n);

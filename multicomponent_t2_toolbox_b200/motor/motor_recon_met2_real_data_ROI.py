@@ -12,6 +12,7 @@ import numpy as np
 from tabulate import tabulate
 
 from .. import batched, nifti_io, pipeline
+from .motor_recon_met2_real_data import tv_denoise
 
 
 def motor_recon_met2_ROIs(TE_array, path_to_data, path_to_mask, path_to_ROIs, path_to_save_data, TR, reg_matrix, denoise,
@@ -27,12 +28,13 @@ def motor_recon_met2_ROIs(TE_array, path_to_data, path_to_mask, path_to_ROIs, pa
         print('Error: Wrong reg_matrix option!')
         raise SystemExit(1)
     if denoise == 'TV':
-        raise NotImplementedError("denoise=TV is host preprocessing outside the accelerated path (SURVEY.md §8f)")
+        data = tv_denoise(data)
     if denoise == 'NESMA':
         data = batched.nesma_filter(data, mask).cpu().numpy()
     data_fa = batched.gaussian_smooth(data, sigma=2.0) if FA_smooth == 'yes' else None
     vol = pipeline.recon_arrays(data, mask, np.asarray(TE_array, dtype=np.float64), TR, "X2", reg_matrix, FA_method,
-                                myelin_T2=myelin_T2, data_fa=data_fa, diagnostics=True, rois=ROIs)
+                                myelin_T2=myelin_T2, data_fa=data_fa, diagnostics=True, rois=ROIs, premasked=True,
+                                fa_only=True)   # the ROI estimator never fits voxel spectra (reference :349-445)
     roi = vol["roi"]
     join = (lambda name: path_to_save_data + name) if path_to_save_data.endswith('/') else \
         (lambda name: os.path.join(path_to_save_data, name))

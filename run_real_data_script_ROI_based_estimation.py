@@ -25,14 +25,16 @@ _FLAGS = [
     ("--denoise", str, "None", ["TV", "NESMA", "None"], True, "pre-processing denoiser (NESMA runs on the GPU; TV is not provided)"),
     ("--reg_matrix", str, "I", ["I", "L1", "L2", "InvT2"], True, "Tikhonov matrix of the per-ROI X2 fit"),
     ("--myelin_T2_cutoff", float, 40, None, True, "upper T2 bound of the myelin-water compartment, ms"),
-    ("--numcores", int, -1, None, False, "accepted for compatibility; the fit runs on the GPU"),
+    ("--numcores", int, -1, None, False, "number of workers; here: number of GPUs, -1 = all visible GPUs"),
 ]
 
 
 def build_parser():
     parser = argparse.ArgumentParser(description='Myelin Water Imaging')
     for flag, typ, default, choices, required, text in _FLAGS:
-        kw = dict(type=typ, default=default, help=text, required=required)
+        kw = dict(type=typ, default=default, help=text)
+        if required:
+            kw["required"] = True
         if choices:
             kw["choices"] = choices
         parser.add_argument(flag, **kw)

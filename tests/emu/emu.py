@@ -177,6 +177,19 @@ def gram_tables(dic, L):
     return G, kband, int(err[0])
 
 
+def echo_basis(dic, R=24):
+    """met2_echo_basis -> (basis [nA][nTE][R], coef [nA][nT2][R], tail [nA])."""
+    dic = np.ascontiguousarray(dic, dtype=np.float64)
+    nA, m, n = dic.shape
+    basis = np.full((nA, m, R), np.nan)
+    coef = np.full((nA, n, R), np.nan)
+    tail = np.full(nA, np.nan)
+    fn = lib().met2_echo_basis
+    fn.argtypes = [P, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, P, P, P, P]
+    _check(fn(_ptr(dic), nA, m, n, R, _ptr(basis), _ptr(coef), _ptr(tail), None), "met2_echo_basis")
+    return basis, coef, tail
+
+
 def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lambdas=None, myelin_T2=40.0, warps=2,
            factor=1.02, lambda_fixed=1.8):
     """met2_t2_fit on host arrays (counting sort, tile list, shared full-set factor tables and the fit kernel, all
@@ -212,11 +225,16 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
         if nbytes < 0:
             raise RuntimeError("met2_t2_workspace_bytes: " + lib().met2_last_error().decode())
         ws = gd.array(int(nbytes), np.uint8, 0xA5)               # poisoned like a fresh torch.empty
-        fn = lib().met2_t2_fit
-        fn.argtypes = [P, P, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [P] * 14
+        basis = coef = None
+        if echo:                                                 # reduced echo basis from the library's own kernel
+            basis, coef, tail = echo_basis(dic)
+            assert tail.max() <= 1e-15, tail.max()
+        fn = lib().met2_t2_fit_echo
+        fn.argtypes = [P, P, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [P] * 16
         _check(fn(_ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(kband),
-                  _ptr(lam), _ptr(logT2), _ptr(comp), _ptr(out["fsol"]), _ptr(out["est_signal"]), _ptr(out["reg"]),
-                  _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), None), "met2_t2_fit")
+                  _ptr(lam), _ptr(logT2), _ptr(comp), _ptr(basis), _ptr(coef), _ptr(out["fsol"]),
+                  _ptr(out["est_signal"]), _ptr(out["reg"]), _ptr(out["maps"]), _ptr(out["status"]), _ptr(ws), None),
+               "met2_t2_fit_echo")
         gd.check("met2_t2_fit")
     finally:
         if old is None:

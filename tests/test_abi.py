@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
     for s in syms:
         assert hasattr(lib, s), "libmet2.so does not export %s" % s
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.met2_version() == 100
+    assert lib.met2_version() == 110
 
 
 def test_struct_layout_matches_header():
@@ -49,6 +49,13 @@ def test_argument_validation_without_gpu():
     assert rc == -1 and b"NULL" in lib.met2_last_error()
     rc = lib.met2_epg_dictionary(None, 3, None, None, 60, 32, 10.0, 1000.0, None, None, None)
     assert rc == -1
+    # GCV lambda-grid mode: the kernel stages at most MET2_MAX_LAMBDAS (64) grid values
+    gcv = _lib.T2Cfg(method=4, nTE=32, nT2=60, nA=91, nLambda=65, flags=32)
+    assert lib.met2_t2_workspace_bytes(10, ctypes.byref(gcv)) == -1 and b"GCV grid" in lib.met2_last_error()
+    gcv.nLambda = 0
+    assert lib.met2_t2_workspace_bytes(10, ctypes.byref(gcv)) == -1
+    gcv.nLambda = 49
+    assert lib.met2_t2_workspace_bytes(10, ctypes.byref(gcv)) > 0
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
@@ -70,7 +77,7 @@ def test_c_host_program_links_and_fails_loudly_without_cuda():
     report the ABI version and stop with an error — not compute anything on the CPU."""
     import subprocess
     r = subprocess.run([_c_host_binary()], capture_output=True, text=True, timeout=120)
-    assert "met2 C-ABI version 100" in r.stdout
+    assert "met2 C-ABI version 110" in r.stdout
     assert r.returncode != 0 and ("error" in r.stderr.lower())
 
 

@@ -290,12 +290,34 @@ def test_whole_chain_against_the_reference_orchestrator_run():
     assert np.max(np.abs(out["est_signal"] - s_ref)) <= 1e-6 * np.abs(s_ref).max()
 
 
-@pytest.mark.parametrize("matrix,npc", [("InvT2", 96), ("I", 96), ("InvT2", 60)])
-def test_echo_space_fixed_lambda_kernel(matrix, npc):
-    """t2_echo_tik_kernel (T2SPARC in echo space, experimental): one solve per voxel from the empty set with rank-one
-    updates of the 32 x 32 factor only; the reference's 96-bin grid uses three column slots per lane."""
+def test_echo_basis_kernel():
+    """met2_echo_basis (column-pivoted Gram-Schmidt per angle): U orthonormal (directions below the rounding of D are
+    zero vectors), U C = D to rounding, residual reported per angle — 32 x 60 and the config-4 shape 48 x 100."""
+    for npc, nte, tau in ((60, 32, 10.0), (100, 48, 8.0)):
+        T2s = np.logspace(1, np.log10(2000.0), npc)
+        Dic = O.create_Dic_3D(npc, T2s, 1000.0 * np.ones(npc), nte, tau, np.array([91.0, 133.0, 180.0]), 1000.0)
+        dic = np.ascontiguousarray(np.transpose(Dic, (2, 0, 1)))
+        U, C, tail = emu.echo_basis(dic)
+        assert tail.max() <= 1e-15
+        for a in range(3):
+            UtU = U[a].T @ U[a]
+            nz = np.diag(UtU) > 0.5
+            assert np.abs(UtU - np.diag(nz.astype(float))).max() < 1e-14
+            assert np.abs(U[a] @ C[a].T - dic[a]).max() <= 2e-15 * np.abs(dic[a]).max()
+    few = emu.echo_basis(np.random.default_rng(0).uniform(size=(1, 8, 12)))      # fewer echoes than R: zero directions
+    assert np.abs(few[0][0] @ few[1][0].T - np.random.default_rng(0).uniform(size=(1, 8, 12))[0]).max() < 1e-14
+    assert few[2][0] <= 1e-15
+    full = emu.echo_basis(np.random.default_rng(1).uniform(size=(1, 32, 60)))    # full-rank dictionary: reported, not hidden
+    assert full[2][0] > 1e-3
+
+
+@pytest.mark.parametrize("matrix,npc,nte", [("InvT2", 96, 32), ("I", 96, 32), ("InvT2", 60, 32), ("InvT2", 100, 48)])
+def test_echo_space_fixed_lambda_kernel(matrix, npc, nte):
+    """t2_echo_tik_kernel (T2SPARC in the reduced echo space): one solve per voxel from the empty set with rank-one
+    updates of the 24 x 24 factor only; the reference's 96-bin grid uses three column slots per lane; 48 echoes / 100
+    bins (config-4 sizes): four column slots, two echo slots."""
     emu.build()
-    gr, Dic, sig, fa = _synthetic(npc, 32, 6, "T2SPARC", matrix)
+    gr, Dic, sig, fa = _synthetic(npc, nte, 6 if nte == 32 else 3, "T2SPARC", matrix)
     outs = [_run(o, sig, fa, Dic, gr["L"], gr["T2s"], "T2SPARC", echo=True) for o in ORDERS]
     assert _same(outs[0], outs[1]) and _same(outs[0], outs[2])
     out = outs[0]

@@ -397,8 +397,13 @@ def test_methods_subset_vs_reference(golden_methods):
             assert r["frac_dMWF_below_1e4"] > 0.85, (key, r)      # reference self-agreement under 1e-13 noise: ~96 %
             continue
         assert r["active_set_disagreements"] <= 2, (key, r)        # <= 1e-3 of the voxels
-        tol = 1e-5 if key.startswith("BayesReg") else REL_SPECTRUM  # flat evidence curve: see LOOSE above
-        assert r["spectrum_rel_err_max_agreeing"] < tol, (key, r)
+        if key.startswith("BayesReg"):
+            # flat evidence curve: under a 1e-13 perturbation of the signal the reference itself moves 1 of these 2 048
+            # voxels by 3.6e-5 (lambda by 1e-4) and none of the others by more than 1e-6
+            # (oracle/measure_bayes_self_agreement.py, profiles/r02_bayes_self_agreement.txt)
+            assert r["spectrum_rel_err_over_1e6"] <= 3 and r["spectrum_rel_err_max_agreeing"] < 1e-3, (key, r)
+        else:
+            assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM, (key, r)
         assert r["max_abs_dMWF_agreeing"] < ABS_MAPS and r["max_abs_dMWF_all"] < 1e-2, (key, r)
 
 

@@ -6,7 +6,8 @@
   * BASELINE.json configs[3] sizes (nTE 48, 100 bins): brute-force FA, plain NNLS and BayesReg + InvT2
     (bayesian_interpolation.py:84-126) on 2 048 voxels, bounded by the reference's own reproducibility under a 1e-13
     relative perturbation of the signal;
-  * the echo-space kernels (MET2_T2_FLAG_ECHO_SPACE) for X2-I, X2-InvT2 and T2SPARC (96 bins).
+  * the reduced-echo-space kernels (MET2_T2_FLAG_ECHO_SPACE) and the Gram-domain kernels for X2-I, X2-InvT2 and T2SPARC
+    (96 bins), and the reduced echo basis itself.
 
 Every test writes its measured rates to gpurun_out/parity_r2_*.json (copied to profiles/ after a run)."""
 import json
@@ -126,24 +127,33 @@ def test_config4_subset_vs_reference(golden_config4):
     assert b["max_abs_dMWF"] < ABS_MAPS, rec
 
 
-def test_echo_space_kernels_vs_reference(golden_config2, golden_methods):
-    """MET2_T2_FLAG_ECHO_SPACE (csrc/met2_t2_echo.cu) on the device: X2-I against the 20 480 reference-fitted voxels,
-    X2-InvT2 against the oracle (160 voxels) and the default kernel (20 480), T2SPARC (96 bins) against the 2 048
-    reference-fitted voxels."""
+def test_echo_space_and_gram_kernels_vs_reference(golden_config2, golden_methods):
+    """X2 and T2SPARC have two kernel families: the reduced-echo-space kernels (csrc/met2_t2_echo.cu; the plan's default
+    for X2-I and T2SPARC, MET2_T2_FLAG_ECHO_SPACE) and the Gram-domain kernels (echo_space=False; the default for every
+    other method / matrix).  Both on the device: X2-I against the 20 480 reference-fitted voxels, X2-InvT2 against the
+    oracle (160 voxels) and against each other (20 480), T2SPARC (96 bins) against the 2 048 reference-fitted voxels."""
     g = golden_config2
     sig, idx = g["sig"], g["fa_idx"].astype(np.int32)
     rec = {}
-    plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="I", FA_method="spline")
-    out = plan.t2_fit(sig, idx, flags=ECHO)
-    f, f_ref = out["fsol"].cpu().numpy(), g["f"]
-    bad = np.any((f > 0) != (f_ref > 0), axis=1)
-    rel = _rel_err(f, f_ref)
-    dreg = np.abs(out["reg"].cpu().numpy() - g["reg"]) / np.abs(g["reg"])
-    rec["X2_I"] = dict(voxels=int(len(f)), active_set_disagreements=int(bad.sum()),
-                       spectrum_rel_err_max_agreeing=float(rel[~bad].max()), k_est_rel_err_max_agreeing=float(dreg[~bad].max()),
-                       max_abs_dMWF_agreeing=float(np.abs(_mwf(f, plan) - _mwf(f_ref, plan))[~bad].max()),
-                       status_nonzero=int((out["status"] != 0).sum()))
+    f_ref = g["f"]
+    for name, echo in (("X2_I_echo", True), ("X2_I_gram", False)):
+        plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="I", FA_method="spline", echo_space=echo)
+        assert bool(plan.t2_cfg().flags & ECHO) == echo
+        out = plan.t2_fit(sig, idx)
+        f = out["fsol"].cpu().numpy()
+        bad = np.any((f > 0) != (f_ref > 0), axis=1)
+        rel = _rel_err(f, f_ref)
+        dreg = np.abs(out["reg"].cpu().numpy() - g["reg"]) / np.abs(g["reg"])
+        est = out["est_signal"].cpu().numpy()
+        D = plan.dict_hr.dic.cpu().numpy()[idx[:512]]
+        est_err = np.abs(est[:512] - np.einsum("vec,vc->ve", D, f[:512])).max() / np.abs(est[:512]).max()
+        rec[name] = dict(voxels=int(len(f)), active_set_disagreements=int(bad.sum()),
+                         spectrum_rel_err_max_agreeing=float(rel[~bad].max()),
+                         k_est_rel_err_max_agreeing=float(dreg[~bad].max()),
+                         max_abs_dMWF_agreeing=float(np.abs(_mwf(f, plan) - _mwf(f_ref, plan))[~bad].max()),
+                         est_signal_vs_D_f_rel=float(est_err), status_nonzero=int((out["status"] != 0).sum()))
     pi = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="InvT2", FA_method="spline")
+    assert not (pi.t2_cfg().flags & ECHO)                       # InvT2: the Gram-domain kernel measured (slightly) faster
     e = pi.t2_fit(sig, idx, flags=ECHO)
     d = pi.t2_fit(sig, idx)
     fe, fd = e["fsol"].cpu().numpy(), d["fsol"].cpu().numpy()
@@ -152,32 +162,62 @@ def test_echo_space_kernels_vs_reference(golden_config2, golden_methods):
     Dic = pi.dict_hr.to_reference_layout()
     f_or, _, reg_or = O.fitting_slice_T2(np.ones(n_or), sig[:n_or], idx[:n_or], n_or, Dic, pi.lambda_reg, 60, 32, "X2",
                                          pi.Laplac)
-    rec["X2_InvT2"] = dict(voxels=int(len(fe)), active_set_disagreements_vs_default=int(bad_ab.sum()),
-                           spectrum_rel_err_over_1e6_vs_default=int((_rel_err(fe, fd) > REL_SPECTRUM).sum()),
+    rec["X2_InvT2"] = dict(voxels=int(len(fe)), active_set_disagreements_echo_vs_gram=int(bad_ab.sum()),
+                           spectrum_rel_err_over_1e6_echo_vs_gram=int((_rel_err(fe, fd) > REL_SPECTRUM).sum()),
                            oracle_voxels=n_or,
-                           active_set_disagreements_vs_oracle=int(np.any((fe[:n_or] > 0) != (f_or > 0), axis=1).sum()),
-                           spectrum_rel_err_max_vs_oracle=float(_rel_err(fe[:n_or], f_or).max()),
-                           status_nonzero=int((e["status"] != 0).sum()))
+                           echo_active_set_disagreements_vs_oracle=int(np.any((fe[:n_or] > 0) != (f_or > 0), axis=1).sum()),
+                           echo_spectrum_rel_err_max_vs_oracle=float(_rel_err(fe[:n_or], f_or).max()),
+                           gram_active_set_disagreements_vs_oracle=int(np.any((fd[:n_or] > 0) != (f_or > 0), axis=1).sum()),
+                           gram_spectrum_rel_err_max_vs_oracle=float(_rel_err(fd[:n_or], f_or).max()),
+                           status_nonzero=int((e["status"] != 0).sum() + (d["status"] != 0).sum()))
     gm = golden_methods
-    pt = batched.Met2Plan(32, 10.0, 1000.0, reg_method="T2SPARC", reg_matrix="InvT2", FA_method="spline", npc=96)
     idx96 = gm["fa_spline_96"].astype(np.int32)
-    t = pt.t2_fit(gm["sig"], idx96, flags=ECHO)
-    ft, ft_ref = t["fsol"].cpu().numpy(), gm["spectrum"]("T2SPARC_InvT2", 96)
-    bad_t = np.any((ft > 0) != (ft_ref > 0), axis=1)
-    rec["T2SPARC_InvT2_96"] = dict(voxels=int(len(ft)), active_set_disagreements=int(bad_t.sum()),
-                                   spectrum_rel_err_max_agreeing=float(_rel_err(ft, ft_ref)[~bad_t].max()),
-                                   max_abs_dMWF=float(np.abs(_mwf(ft, pt) - _mwf(ft_ref, pt)).max()),
-                                   status_nonzero=int((t["status"] != 0).sum()))
+    ft_ref = gm["spectrum"]("T2SPARC_InvT2", 96)
+    for name, echo in (("T2SPARC_InvT2_96_echo", True), ("T2SPARC_InvT2_96_gram", False)):
+        pt = batched.Met2Plan(32, 10.0, 1000.0, reg_method="T2SPARC", reg_matrix="InvT2", FA_method="spline", npc=96,
+                              echo_space=echo)
+        assert bool(pt.t2_cfg().flags & ECHO) == echo
+        t = pt.t2_fit(gm["sig"], idx96)
+        ft = t["fsol"].cpu().numpy()
+        bad_t = np.any((ft > 0) != (ft_ref > 0), axis=1)
+        rec[name] = dict(voxels=int(len(ft)), active_set_disagreements=int(bad_t.sum()),
+                         spectrum_rel_err_max_agreeing=float(_rel_err(ft, ft_ref)[~bad_t].max()),
+                         max_abs_dMWF=float(np.abs(_mwf(ft, pt) - _mwf(ft_ref, pt)).max()),
+                         status_nonzero=int((t["status"] != 0).sum()))
     _record("parity_r2_echo_space.json", rec)
-    r = rec["X2_I"]
-    assert r["status_nonzero"] == 0 and r["active_set_disagreements"] <= 4, rec      # Brent branch points, see config-2 test
-    assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF_agreeing"] < ABS_MAPS, rec
+    for name in ("X2_I_echo", "X2_I_gram"):
+        r = rec[name]
+        assert r["status_nonzero"] == 0 and r["active_set_disagreements"] <= 4, rec  # Brent branch points (config-2 test)
+        assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF_agreeing"] < ABS_MAPS, rec
+        assert r["est_signal_vs_D_f_rel"] < 1e-12, rec
     r = rec["X2_InvT2"]
-    assert r["status_nonzero"] == 0 and r["active_set_disagreements_vs_oracle"] == 0, rec
-    assert r["spectrum_rel_err_max_vs_oracle"] < REL_SPECTRUM, rec
+    assert r["status_nonzero"] == 0, rec
+    assert r["echo_active_set_disagreements_vs_oracle"] == 0 and r["gram_active_set_disagreements_vs_oracle"] == 0, rec
+    assert r["echo_spectrum_rel_err_max_vs_oracle"] < REL_SPECTRUM and r["gram_spectrum_rel_err_max_vs_oracle"] < REL_SPECTRUM, rec
     # Brent branch points (absolute xtol 1e-5 on lambda): two exact solvers part ways on ~4 voxels in 10^4, like the
-    # reference against itself (config-2 test above; warm/cold A/B of round 1: 15 of 552 960)
-    assert r["active_set_disagreements_vs_default"] <= 4 and r["spectrum_rel_err_over_1e6_vs_default"] <= 12, rec
-    r = rec["T2SPARC_InvT2_96"]
-    assert r["status_nonzero"] == 0 and r["active_set_disagreements"] == 0, rec
-    assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF"] < ABS_MAPS, rec
+    # reference against itself (config-2 test; warm/cold A/B of round 1: 15 of 552 960)
+    assert r["active_set_disagreements_echo_vs_gram"] <= 4 and r["spectrum_rel_err_over_1e6_echo_vs_gram"] <= 12, rec
+    for name in ("T2SPARC_InvT2_96_echo", "T2SPARC_InvT2_96_gram"):
+        r = rec[name]
+        assert r["status_nonzero"] == 0 and r["active_set_disagreements"] == 0, rec
+        assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF"] < ABS_MAPS, rec
+
+
+def test_echo_basis_reproduces_the_dictionary():
+    """met2_echo_basis: U orthonormal, U C = D to rounding, for the three dictionary shapes in use."""
+    dev = torch.device("cuda", 0)
+    for nte, tau, npc, alphas in ((32, 10.0, 60, np.linspace(90, 180, 273)), (32, 10.0, 96, np.linspace(90, 180, 15)),
+                                  (48, 8.0, 100, np.linspace(90, 180, 91))):
+        T2s = np.logspace(1, np.log10(2000.0), npc)
+        d = batched.Dictionary(alphas, T2s, 1000.0 * np.ones(npc), nte, tau, 1000.0, dev)
+        red = d.echo_basis()
+        assert red is not None and d.echo_tail <= 1e-15, d.echo_tail
+        U, C = red[0].cpu().numpy(), red[1].cpu().numpy()
+        D = d.dic.cpu().numpy()
+        UtU = np.einsum("ake,akf->aef", U, U)
+        nz = np.abs(np.diagonal(UtU, axis1=1, axis2=2)) > 0.5       # directions below D's rounding are zero vectors
+        eye = np.zeros_like(UtU)
+        ii = np.arange(UtU.shape[1])
+        eye[:, ii, ii] = nz
+        assert np.abs(UtU - eye).max() < 1e-14
+        assert np.abs(np.einsum("ake,aje->akj", U, C) - D).max() <= 2e-15 * np.abs(D).max()

@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import run_real_data_script as cli
+import run_real_data_script_ROI_based_estimation as cli_roi
 from multicomponent_t2_toolbox_b200 import nifti_io
 
 
@@ -92,13 +93,45 @@ def test_nifti_big_endian_qform_and_shapes(tmp_path):
         assert np.array_equal(nifti_io.load(q).get_fdata(), x)
 
 
+def _reference_flags(path):
+    """(flag -> dict(type, default, choices, required)) parsed from the reference script's own argparse block."""
+    import ast
+    tree = ast.parse(open(path).read())
+    out = {}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Call) and getattr(node.func, "attr", "") == "add_argument":
+            flag = ast.literal_eval(node.args[0])
+            kw = {k.arg: k.value for k in node.keywords}
+            out[flag] = dict(type=kw["type"].id if "type" in kw else None,
+                             default=ast.literal_eval(kw["default"]) if "default" in kw else None,
+                             choices=ast.literal_eval(kw["choices"]) if "choices" in kw else None,
+                             required=ast.literal_eval(kw["required"]) if "required" in kw else False)
+    return out
+
+
+@pytest.mark.parametrize("script,mod", [("run_real_data_script.py", "cli"),
+                                        ("run_real_data_script_ROI_based_estimation.py", "cli_roi")])
+def test_cli_flag_table_equals_reference_argparse(script, mod):
+    """Flag / type / default / choices / required of every option, diffed against the reference's own argparse block
+    (run_real_data_script.py:18-62, run_real_data_script_ROI_based_estimation.py:18-52)."""
+    path = os.path.join("/root/reference", script)
+    if not os.path.exists(path):
+        pytest.skip("reference tree not present on this box")
+    ref = _reference_flags(path)
+    ours = {f: dict(type=t.__name__, default=d, choices=c, required=r)
+            for f, t, d, c, r, _ in globals()[mod]._FLAGS}
+    assert ours == ref
+
+
 def test_cli_flags_match_reference():
     argv = ("--path_to_folder /data/ --input Data.nii.gz --mask Mask.nii.gz --minTE 10.68 --nTE 32 --TR 1000 "
-            "--FA_method spline --FA_smooth yes --denoise None --reg_method X2 --reg_matrix I --numcores -1 "
+            "--FA_method spline --FA_smooth yes --denoise None --reg_method X2 --reg_matrix I "
             "--myelin_T2=40 --savefig no --savefig_slice 30").split()   # --myelin_T2 relies on prefix matching
     a = cli.build_parser().parse_args(argv)
     assert a.myelin_T2_cutoff == 40.0 and a.reg_method == "X2" and a.FA_method == "spline" and a.nTE == 32
+    assert a.numcores == -1                                           # optional, default -1 (= all), like the reference
+    assert cli.build_parser().parse_args(argv + ["--numcores", "2"]).numcores == 2
     with pytest.raises(SystemExit):
-        cli.build_parser().parse_args(argv[:-2])                  # every flag is required, like the reference
+        cli.build_parser().parse_args(argv[:-2])                  # every other flag is required, like the reference
     with pytest.raises(SystemExit):
         cli.build_parser().parse_args([x if x != "X2" else "Tikhonov" for x in argv])

@@ -1,7 +1,8 @@
 """Multi-rank path on CPU: world_size-2 gloo run of the slab partition + final gather.
 
 The fit itself needs a GPU; here each rank fills its slab with a deterministic per-voxel function so that the
-partition/scatter/gather logic is checked end to end: the gathered volumes must equal the single-rank result."""
+partition / all-gather-of-slabs logic (pipeline.gather_slabs) is checked end to end: the gathered arrays must equal
+the single-rank result."""
 import os
 import sys
 
@@ -28,18 +29,21 @@ def _worker(rank, world, port, q):
     mask = (rng.uniform(0, 1, (5, 4, 3)) > 0.3).astype(np.int64)
     flat, sig = pipeline.masked_voxel_list(data, mask)
     lo, hi = pipeline.slab_bounds(len(flat), rank, world)
-    vol = np.zeros(5 * 4 * 3)
-    vol[flat[lo:hi]] = _fake_fit(sig[lo:hi])
-    out = pipeline.gather_volumes({"MWF": vol.reshape(5, 4, 3), "T2s": np.arange(3.0)})
-    full = np.zeros(5 * 4 * 3)
-    full[flat] = _fake_fit(sig)
-    ok = np.array_equal(out["MWF"].reshape(-1), full) and np.array_equal(out["T2s"], np.arange(3.0))
-    # block-cyclic (over-decomposed) partition: same gather, same result
-    mine = pipeline.cyclic_slab(len(flat), rank, world, chunk=4)
-    vol2 = np.zeros(5 * 4 * 3)
-    vol2[flat[mine]] = _fake_fit(sig[mine])
-    out2 = pipeline.gather_volumes({"MWF": vol2.reshape(5, 4, 3)})
-    ok = ok and np.array_equal(out2["MWF"].reshape(-1), full) and 0 < len(mine) < len(flat)
+    # this rank's per-voxel outputs for ITS slab only (a vector and a [V, 3] array, like reg / maps of the real fit)
+    mine = {"reg": _fake_fit(sig[lo:hi]), "maps": np.stack([sig[lo:hi, 0], sig[lo:hi, 1], sig[lo:hi, 2]], 1),
+            "idx": np.arange(lo, hi, dtype=np.int32)}
+    out = pipeline.gather_slabs(mine, np.arange(lo, hi), len(flat))
+    ok = np.array_equal(out["reg"], _fake_fit(sig)) and np.array_equal(out["maps"], sig[:, :3]) and \
+        np.array_equal(out["idx"], np.arange(len(flat), dtype=np.int32))
+    # over-decomposed partition (chunk_deal, the one MultiGpuFit uses): same gather, same result
+    ranges = pipeline.chunk_deal(len(flat), world, chunks_per_part=3, align=2)[rank]
+    sel = np.concatenate([np.arange(a, b) for a, b in ranges]) if ranges else np.zeros(0, dtype=np.int64)
+    out2 = pipeline.gather_slabs({"reg": _fake_fit(sig[sel])}, sel, len(flat))
+    ok = ok and np.array_equal(out2["reg"], _fake_fit(sig)) and 0 < len(sel) < len(flat)
+    # block-cyclic index sets
+    cyc = pipeline.cyclic_slab(len(flat), rank, world, chunk=4)
+    out3 = pipeline.gather_slabs({"reg": _fake_fit(sig[cyc])}, cyc, len(flat))
+    ok = ok and np.array_equal(out3["reg"], _fake_fit(sig))
     q.put((rank, bool(ok), hi - lo))
     dist.barrier()
     dist.destroy_process_group()

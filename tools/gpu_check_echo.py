@@ -23,7 +23,7 @@ ECHO = 64
 rm = os.environ.get("RM", "I")
 method = os.environ.get("METHOD", "X2")
 shape = tuple(int(x) for x in os.environ.get("SHAPE", "96,96,60").split(","))
-plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method="spline")
+plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method="spline", echo_space=False)
 rep = dict(rm=rm, method=method)
 
 # ---- 1. golden voxels (20 480, fitted by the unmodified reference with X2-I)
