@@ -214,8 +214,8 @@ class Met2Plan:
         self.lib = _lib.load()
         self.reg_method, self.reg_matrix, self.FA_method = reg_method, reg_matrix, FA_method
         self.t2_flags = int(t2_flags)    # MET2_T2_FLAG_* applied to every t2_fit of this plan (e.g. GCV_GRID)
-        # reduced-echo-space kernels for the configurations where they measured faster than the Gram-domain ones
-        # (X2 with the identity matrix, T2SPARC; profiles/r02_ab_*); echo_space=False keeps the Gram-domain kernels
+        # reduced-echo-space kernels wherever they apply (X2 and T2SPARC with a diagonal matrix: I, InvT2), where they
+        # measured 1.4-3x faster than the Gram-domain ones (profiles/r02_ab_*); echo_space=False keeps the latter
         self.echo_space = bool(echo_space)
         self.nTE, self.tau, self.TR = int(n_echoes), float(tau), float(TR)
         if Dic_3D is not None:
@@ -291,10 +291,11 @@ class Met2Plan:
                 cfg.log_det_L = float(np.log(np.linalg.det(self.Laplac)))
         if method == "X2" and np.array_equal(self.Laplac, np.eye(self.npc)):
             cfg.flags |= FULL_START
-            if self.echo_space and self.npc <= 64 and not (cfg.flags & COLD_START):
+        if self.echo_space and self._diagonal_L() and not (cfg.flags & COLD_START):
+            # measured on the config-2 volume (profiles/r02_ab_*): X2-I 365 -> 211 ms, X2-InvT2 262 -> 190 ms,
+            # T2SPARC (96 bins) 282 -> 91 ms
+            if (method == "X2" and self.npc <= 64) or (method == "T2SPARC" and self.npc <= 128):
                 cfg.flags |= ECHO_SPACE
-        if method == "T2SPARC" and self.echo_space and self.npc <= 128 and self._diagonal_L():
-            cfg.flags |= ECHO_SPACE
         for k, v in overrides.items():   # e.g. factor=..., lambda_fixed=..., maxfun=...
             setattr(cfg, k, v)
         return cfg

@@ -55,6 +55,9 @@ __host__ __device__ __forceinline__ int fa_table_doubles(int n, int m) { return 
 
 template <int NS, int ME>
 __global__ void __launch_bounds__(FA_SEARCH_WARPS * 32, 1) fa_search_kernel(FaArgs A) {
+    // a plain solve has at most min(nT2, nTE) <= 32 ME positive columns: position-space loops of ME slots, not NS
+    constexpr int FA_PS = (ME < NS) ? ME : NS;
+    __shared__ int s_next;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
     const int ldg = fa_ldg(n);
@@ -81,8 +84,16 @@ __global__ void __launch_bounds__(FA_SEARCH_WARPS * 32, 1) fa_search_kernel(FaAr
                 S[oG + r * ldg + (i - r * n)] = __ldg(G + i);
             }
         }
+        if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
-        for (long long v = v0 + warp; v < v1; v += (blockDim.x >> 5)) {
+        // the warps pull the CTA's voxels one at a time (a static deal left them waiting for the slowest warp at the
+        // barrier that ends every angle: 1.3 stalled warps per issue in profiles/r02_fa_*_ncu_summary.txt)
+        while (true) {
+            int iv = 0;
+            if (lane == 0) iv = atomicAdd(&s_next, 1);
+            iv = __shfl_sync(FULL_MASK, iv, 0);
+            const long long v = v0 + iv;
+            if (v >= v1) break;
             unsigned st = load_signal<ME>(A.sig, v, m, oM, lane);
             if (st) continue;
             compute_c_sh<NS>(W, oD, oM, m, n, lane);
@@ -99,7 +110,7 @@ __global__ void __launch_bounds__(FA_SEARCH_WARPS * 32, 1) fa_search_kernel(FaAr
             }
             int nst = 0;
             set_dspace<NS>(W, A.dicT_s + (size_t)a * n * m, oM, lane);
-            int p = nnls_gram<NS, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, p0);
+            int p = nnls_gram<NS, true, FA_PS>(W, oG, nullptr, ldg, 0, false, 0.0, n, m, lane, nst, p0);
             if (a + 1 < A.nS) {
                 const bool keep = (p <= FA_CARRY);
                 if (keep && lane < p) {
@@ -192,6 +203,7 @@ __device__ __forceinline__ double spline_eval(int oX, int oY, int oM2, int K, do
 
 template <int NS, int ME>
 __global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_select_kernel(FaArgs A) {
+    constexpr int FA_PS = (ME < NS) ? ME : NS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE, nA = A.cfg.nA;
     Slots<NS> W;
@@ -259,7 +271,7 @@ __global__ void __launch_bounds__(FA_WARPS * 32, 3) fa_select_kernel(FaArgs A) {
             compute_c<NS>(W, D, oM, m, n, lane);
             int nst = 0;
             set_dspace<NS>(W, A.dicT + (size_t)index * n * m, oM, lane);
-            (void)nnls_gram<NS, false>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst);
+            (void)nnls_gram<NS, false, FA_PS>(W, 0, G, n, 0, false, 0.0, n, m, lane, nst);
             if (nst && lane == 0) A.status[v] |= MET2_ST_ITMAX;
             // nnls_gram leaves the solution in column space in S[W.xc..]; km = sum(f)
             double part = 0.0;

@@ -57,7 +57,7 @@ struct Unroll {
     static constexpr int v = (NS >= MET2_UNROLL_WIDE_NS) ? 4 : 1;
 };
 
-__host__ __device__ __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
+__host__ __device__ constexpr __forceinline__ int tri(int i) { return (i * (i + 1)) >> 1; }
 
 __host__ __device__ __forceinline__ size_t align_up256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -114,9 +114,43 @@ __device__ __forceinline__ int warp_argmin_nonneg(double v, int index, double& v
 //   aux: two doubles after ix — [0] the pointer to the transposed dictionary [n][m] of the solve in flight (global
 //        memory), [1] (as int) the offset of its right-hand side in S; read only by the rare D-space evaluation of a
 //        nearly dependent candidate (dspace_candidate), kept here rather than in registers (see set_dspace)
+// The two entries of the augmented 8 x 16 block [S | I] that lane `lane` owns in ldl_8x8 (entry e = lane + 32 sl:
+// e < 36 -> (r, c) of the upper triangle of S, row-major; e >= 36 -> (r, 8 + c') with c' < r, the strictly-lower part
+// of the inverse factor), packed as bytes r0 | c0 << 8 | r1 << 16 | c1 << 24.  Depends on the lane only: computed once
+// per kernel (Slots::carve) — recomputed inside every elimination it was 9 % of the 96-register X2 kernel.
+__device__ __forceinline__ unsigned ldl_lane_code(int lane) {
+    unsigned code = 0u;
+#pragma unroll
+    for (int sl = 0; sl < 2; ++sl) {
+        const int e = lane + 32 * sl;
+        int rr, cc;
+        if (e < 36) {
+            rr = 0;
+            int rem = e;
+#pragma unroll
+            for (int t = 0; t < 7; ++t)
+                if (rem >= 8 - rr) {
+                    rem -= 8 - rr;
+                    ++rr;
+                }
+            cc = rr + rem;
+        } else {
+            const int f = e - 36;
+            rr = 1;
+#pragma unroll
+            for (int t = 0; t < 6; ++t)
+                if (f >= (rr * (rr + 1)) / 2) ++rr;
+            cc = 8 + f - (rr * (rr - 1)) / 2;
+        }
+        code |= ((unsigned)rr | ((unsigned)cc << 8)) << (16 * sl);
+    }
+    return code;
+}
+
 template <int NS>
 struct Slots {
     int T, gs, rs, xs, cc, xc, ix;
+    unsigned code;   // ldl_lane_code of this lane
     static constexpr int LEN = 32 * NS;
     __host__ __device__ static int doubles(int pmax) { return tri(pmax) + 5 * LEN + LEN / 2 + 2; }
     __device__ __forceinline__ void carve(int base, int pmax) {
@@ -127,6 +161,7 @@ struct Slots {
         cc = xs + LEN;
         xc = cc + LEN;
         ix = xc + LEN;
+        code = ldl_lane_code((int)(threadIdx.x & 31));
     }
     __device__ __forceinline__ int aux() const { return ix + LEN / 2; }
 };
@@ -322,29 +357,9 @@ __device__ __forceinline__ void ldl_8x8(const Slots<NS>& W, double s0, double s1
     double ev[2];
 #pragma unroll
     for (int sl = 0; sl < 2; ++sl) {
-        const int e = lane + 32 * sl;
-        int rr, cc;
-        if (e < 36) {
-            rr = 0;
-            int rem = e;
-#pragma unroll
-            for (int t = 0; t < 7; ++t)
-                if (rem >= 8 - rr) {
-                    rem -= 8 - rr;
-                    ++rr;
-                }
-            cc = rr + rem;
-        } else {
-            const int f = e - 36;
-            rr = 1;
-#pragma unroll
-            for (int t = 0; t < 6; ++t)
-                if (f >= (rr * (rr + 1)) / 2) ++rr;
-            cc = 8 + f - (rr * (rr - 1)) / 2;
-        }
-        er[sl] = rr;
-        ec[sl] = cc;
-        ev[sl] = S[oFR + rr * 16 + cc];
+        er[sl] = (int)((W.code >> (16 * sl)) & 0xffu);
+        ec[sl] = (int)((W.code >> (16 * sl + 8)) & 0xffu);
+        ev[sl] = S[oFR + er[sl] * 16 + ec[sl]];
     }
 #pragma unroll 1
     for (int k = 0; k < nv - 1; ++k) {
@@ -631,21 +646,23 @@ __device__ __forceinline__ void warp_scan_positions(double (&v)[NS], int lane) {
 }
 
 // Delete position k of the positive set (p -> p-1): re-triangularise T, shift idx and x.
-template <int NS>
-__device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& p, int lane, double (&x)[NS]) {
+// PS = position slots per lane (positions lane + 32 t, t < PS): ceil(pmax / 32), which can be smaller than the column
+// slots NS of the Slots layout (FA stage: 60 columns, at most 32 positions) — the loops then run half as long.
+template <int NS, int PS = NS>
+__device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& p, int lane, double (&x)[PS]) {
     const int oT = W.T;
     // rotation parameters from the prefix sums of squares of row k
-    double tau[NS], Sq[NS];
+    double tau[PS], Sq[PS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int q = lane + 32 * t;
         tau[t] = (q >= k && q < p) ? S[oT + tri(q) + k] : 0.0;
         Sq[t] = tau[t] * tau[t];
     }
-    warp_scan_positions<NS>(Sq, lane);
+    warp_scan_positions<PS>(Sq, lane);
     // nu_q = sqrt(S_q); step q (k <= q <= p-2) needs c_q = tau_{q+1}/nu_{q+1}, s_q = nu_q/nu_{q+1}
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int q = lane + 32 * t;
         if (q >= k && q < p) {
             S[W.rs + q] = sqrt(Sq[t]);   // nu_q
@@ -653,9 +670,9 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
         }
     }
     __syncwarp();
-    double cq[NS], sq[NS];
+    double cq[PS], sq[PS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int q = lane + 32 * t;
         cq[t] = 0.0;
         sq[t] = 1.0;
@@ -667,7 +684,7 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
     }
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int q = lane + 32 * t;
         if (q >= k && q + 1 < p) {
             S[W.gs + q] = cq[t];
@@ -676,17 +693,17 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
         if (q < p) S[W.xs + q] = x[t];   // x is shifted through xs below
     }
     __syncwarp();
-    int idx_next[NS];
+    int idx_next[PS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int i = lane + 32 * t;
         idx_next[t] = (i >= k && i + 1 < p) ? SI(W.ix, i + 1) : -1;
         if (i >= k) x[t] = (i + 1 < p) ? S[W.xs + i + 1] : 0.0;
     }
     // row sweep: lane-slot owns old row rr (rr != k); carry starts as T(rr, k)
-    double carry[NS];
+    double carry[PS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int rr = lane + 32 * t;
         carry[t] = (rr < k) ? S[oT + tri(k) + rr] : 0.0;
     }
@@ -694,9 +711,9 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
     for (int q = k; q + 1 < p; ++q) {
         const double c = S[W.gs + q], s = S[W.rs + q];
         const int tq1 = oT + tri(q + 1), tq = oT + tri(q);
-        double nv[NS];
+        double nv[PS];
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int rr = lane + 32 * t;
             double b = (rr <= q + 1 && rr != k) ? S[tq1 + rr] : 0.0;
             nv[t] = s * b - c * carry[t];
@@ -704,20 +721,20 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
         }
         __syncwarp();
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int rr = lane + 32 * t;
             if (rr != k && rr <= q + 1) S[tq + rr - (rr > k ? 1 : 0)] = nv[t];
         }
     }
     __syncwarp();
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int i = lane + 32 * t;
         if (idx_next[t] >= 0) SI(W.ix, i) = idx_next[t];
     }
     --p;
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int i = lane + 32 * t;
         if (i < p) S[W.xs + i] = x[t];
     }
@@ -736,13 +753,13 @@ __device__ __forceinline__ void remove_position(const Slots<NS>& W, int k, int& 
 #else
 #define MET2_DSPACE_FN __forceinline__
 #endif
-template <int NS>
+template <int PS>
 __device__ MET2_DSPACE_FN double2 dspace_candidate(int oT, int oGs, int oRs, int oIx, const double* __restrict__ DtR,
                                                  int oMR, int mrows, int j, int p, int lane) {
-    double a[NS];
-    tmul<NS>(oT, oRs, p, lane, a);
+    double a[PS];
+    tmul<PS>(oT, oRs, p, lane, a);
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int k = lane + 32 * t;
         if (k < p) S[oGs + k] = a[t];
     }
@@ -772,7 +789,7 @@ __device__ MET2_DSPACE_FN double2 dspace_candidate(int oT, int oGs, int oRs, int
 // support has non-positive entries) and the main loop continues as usual.  The minimiser of the (strictly convex)
 // Tikhonov problem does not depend on the starting point; tools/proto_warm_start.py measured identical supports and
 // lambda/k_est within 1e-11 against SciPy's cold-started path, with 13x fewer main-loop iterations.
-template <int NS, bool GSH>
+template <int NS, bool GSH, int PS = NS>
 __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
                                          bool reg, double lam, int n, int mrows, int lane, int& status, int p0 = 0,
                                          bool t_ready = false) {
@@ -787,9 +804,9 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         if (col < n) S[W.xc + col] = 0.0;
     }
     unsigned inP = 0u;
-    double x[NS], y[NS], z[NS];
+    double x[PS], y[PS], z[PS];
 #pragma unroll
-    for (int t = 0; t < NS; ++t) x[t] = y[t] = z[t] = 0.0;
+    for (int t = 0; t < PS; ++t) x[t] = y[t] = z[t] = 0.0;
     int p = 0, iter = 0;
     __syncwarp();
 
@@ -799,7 +816,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         double gjj = Gat(j, j);
         if (reg) gjj = fma(lam, S[oKb + 2 * n + j], gjj);
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int i = lane + 32 * t;
             if (i < p) {
                 int r = SI(W.ix, i);
@@ -812,11 +829,11 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             }
         }
         __syncwarp();
-        double r[NS];
-        tmul_transposed<NS>(W.T, W.gs, p, lane, r);
+        double r[PS];
+        tmul_transposed<PS>(W.T, W.gs, p, lane, r);
         double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int i = lane + 32 * t;
             if (i < p) {
                 s1 = fma(r[t], r[t], s1);
@@ -836,7 +853,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             __syncwarp();
             const double* DtR = *reinterpret_cast<const double* const*>(S + W.aux());
             if (DtR) {
-                const double2 qd = dspace_candidate<NS>(W.T, W.gs, W.rs, W.ix, DtR, SI(W.aux() + 1, 0), mrows, j, p, lane);
+                const double2 qd = dspace_candidate<PS>(W.T, W.gs, W.rs, W.ix, DtR, SI(W.aux() + 1, 0), mrows, j, p, lane);
                 rho2 = qd.x;
                 rinv = rsqrt_fast(rho2);
                 ynew = qd.y * rinv;
@@ -850,11 +867,11 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
                    ok ? "accepted" : "rejected");
         __syncwarp();
         if (!ok) return false;
-        double acc[NS];
-        tmul<NS>(W.T, W.rs, p, lane, acc);
+        double acc[PS];
+        tmul<PS>(W.T, W.rs, p, lane, acc);
         const int tp = W.T + tri(p);
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int k = lane + 32 * t;
             if (k < p) {
                 double tk = -acc[t] * rinv;
@@ -897,7 +914,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             }
             // x = the carried-over coefficients; y = T^T c_P and z = T y are computed at the top of the secondary loop
 #pragma unroll
-            for (int t = 0; t < NS; ++t) {
+            for (int t = 0; t < PS; ++t) {
                 int i = lane + 32 * t;
                 x[t] = (i < p) ? S[W.xs + i] : 0.0;
             }
@@ -915,23 +932,23 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         // (Measured: T2 stage 426 -> 398 ms.  The same one-step drop for EVERY warm start did not pay — X2 unchanged,
         // L-curve 598 -> 621 ms — because a carried-over support rarely loses more than one or two columns.)
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int i = lane + 32 * t;
             if (i < p) S[W.gs + i] = S[W.cc + SI(W.ix, i)];
         }
         __syncwarp();
-        tmul_transposed<NS>(W.T, W.gs, p, lane, y);
+        tmul_transposed<PS>(W.T, W.gs, p, lane, y);
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int i = lane + 32 * t;
             if (i < p) S[W.rs + i] = y[t];
         }
         __syncwarp();
-        tmul<NS>(W.T, W.rs, p, lane, z);
+        tmul<PS>(W.T, W.rs, p, lane, z);
         __syncwarp();
         unsigned negm = 0u;
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int i = lane + 32 * t;
             if (i < p && z[t] <= 0.0) negm |= 1u << t;
         }
@@ -940,7 +957,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         while (true) {
             int k = -1;
 #pragma unroll
-            for (int t = 0; t < NS; ++t) {
+            for (int t = 0; t < PS; ++t) {
                 int i = lane + 32 * t;
                 if (((negm >> t) & 1u) && i < cur && i > k) k = i;
             }
@@ -950,12 +967,12 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             if (colk / NS == lane) inP &= ~(1u << (colk % NS));
             if (lane == 0) S[W.xc + colk] = 0.0;
             __syncwarp();
-            remove_position<NS>(W, k, p, lane, x);
+            remove_position<NS, PS>(W, k, p, lane, x);
             cur = k;
         }
         if (!have_yz) {
 #pragma unroll
-            for (int t = 0; t < NS; ++t) y[t] = z[t] = 0.0;
+            for (int t = 0; t < PS; ++t) y[t] = z[t] = 0.0;
         }
     }
 
@@ -1086,20 +1103,20 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             } else if (fresh) {
                 // y = T^T c_P and z = T y from scratch (after a warm-start rebuild or a removal)
 #pragma unroll
-                for (int t = 0; t < NS; ++t) {
+                for (int t = 0; t < PS; ++t) {
                     int i = lane + 32 * t;
                     if (i < p) S[W.gs + i] = S[W.cc + SI(W.ix, i)];
                 }
                 __syncwarp();
-                tmul_transposed<NS>(W.T, W.gs, p, lane, y);
+                tmul_transposed<PS>(W.T, W.gs, p, lane, y);
 #pragma unroll
-                for (int t = 0; t < NS; ++t) {
+                for (int t = 0; t < PS; ++t) {
                     int i = lane + 32 * t;
                     if (i < p) S[W.rs + i] = y[t];
                     else y[t] = 0.0;
                 }
                 __syncwarp();
-                tmul<NS>(W.T, W.rs, p, lane, z);
+                tmul<PS>(W.T, W.rs, p, lane, z);
                 __syncwarp();
             }
             fresh = true;
@@ -1111,7 +1128,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             }
             bool neg = false;
 #pragma unroll
-            for (int t = 0; t < NS; ++t) {
+            for (int t = 0; t < PS; ++t) {
                 int i = lane + 32 * t;
                 if (i < p && z[t] <= 0.0) neg = true;
             }
@@ -1119,7 +1136,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             double bt = 2.0;
             int bi = -1;
 #pragma unroll
-            for (int t = 0; t < NS; ++t) {
+            for (int t = 0; t < PS; ++t) {
                 int i = lane + 32 * t;
                 if (i < p && z[t] <= 0.0) {
                     double tt = x[t] / (x[t] - z[t]);
@@ -1133,7 +1150,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
             int jb = warp_argmin_nonneg(bt, bi, alpha);
             if (jb < 0) break;
 #pragma unroll
-            for (int t = 0; t < NS; ++t) {
+            for (int t = 0; t < PS; ++t) {
                 int i = lane + 32 * t;
                 if (i < p) x[t] = x[t] + alpha * (z[t] - x[t]);
             }
@@ -1144,10 +1161,10 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
                 if (colk / NS == lane) inP &= ~(1u << (colk % NS));
                 if (lane == 0) S[W.xc + colk] = 0.0;
                 __syncwarp();
-                remove_position<NS>(W, k, p, lane, x);
+                remove_position<NS, PS>(W, k, p, lane, x);
                 int q = 0x7fffffff;
 #pragma unroll
-                for (int t = NS - 1; t >= 0; --t) {
+                for (int t = PS - 1; t >= 0; --t) {
                     int i = lane + 32 * t;
                     if (i < p && x[t] <= 0.0) q = i;
                 }
@@ -1158,7 +1175,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
         }
         if (stop) break;
 #pragma unroll
-        for (int t = 0; t < NS; ++t) {
+        for (int t = 0; t < PS; ++t) {
             int i = lane + 32 * t;
             if (i < p) {
                 x[t] = z[t];
@@ -1170,7 +1187,7 @@ __device__ __forceinline__ int nnls_gram(const Slots<NS>& W, int oG, const doubl
     }
     // xs mirrors x on every path; make the column-space copy current for the caller
 #pragma unroll
-    for (int t = 0; t < NS; ++t) {
+    for (int t = 0; t < PS; ++t) {
         int i = lane + 32 * t;
         if (i < p) S[W.xc + SI(W.ix, i)] = x[t];
     }

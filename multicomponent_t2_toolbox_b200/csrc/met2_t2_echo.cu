@@ -43,18 +43,32 @@ constexpr int EC_LDD = RD + 2;        // row stride of the staged Ct table [colu
 constexpr int EC_NCOL = 64;           // columns of the X2 kernel (nT2 <= 64), zero rows beyond nT2
 
 struct EchoOff {
-    int Ct, Mp, B, V, D;   // offsets into S: staged Ct table; per warp: M_P packed lower, bt (RD), v (RD), d (RD)
+    int Ct, RC, Mp, B, V, D;   // offsets into S: staged Ct table, (row, column) bytes of the packed triangle; per warp:
+                               // M_P packed lower, bt (RD), v (RD), d (RD)
 };
+constexpr int EC_RC_DOUBLES = (2 * tri(RD) + 7) / 8;   // tri(RD) byte pairs
 
-// per-warp shared memory of the X2 kernel (doubles): Slots<2>(pmax RD) | M_P packed lower tri(RD) | raw signal (64) |
-// bt (32) | v (32) | d (32) | Brent-best snapshot of xt (64)
+// (row, column) of every packed lower-triangle entry, as bytes: rc[2 e] = r, rc[2 e + 1] = c for e = tri(r) + c.
+__device__ __forceinline__ void echo_stage_rc(int oRC) {
+    unsigned char* rc = reinterpret_cast<unsigned char*>(S + oRC);
+    for (int e = threadIdx.x; e < tri(RD); e += blockDim.x) {
+        int r = 0;
+        while (tri(r + 1) <= e) ++r;
+        rc[2 * e] = (unsigned char)r;
+        rc[2 * e + 1] = (unsigned char)(e - tri(r));
+    }
+}
+
+// per-warp shared memory of the X2 kernel (doubles): Slots<2>(pmax RD) | M_P packed lower tri(RD) | raw signal, later
+// the Brent-best snapshot of xt (64) | bt (RD) | v (RD) | d (RD) — 8.8 KB, so that 20 warps fit beside the tables
+// (the kernel is latency bound: 8 / 12 / 14 / 16 warps measured 329 / 250 / 234 / 211 ms per volume)
 __host__ __device__ __forceinline__ int echo_warp_doubles() {
-    return (Slots<2>::doubles(RD) + tri(RD) + 64 + 32 + 32 + 32 + 64 + 31) & ~31;
+    return (Slots<2>::doubles(RD) + tri(RD) + 64 + 3 * RD + 7) & ~7;
 }
 // CTA tables (doubles): G [n][ldg] | Ct [64][EC_LDD] | U [m][RD] | M_full packed tri(RD) | l (64) | 1/l (64) | logT2 (64) |
-// comp (8)
+// comp (8) | (row, column) bytes of the packed triangle
 __host__ __device__ __forceinline__ int echo_table_doubles(int n, int m) {
-    return (n * t2_ldg(n) + EC_NCOL * EC_LDD + m * RD + tri(RD) + 3 * 64 + 8 + 31) & ~31;
+    return (n * t2_ldg(n) + EC_NCOL * EC_LDD + m * RD + tri(RD) + 3 * 64 + 8 + EC_RC_DOUBLES + 31) & ~31;
 }
 
 // g = Ct^T v for v at S[oV .. oV + RD): lane + 32 s = column (NC column slots per lane: nT2 <= 32 NC).
@@ -113,17 +127,20 @@ __device__ __forceinline__ bool echo_refactor(const Slots<2>& W, const EchoOff& 
     return rebuild_T_blocked<2>(W, Aent, RD, lane);
 }
 
-// M_P += sgn d d^T on the packed lower triangle (row = lane), d = column j of the staged Ct table; leaves d in S[O.D..].
+// M_P += sgn d d^T on the packed lower triangle, d = column j of the staged Ct table; leaves d in S[O.D..].
+// The tri(RD) = 300 packed entries are dealt to the 32 lanes (entry e = lane + 32 t) with their (row, column) read from
+// a byte table built once per CTA (O.RC): ten balanced steps instead of RD steps of a half-empty warp (the row-per-lane
+// version was the single hottest line of the first reduced kernel, 7.6 % of its instructions).
 __device__ __forceinline__ void echo_mp_rank1(const EchoOff& O, int j, double sgn, int lane) {
     const double d = (lane < RD) ? S[O.Ct + j * EC_LDD + lane] : 0.0;
     __syncwarp();
     if (lane < RD) S[O.D + lane] = d;
     __syncwarp();
-    if (lane < RD) {
-        const int row = O.Mp + tri(lane);
-        const double sd = sgn * d;
+    const unsigned char* rc = reinterpret_cast<const unsigned char*>(S + O.RC);
 #pragma unroll 1
-        for (int c = 0; c <= lane; ++c) S[row + c] = fma(sd, S[O.D + c], S[row + c]);
+    for (int e = lane; e < tri(RD); e += 32) {
+        const double dr = S[O.D + rc[2 * e]], dc = S[O.D + rc[2 * e + 1]];
+        S[O.Mp + e] = fma(sgn * dr, dc, S[O.Mp + e]);
     }
     __syncwarp();
 }
@@ -434,7 +451,10 @@ __device__ __forceinline__ void echo_stage_diag(const T2Args& A, int ncol, int n
     }
 }
 
-constexpr int ECHO_MAX_THREADS = 512;   // 16 warps at 128 registers
+#ifndef MET2_ECHO_MAX_THREADS
+#define MET2_ECHO_MAX_THREADS 640       // A/B switch: 512 = 16 warps at 128 registers, 640 = 20 warps at 96 registers
+#endif
+constexpr int ECHO_MAX_THREADS = MET2_ECHO_MAX_THREADS;
 
 template <int ME>
 __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args A) {
@@ -450,21 +470,24 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
     const int oIL = oL + 64;
     const int oLogT2 = oIL + 64;
     unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + 64);
+    const int oRC = oLogT2 + 64 + 8;
     const int wbase = echo_table_doubles(n, m) + warp * echo_warp_doubles();
     Slots<2> W;
     W.carve(wbase, RD);
     EchoOff O;
     O.Ct = oCt;
+    O.RC = oRC;
     O.Mp = wbase + Slots<2>::doubles(RD);
     const int oM = O.Mp + tri(RD);
     O.B = oM + 64;
-    O.V = O.B + 32;
-    O.D = O.V + 32;
-    const int oSnap = O.D + 32;
+    O.V = O.B + RD;
+    O.D = O.V + RD;
+    const int oSnap = oM;     // the raw signal is not needed once it is projected (bt) and km is in a register
 
     if (threadIdx.x == 0) s_badL = 0;
     __syncthreads();
     echo_stage_diag(A, 64, n, oL, oIL, oLogT2, scomp, &s_badL);
+    echo_stage_rc(oRC);
     const int ntiles = A.counters[0];
 
     while (true) {
@@ -549,7 +572,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                 }
                 set_dspace<2>(W, Cg, O.B, lane);     // candidate test in the reduced space: rows of C, right-hand side bt
                 int nst = 0;
-                (void)nnls_gram<2, true>(W, oG, nullptr, ldg, 0, false, 0.0, n, RD, lane, nst, 0, false);
+                (void)nnls_gram<2, true, 1>(W, oG, nullptr, ldg, 0, false, 0.0, n, RD, lane, nst, 0, false);   // <= RD positions
                 // xt0 = l * x0 -> column space; SSE = |Ct xt0 - bt|^2 + |b_perp|^2
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
@@ -608,7 +631,15 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
 #pragma unroll
                     for (int s = 0; s < 2; ++s) S[W.xc + lane + 32 * s] = x[s];
                     __syncwarp();
-                    const double sse = echo_fit_sse(W.xc, O, n, lane, -1) + perp;
+                    // residual of the reduced system: bt - Ct xt = lam v exactly (push-through identity), v left in
+                    // S[O.V..] by the solve echo_nnls accepted; the explicit product only after an itmax stop
+                    double sse;
+                    if (est & 1) {
+                        sse = echo_fit_sse(W.xc, O, n, lane, -1) + perp;
+                    } else {
+                        const double ve = (lane < RD) ? S[O.V + lane] : 0.0;
+                        sse = fma(lam * lam, warp_sum(ve * ve), perp);
+                    }
                     const double cost = fabs(sse - A.cfg.factor * SSE) / SSE;
                     const double lam_eval = lam;
                     const bool more = B.feed(cost, lam);
@@ -656,7 +687,7 @@ __host__ __device__ __forceinline__ int echo_tik_warp_doubles() {
 // CTA tables (doubles): Ct [32 NC][EC_LDD] | U [m][RD] | l | 1/l | logT2 (32 NC each) | comp
 template <int NC>
 __host__ __device__ __forceinline__ int echo_tik_table_doubles(int m) {
-    return (32 * NC * EC_LDD + m * RD + 3 * 32 * NC + (32 * NC + 7) / 8 + 31) & ~31;
+    return (32 * NC * EC_LDD + m * RD + 3 * 32 * NC + (32 * NC + 7) / 8 + EC_RC_DOUBLES + 31) & ~31;
 }
 
 template <int NC, int ME>
@@ -671,11 +702,13 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
     const int oIL = oL + NCOL;
     const int oLogT2 = oIL + NCOL;
     unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLogT2 + NCOL);
+    const int oRC = oLogT2 + NCOL + (NCOL + 7) / 8;
     const int wbase = echo_tik_table_doubles<NC>(m) + warp * echo_tik_warp_doubles<NC>();
     Slots<2> W;
     W.carve(wbase, RD);
     EchoOff O;
     O.Ct = oCt;
+    O.RC = oRC;
     O.Mp = wbase + Slots<2>::doubles(RD);
     const int oM = O.Mp + tri(RD);
     O.B = oM + 64;
@@ -688,6 +721,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
     if (threadIdx.x == 0) s_badL = 0;
     __syncthreads();
     echo_stage_diag(A, NCOL, n, oL, oIL, oLogT2, scomp, &s_badL);
+    echo_stage_rc(oRC);
     const int ntiles = A.counters[0];
 
     while (true) {

@@ -481,6 +481,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
     constexpr int method = METHOD;
+    // position slots of the solver: a plain solve has at most min(nT2, nTE) <= 32 ME positive columns
+    constexpr int PS = (METHOD == MET2_REG_NNLS && ME < NS) ? ME : NS;
     const int oG = 0;
     const int ldg = t2_ldg(n);
     const int oKb = oG + n * ldg;        // K band rows 0..4
@@ -665,7 +667,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 };
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
-                    p = nnls_gram<NS, true>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
+                    p = nnls_gram<NS, true, PS>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
                                             warm ? p : 0, t_ready);
                     t_ready = false;
                     if (method == MET2_REG_NNLS && nst == 0 && p > 0)

@@ -6,7 +6,7 @@ workload (config 2: spline FA = 15 + 1 plain solves; X2-I = 1 plain + Brent eval
 on seeded phantom voxels.  The Brent abscissae are taken from the real SciPy path so the solve sequence is the
 reference's.  Writes oracle/F_ALG.json; bench.py quotes the numbers.
 
-    python oracle/flop_model.py [n_voxels]
+    python oracle/flop_model.py [n_voxels = 1024]      (all local cores; ~10 minutes for 1 024 voxels on 8 cores)
 """
 import json
 import os
@@ -23,44 +23,50 @@ from multicomponent_t2_toolbox_b200.phantom import make_phantom  # noqa: E402
 from scipy.optimize import fminbound  # noqa: E402
 
 
+_G = {}
+
+
+def _voxel(v):
+    g, Dic, DicLR, L, sig = _G["g"], _G["Dic"], _G["DicLR"], _G["L"], _G["sig"]
+    M = sig[v]
+    c = O.FlopCounter()
+    for i in range(15):
+        O.lh_nnls(np.ascontiguousarray(DicLR[:, :, i]), M, counter=c)
+    idx, _, _, _ = O.spline_optimal_FA(M, DicLR, Dic, g["alpha_spline"], g["alpha_values"])
+    D = np.ascontiguousarray(Dic[:, :, idx])
+    O.lh_nnls(D, M, counter=c)
+    fa = c.flops
+    c = O.FlopCounter()
+    Mn = M / M[0]
+    f0, _, _ = O.lh_nnls(D, Mn, counter=c)
+    SSE = np.sum((D @ f0 - Mn) ** 2)
+    Maug = np.concatenate((Mn, np.zeros(60)))
+
+    def obj(x):
+        f, _, _ = O.lh_nnls(np.concatenate((D, np.sqrt(x) * L)), Maug, counter=c)
+        return abs(np.sum((D @ f - Mn) ** 2) - 1.02 * SSE) / SSE
+    reg = fminbound(obj, 0.0, 10.0, xtol=1e-5, maxfun=300)
+    O.lh_nnls(np.concatenate((D, np.sqrt(reg) * L)), Maug, counter=c)
+    return fa, c.flops, c.solves, c.outer
+
+
 def main():
-    nv = int(sys.argv[1]) if len(sys.argv) > 1 else 12
-    ph = make_phantom((96, 4, 1), seed=2, fa_mode="b1")
+    import multiprocessing as mp
+    nv = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+    ph = make_phantom((96, 96, 1), seed=2, fa_mode="b1")
     sig = ph["data"].reshape(-1, 32)
     rng = np.random.default_rng(0)
     pick = rng.choice(sig.shape[0], nv, replace=False)
     g = O._grids("X2", "I", "spline", 40.0, 32, 10.0, 1000.0)
-    Dic = O.create_Dic_3D(60, g["T2s"], g["T1s"], 32, 10.0, g["alpha_values"], 1000.0)
-    DicLR = O.create_Dic_3D(60, g["T2s"], g["T1s"], 32, 10.0, g["alpha_spline"], 1000.0)
-    L = g["L"]
-    fa_flops, t2_flops, t2_solves, t2_outer = [], [], [], []
-    for v in pick:
-        M = sig[v]
-        c = O.FlopCounter()
-        for i in range(15):
-            O.lh_nnls(np.ascontiguousarray(DicLR[:, :, i]), M, counter=c)
-        idx, _, _, _ = O.spline_optimal_FA(M, DicLR, Dic, g["alpha_spline"], g["alpha_values"])
-        D = np.ascontiguousarray(Dic[:, :, idx])
-        O.lh_nnls(D, M, counter=c)
-        fa_flops.append(c.flops)
-        c = O.FlopCounter()
-        Mn = M / M[0]
-        f0, _, _ = O.lh_nnls(D, Mn, counter=c)
-        SSE = np.sum((D @ f0 - Mn) ** 2)
-        Maug = np.concatenate((Mn, np.zeros(60)))
-
-        def obj(x):
-            f, _, _ = O.lh_nnls(np.concatenate((D, np.sqrt(x) * L)), Maug, counter=c)
-            return abs(np.sum((D @ f - Mn) ** 2) - 1.02 * SSE) / SSE
-        reg = fminbound(obj, 0.0, 10.0, xtol=1e-5, maxfun=300)
-        O.lh_nnls(np.concatenate((D, np.sqrt(reg) * L)), Maug, counter=c)
-        t2_flops.append(c.flops)
-        t2_solves.append(c.solves)
-        t2_outer.append(c.outer)
-        print("voxel %d: FA %.3f MFLOP, X2 %.3f MFLOP, %d solves, %d outer iterations" %
-              (v, fa_flops[-1] / 1e6, c.flops / 1e6, c.solves, c.outer), flush=True)
+    _G.update(g=g, sig=sig, L=g["L"],
+              Dic=O.create_Dic_3D(60, g["T2s"], g["T1s"], 32, 10.0, g["alpha_values"], 1000.0),
+              DicLR=O.create_Dic_3D(60, g["T2s"], g["T1s"], 32, 10.0, g["alpha_spline"], 1000.0))
+    with mp.get_context("fork").Pool(os.cpu_count()) as pool:
+        res = np.array(pool.map(_voxel, [int(v) for v in pick], chunksize=4), dtype=np.float64)
+    fa_flops, t2_flops, t2_solves, t2_outer = res.T
     out = dict(workload="config 2: spline FA + X2-I, nTE=32, nT2=60", n_voxels=nv,
-               F_alg_fa_spline=float(np.mean(fa_flops)), F_alg_t2_x2_I=float(np.mean(t2_flops)),
+               F_alg_fa_spline=float(np.mean(fa_flops)), F_alg_fa_spline_sd=float(np.std(fa_flops)),
+               F_alg_t2_x2_I=float(np.mean(t2_flops)), F_alg_t2_x2_I_sd=float(np.std(t2_flops)),
                F_alg_t2_x2_I_min=float(np.min(t2_flops)), F_alg_t2_x2_I_max=float(np.max(t2_flops)),
                nnls_solves_x2=float(np.mean(t2_solves)), outer_iterations_x2=float(np.mean(t2_outer)),
                model="SURVEY.md 8d: gradient 2(m-p)|Z|, Householder build 3(m-p) + apply 4(m-p) per column, "

@@ -153,9 +153,10 @@ def test_echo_space_and_gram_kernels_vs_reference(golden_config2, golden_methods
                          max_abs_dMWF_agreeing=float(np.abs(_mwf(f, plan) - _mwf(f_ref, plan))[~bad].max()),
                          est_signal_vs_D_f_rel=float(est_err), status_nonzero=int((out["status"] != 0).sum()))
     pi = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="InvT2", FA_method="spline")
-    assert not (pi.t2_cfg().flags & ECHO)                       # InvT2: the Gram-domain kernel measured (slightly) faster
-    e = pi.t2_fit(sig, idx, flags=ECHO)
-    d = pi.t2_fit(sig, idx)
+    pg = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="InvT2", FA_method="spline", echo_space=False)
+    assert (pi.t2_cfg().flags & ECHO) and not (pg.t2_cfg().flags & ECHO)
+    e = pi.t2_fit(sig, idx)
+    d = pg.t2_fit(sig, idx)
     fe, fd = e["fsol"].cpu().numpy(), d["fsol"].cpu().numpy()
     bad_ab = np.any((fe > 0) != (fd > 0), axis=1)
     n_or = 160
