@@ -398,7 +398,7 @@ def run_ours(args):
 def one_volume(args, torch, dist, pipeline, plan, dev, rank, world, host_group, shape, barrier):
     """ONE config-2 volume (seed 2) spread over the N GPUs, host memory in -> host memory out, two ways:
       (a) the product API: pipeline.MultiGpuFit in ONE process (what motor_recon_met2 does with num_cores = N): a host
-          thread per GPU copies its chunks of the pinned input, fits, and copies every output into its rows of one set
+          device copies its chunks of the pinned input, fits, and copies every output into its rows of one set
           of pinned host arrays.  Measured on rank 0 (wall clock around the call: it is a host API) while the other
           ranks wait on a HOST barrier, their GPUs idle;
       (b) one process per GPU (this torchrun job): every rank copies in its chunks, fits, and the outputs are gathered
@@ -484,7 +484,7 @@ def one_volume(args, torch, dist, pipeline, plan, dev, rank, world, host_group, 
                                     "h2d_bytes": int(V * N_ECHOES * 8),
                                     "d2h_bytes": int(sum(t.numel() * t.element_size() for t in bufs.values())),
                                     "note": "pipeline.MultiGpuFit (the path of motor_recon_met2 with num_cores = N): one "
-                                            "process, one host thread per GPU, pinned host in -> pinned host out, no "
+                                            "process, all GPUs enqueued from one thread, pinned host in -> pinned host out, no "
                                             "collective; wall clock around the call, other ranks' GPUs idle"}
         except Exception as exc:   # never lose the headline line over the extra measurement
             out["multi_gpu_fit"] = {"error": repr(exc)[:300]}

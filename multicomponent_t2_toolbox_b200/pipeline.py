@@ -3,6 +3,9 @@ NIfTI writer" (motor/motor_recon_met2_real_data.py:167-182, 279, 349-373, 428-47
 -> scatter.  Also holds the voxel-slab partition used for multi-GPU runs: voxels are independent, so
 each rank fits a contiguous slab of the masked-voxel list and no collective runs during the fit.
 """
+import os
+import time
+
 import numpy as np
 import torch
 
@@ -99,8 +102,6 @@ class MultiGpuFit:
         self.chunks_per_device = int(chunks_per_device)
         self.streams = [torch.cuda.Stream(device=p.dev) for p in self.plans]
         self._bufs = {}
-        from concurrent.futures import ThreadPoolExecutor
-        self._pool = ThreadPoolExecutor(max_workers=len(self.plans))
 
     @classmethod
     def create(cls, n_gpus, *plan_args, chunks_per_device=4, **plan_kwargs):
@@ -115,58 +116,81 @@ class MultiGpuFit:
                                 range(n)))
         return cls(plans, chunks_per_device)
 
-    def _device_run(self, d, ranges, sig, sig_fa, out):
-        plan, stream = self.plans[d], self.streams[d]
-        Vd = sum(hi - lo for lo, hi in ranges)
-        if Vd == 0:
-            return None
-        with torch.cuda.device(plan.dev), torch.cuda.stream(stream):
-            key = (Vd, sig_fa is not None)
-            bufs = self._bufs.get((d,) + key)
-            if bufs is None:
-                bufs = dict(sig=torch.empty((Vd, plan.nTE), dtype=torch.float64, device=plan.dev),
-                            sig_fa=(torch.empty((Vd, plan.nTE), dtype=torch.float64, device=plan.dev)
-                                    if sig_fa is not None else None), fa=None, t2=None)
-                self._bufs = {k: v for k, v in self._bufs.items() if k[0] != d}
-                self._bufs[(d,) + key] = bufs
-            o = 0
-            for lo, hi in ranges:
-                bufs["sig"][o:o + hi - lo].copy_(sig[lo:hi], non_blocking=True)
-                if sig_fa is not None:
-                    bufs["sig_fa"][o:o + hi - lo].copy_(sig_fa[lo:hi], non_blocking=True)
-                o += hi - lo
-            fa = plan.fa_fit(bufs["sig"] if sig_fa is None else bufs["sig_fa"], out=bufs["fa"])
-            t2 = plan.t2_fit(bufs["sig"], fa["fa_index"], out=bufs["t2"])
-            bufs["fa"], bufs["t2"] = fa, t2
-            dev_out = dict(fa_index=fa["fa_index"], fa_deg=fa["fa_deg"], km=fa["km"], fa_status=fa["status"],
-                           fsol=t2["fsol"], est_signal=t2["est_signal"], reg=t2["reg"], maps=t2["maps"],
-                           status=t2["status"])
-            o = 0
-            for lo, hi in ranges:
-                for k in OUT_KEYS:
-                    out[k][lo:hi].copy_(dev_out[k][o:o + hi - lo], non_blocking=True)
-                o += hi - lo
-            fsum = fa["fsol_sum"].to("cpu", non_blocking=False)      # npc doubles; also drains this device's stream
-            stream.synchronize()
-        return fsum
-
     def fit(self, sig, sig_fa=None, out=None):
         """sig[V, nTE] (+ sig_fa for the FA stage): host tensors / arrays, pinned for full-speed DMA.  `out`: dict of
-        host tensors as from `host_buffers` (allocated if None).  Returns dict of numpy views of `out`."""
+        host tensors as from `host_buffers` (allocated if None).  Returns dict of numpy views of `out`.
+
+        Everything is ENQUEUED from this one thread, phase by phase over the devices (copies in, FA stage, T2 stage,
+        copies out: ~0.1 ms of host time per device and phase, all asynchronous), then the streams are drained.  A
+        thread per device was measured slower: two threads inside the CUDA runtime stalled each other for ~36 ms per
+        call (profiles/r02_multi_gpu.json), a serial enqueue staggers the devices by well under a millisecond."""
         sig = torch.as_tensor(sig)
         if sig_fa is not None:
             sig_fa = torch.as_tensor(sig_fa)
         V = sig.shape[0]
         if out is None:
             out = host_buffers(self.plans[0], V)
-        parts = chunk_deal(V, len(self.plans), self.chunks_per_device)
-        futs = [self._pool.submit(self._device_run, d, parts[d], sig, sig_fa, out) for d in range(len(self.plans))]
-        sums = [f.result() for f in futs]
+        nd = len(self.plans)
+        parts = chunk_deal(V, nd, self.chunks_per_device)
+        trace = [dict() for _ in self.plans] if os.environ.get("MET2_MULTI_TRACE") else None
+        t0 = time.perf_counter()
+
+        def mark(d, what):
+            if trace is not None:
+                trace[d][what] = round(1e3 * (time.perf_counter() - t0), 2)
+        live = [d for d in range(nd) if parts[d]]
+        bufs = {}
+        for d in live:                                   # ---- phase 1: host -> device
+            plan = self.plans[d]
+            Vd = sum(hi - lo for lo, hi in parts[d])
+            key = (d, Vd, sig_fa is not None)
+            b = self._bufs.get(key)
+            with torch.cuda.device(plan.dev), torch.cuda.stream(self.streams[d]):
+                if b is None:
+                    b = dict(sig=torch.empty((Vd, plan.nTE), dtype=torch.float64, device=plan.dev),
+                             sig_fa=(torch.empty((Vd, plan.nTE), dtype=torch.float64, device=plan.dev)
+                                     if sig_fa is not None else None), fa=None, t2=None)
+                    self._bufs = {k: v for k, v in self._bufs.items() if k[0] != d}
+                    self._bufs[key] = b
+                o = 0
+                for lo, hi in parts[d]:
+                    b["sig"][o:o + hi - lo].copy_(sig[lo:hi], non_blocking=True)
+                    if sig_fa is not None:
+                        b["sig_fa"][o:o + hi - lo].copy_(sig_fa[lo:hi], non_blocking=True)
+                    o += hi - lo
+            bufs[d] = b
+            mark(d, "h2d_enqueued")
+        for d in live:                                   # ---- phase 2: flip-angle stage
+            plan, b = self.plans[d], bufs[d]
+            with torch.cuda.device(plan.dev), torch.cuda.stream(self.streams[d]):
+                b["fa"] = plan.fa_fit(b["sig"] if sig_fa is None else b["sig_fa"], out=b["fa"])
+            mark(d, "fa_enqueued")
+        for d in live:                                   # ---- phase 3: spectrum fit + maps
+            plan, b = self.plans[d], bufs[d]
+            with torch.cuda.device(plan.dev), torch.cuda.stream(self.streams[d]):
+                b["t2"] = plan.t2_fit(b["sig"], b["fa"]["fa_index"], out=b["t2"])
+            mark(d, "t2_enqueued")
+        for d in live:                                   # ---- phase 4: device -> its rows of the host arrays
+            plan, b = self.plans[d], bufs[d]
+            fa, t2 = b["fa"], b["t2"]
+            dev_out = dict(fa_index=fa["fa_index"], fa_deg=fa["fa_deg"], km=fa["km"], fa_status=fa["status"],
+                           fsol=t2["fsol"], est_signal=t2["est_signal"], reg=t2["reg"], maps=t2["maps"],
+                           status=t2["status"])
+            with torch.cuda.device(plan.dev), torch.cuda.stream(self.streams[d]):
+                o = 0
+                for lo, hi in parts[d]:
+                    for k in OUT_KEYS:
+                        out[k][lo:hi].copy_(dev_out[k][o:o + hi - lo], non_blocking=True)
+                    o += hi - lo
+            mark(d, "d2h_enqueued")
         fs = torch.zeros(self.plans[0].npc, dtype=torch.float64)
-        for t in sums:                      # fixed device order: deterministic for a given device count
-            if t is not None:
-                fs += t
+        for d in live:                                   # ---- drain; fixed device order: deterministic fsol_sum
+            self.streams[d].synchronize()
+            mark(d, "stream_done")
+            with torch.cuda.device(self.plans[d].dev), torch.cuda.stream(self.streams[d]):
+                fs += bufs[d]["fa"]["fsol_sum"].cpu()
         out["fsol_sum"][:] = fs
+        self.last_trace = trace
         return {k: (v.numpy() if k == "fsol_sum" else v[:V].numpy()) for k, v in out.items()}
 
 

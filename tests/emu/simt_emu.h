@@ -62,6 +62,12 @@ inline cudaError_t cudaGetDevice(int* d) {
     *d = 0;
     return cudaSuccess;
 }
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount = 16 };
+inline cudaError_t cudaDeviceGetAttribute(int* v, cudaDeviceAttr, int) {
+    const char* ev = getenv("SIMT_EMU_SMS");
+    *v = ev ? atoi(ev) : 2;   // "SMs" of the emulated device: sizes the persistent grids
+    return cudaSuccess;
+}
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     const char* ev = getenv("SIMT_EMU_SMS");
     p->multiProcessorCount = ev ? atoi(ev) : 2;   // "SMs" of the emulated device: sizes the persistent grids
