@@ -76,7 +76,9 @@ typedef struct met2_fa_cfg {
                                         stores, motor...:134-155: 0 | 1.8 | k_est for X2 | lambda) */
 #define MET2_T2_FLAG_NO_NORMALISE 2  /* fit M as given instead of M / M[0] (per-voxel API of algorithms.py) */
 #define MET2_T2_FLAG_GCV_EVAL 8      /* GCV only: no search; solve at lambda_fixed and return the GCV objective
-                                        (algorithms.py:285-296) in reg[v] — for objective-level parity tests */
+                                        (algorithms.py:285-296) in reg[v] — for objective-level parity tests; bits
+                                        16-23 of status[v] then hold the rank the truncated pseudo-inverse kept
+                                        (the `rank` of the reference's np.linalg.lstsq) */
 #define MET2_T2_FLAG_GCV_GRID 32     /* GCV only (extension, BASELINE.json configs[2]): instead of Brent, evaluate the
                                         objective of algorithms.py:285-296 on `lambdas[0..nLambda)` and take the arg-min */
 #define MET2_T2_FLAG_FULL_START 16    /* X2: start the solves at Brent's first (voxel-independent) abscissae from the full

@@ -194,7 +194,8 @@ constexpr int GCV_LDC = GCV_RCAP + 1;     // odd row stride: conflict-free colum
 __host__ __device__ __forceinline__ int gcv_region_doubles(int n) { return n * GCV_LDC + GCV_RCAP * (GCV_RCAP | 1); }
 
 template <int NS>
-__device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N, double xs_scale, int k_sel, int lane) {
+__device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N, double xs_scale, int k_sel, int lane,
+                                               int& kept) {
     // matrix H: N x N row-major with stride LD at S[oA ..]; functional e at S[W.rs ..]; (c, s) of a round at S[W.gs ..]
     const int LD = N | 1;
     const int Ne = N + (N & 1);
@@ -296,19 +297,22 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N
     for (int o = 16; o > 0; o >>= 1) lmax = fmax(lmax, __shfl_xor_sync(FULL_MASK, lmax, o));
     const double tau = 2.220446049250313e-16 * (double)k_sel * lmax;
     double tr = 0.0;
+    int nk = 0;
     for (int i = lane; i < N; i += 32) {
         const double li = S[oA + i * LD + i];
         if (li > tau) {
             const double ei = S[W.rs + i];
             tr += 1.0 - xs_scale * (ei * ei) / (li * li);
+            ++nk;
         }
     }
+    kept = __reduce_add_sync(FULL_MASK, nk);     // eigenvalues above the cut-off = rank of the truncated pseudo-inverse
     return warp_sum(tr);
 }
 
 template <int NS>
 __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, int oLb, int n, int m, int lane,
-                                           double x, double sse, double nrm, int p) {
+                                           double x, double sse, double nrm, int p, int& kept) {
     // ---- sel = positions with a strictly positive coefficient (after an itmax stop some may be 0), compacted as
     //      column indices into S[W.gs ..] (ints); row i of Mk <-> lane i % 32, slot i / 32
     __syncwarp();
@@ -412,7 +416,8 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
         S[W.rs + lane] = g;
     }
     __syncwarp();
-    const double tr = (r > 0) ? jacobi_trace<NS>(W, oH, r, xs, k, lane) : 0.0;
+    kept = 0;
+    const double tr = (r > 0) ? jacobi_trace<NS>(W, oH, r, xs, k, lane, kept) : 0.0;
     const double dm = (double)m;
     const double num = (1.0 / dm) * (sse + x * nrm);
     const double den = (1.0 / dm) * (dm - tr);
@@ -678,7 +683,9 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     if (stage == ST_FINAL) {
                         if (method == MET2_REG_GCV && (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL)) {
                             const double nrm = reg_norm2<NS>(W, oLb, n, lane);
-                            regv = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p);
+                            int kept = 0;
+                            regv = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p, kept);
+                            st |= ((unsigned)kept & 0xffu) << 16;     // MET2_T2_FLAG_GCV_EVAL: kept rank in bits 16-23
                             (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                         } else
                         if (method == MET2_REG_X2 && !(A.cfg.flags & MET2_T2_FLAG_REG_IS_LAMBDA))
@@ -690,7 +697,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     if (method == MET2_REG_GCV) {
                         // algorithms.py:276-296
                         const double nrm = reg_norm2<NS>(W, oLb, n, lane);
-                        const double cost = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p);
+                        int kept = 0;
+                        const double cost = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p, kept);
                         if (A.cfg.flags & MET2_T2_FLAG_GCV_GRID) {
                             // np.argmin over the grid: first minimum, a NaN wins and stays
                             if (gi == 0 || (SSE == SSE && (cost < SSE || cost != cost))) {

@@ -128,11 +128,23 @@ def _solve(D, M, L, method, lambda_reg=None, lam_fixed=None, factor=1.02):
 
 
 def nnls(A, b):
-    """algorithms.py:55 — (x, rnorm).  A is [m, n] with m <= 64 (the per-echo dictionary); the stacked Tikhonov form is
-    reached through nnls_tik."""
+    """algorithms.py:55 — (x, rnorm) with rnorm = |A x - b|_2 like Lawson-Hanson's.  A is [m, n] with m <= 64 (a
+    per-echo dictionary), or the STACKED Tikhonov system the reference builds at algorithms.py:77,229,264,286 —
+    [D; sqrt(lambda) L] with a zero tail of b — recognised by its banded square bottom block and solved through the
+    Tikhonov path (D, b_top, L' = sqrt(lambda) L, lambda = 1)."""
     A = np.asarray_chkfinite(np.asarray(A, dtype=np.float64))
     b = np.asarray_chkfinite(np.asarray(b, dtype=np.float64))
-    x, _ = _solve(A, b, None, "NNLS")
+    m, n = A.shape
+    if m > 64:
+        top = m - n
+        Lp = A[top:] if top > 0 else None
+        off = np.abs(np.subtract.outer(np.arange(n), np.arange(n))) > 2
+        if Lp is None or top > 64 or np.any(b[top:] != 0.0) or np.any(Lp[off] != 0.0):
+            raise ValueError("nnls: A has %d rows; supported are m <= 64 or the stacked system [D; sqrt(lambda) L] with "
+                             "a banded L and a zero tail of b" % m)
+        x, _ = _solve(A[:top], b[:top], Lp, "T2SPARC", lam_fixed=1.0)
+    else:
+        x, _ = _solve(A, b, None, "NNLS")
     return x, float(np.sqrt(np.sum((np.dot(A, x) - b) ** 2)))
 
 

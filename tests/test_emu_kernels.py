@@ -342,11 +342,17 @@ def test_gcv_objective_and_grid_modes(setup):
     d = []
     for lam in (1e-3, 0.1, 3.8197):
         out = _run("shuffle", sig, fa, setup["Dic"], gr["L"], gr["T2s"], "GCV", flags=8, lambda_fixed=lam)
-        assert not out["status"].any()
+        assert not (out["status"] & 0xffff).any()
+        kept = (out["status"].astype(np.int64) >> 16) & 0xff      # rank of the truncated pseudo-inverse (met2.h)
         for i in range(len(sel)):
             M = sig[i] / sig[i, 0]
             with np.errstate(all="ignore"):
                 ref = O.obj_nnls_gcv(lam, Dv[i], gr["L"], np.concatenate((M, np.zeros(60))), 32, np.eye(32))
+                f, _ = O.nnls(np.concatenate((Dv[i], np.sqrt(lam) * gr["L"])), np.concatenate((M, np.zeros(60))))
+                s = f > 0
+                Dr, Lr = Dv[i][:, s], gr["L"][s, s]
+                rank = np.linalg.lstsq(Dr.T @ Dr + lam * (Lr.T @ Lr), Dr.T, rcond=None)[2]
+            assert kept[i] == rank, (lam, i, kept[i], rank)
             d.append(abs(out["reg"][i] - ref))
     d = np.array(d)
     assert np.median(d) < 1e-4 and (d < 1e-2).mean() > 0.9, (np.median(d), d.max())

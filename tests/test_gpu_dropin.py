@@ -13,7 +13,8 @@ from multicomponent_t2_toolbox_b200.flip_angle_algorithms.fa_estimation import (
 from multicomponent_t2_toolbox_b200.intravoxel_algorithms.algorithms import (nnls, nnls_gcv, nnls_lcurve_wrapper,
                                                                              nnls_tik, nnls_x2)
 from multicomponent_t2_toolbox_b200.intravoxel_algorithms.bayesian_interpolation import BayesReg_nnls
-from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data import fitting_slice_T2, motor_recon_met2
+from multicomponent_t2_toolbox_b200.motor.motor_recon_met2_real_data import (create_Laplacian_matrix, fitting_slice_T2,
+                                                                             motor_recon_met2)
 from multicomponent_t2_toolbox_b200.phantom import make_phantom
 
 pytestmark = pytest.mark.gpu
@@ -78,6 +79,35 @@ def test_per_voxel_api(golden_voxels, dics):
     assert idx == io and alpha == ao and abs(km - kmo) < 1e-6 * kmo and abs(sse - sseo) < 1e-6 * sseo
     with pytest.raises(ValueError):
         nnls(D, np.full(32, np.nan))           # asarray_chkfinite, like algorithms.py:56
+    # the stacked Tikhonov system the reference hands to nnls itself (algorithms.py:264): 92 x 60
+    L2 = create_Laplacian_matrix(60, 2)
+    A = np.concatenate((D, np.sqrt(0.05) * L2))
+    b = np.concatenate((M, np.zeros(60)))
+    xs, rs = nnls(A, b)
+    xo, ro = O.nnls(A, b)
+    assert np.array_equal(xs > 0, xo > 0) and np.allclose(xs, xo, rtol=1e-6, atol=1e-9) and abs(rs - ro) < 1e-8
+    with pytest.raises(ValueError):
+        nnls(np.concatenate((D, D, D)), np.concatenate((M, M, M)))      # 96 rows that are not [D; L]
+
+
+def test_plan_cache_distinguishes_regularisation_matrices(golden_voxels, dics):
+    """the cache key of the drop-in functions used to sample ~16 entries per array, which are equal
+    for I, L1 and L2 — a call with L1 after the same call with I silently reused I's tables.  Same dictionary and
+    method, three matrices in a row, each against the oracle; then again in another order."""
+    g = golden_voxels
+    D = np.ascontiguousarray(dics["d273"][:, :, int(g["nnls_D_index"])])
+    M = g["sig"][0] / g["sig"][0, 0]
+    mats = {"I": np.eye(60), "L1": create_Laplacian_matrix(60, 1), "L2": create_Laplacian_matrix(60, 2)}
+    ref = {k: O.nnls_x2(D, M, L, 1.02) for k, L in mats.items()}
+    assert abs(ref["I"][1] - ref["L1"][1]) > 1e-6 and abs(ref["L1"][1] - ref["L2"][1]) > 1e-6     # they DO differ
+    for order in (("I", "L1", "L2"), ("L2", "I", "L1")):
+        for k in order:
+            f, lam, kest = nnls_x2(D, M, mats[k], 1.02)
+            fo, lamo, ko = ref[k]
+            assert np.array_equal(f > 0, fo > 0), k
+            assert np.allclose(f, fo, rtol=1e-6, atol=1e-9) and abs(lam - lamo) < 1e-6 * lamo and abs(kest - ko) < 1e-6, k
+            ft = nnls_tik(D, M, mats[k], 0.02)
+            assert np.allclose(ft, O.nnls_tik(D, M, mats[k], 0.02), rtol=1e-6, atol=1e-9), k
 
 
 def test_motor_recon_met2_files(tmp_path):

@@ -276,31 +276,69 @@ def test_warm_start_equals_cold_start(phantom_sig):
         assert np.allclose(warm["reg"].cpu().numpy(), cold["reg"].cpu().numpy(), rtol=1e-6, atol=0), (method, rm)
 
 
+def _gcv_objective_and_rank(lam, D, M, L):
+    """obj_nnls_gcv of algorithms.py:285-296 (same arithmetic as the oracle's) plus the rank np.linalg.lstsq kept."""
+    m, n = D.shape
+    f, SSEr = O.nnls(np.concatenate((D, np.sqrt(lam) * L)), np.concatenate((M, np.zeros(n))))
+    sel = f > 0
+    Dr, Lr = D[:, sel], L[sel, sel]
+    X, _, rank, _ = np.linalg.lstsq(np.matmul(Dr.T, Dr) + lam * np.matmul(Lr.T, Lr), Dr.T, rcond=None)
+    cost = ((1.0 / m) * (SSEr ** 2.0)) / ((1.0 / m) * np.trace(np.eye(m) - np.matmul(Dr, X))) ** 2.0
+    return np.log(cost), int(rank)
+
+
 def test_gcv_objective_and_pipeline(phantom_sig):
-    """GCV (algorithms.py:276-296).  The reference's objective rests on a truncated pseudo-inverse whose keep/drop
-    decisions and 1/lambda_i terms sit at rounding level; the reference does not reproduce itself under a 1e-13
-    perturbation of the input (lambda moves by up to 45 %).  Parity criterion used here:
-      (i) objective level: at fixed lambdas the GCV objective agrees with the oracle's to ~1e-5 (median) — the size of
-          the reference's own numerical noise in that quantity — and the solves agree to 1e-6;
+    """GCV (algorithms.py:276-296).  SURVEY.md a-8 (i) asked for the objective at fixed lambda within 1e-8.  Measured
+    here instead of assumed: the objective is ill-conditioned — tr(Dr Mk^+ Dr^T) sums 1 - x s (1.u_i)^2 / mu_i over
+    eigenvalues down to the eps k mu_max cut-off, and those carry O(1) relative rounding error in ANY implementation.
+    The reference against ITSELF, with the dictionary perturbed by one ulp (relative 1.1e-16), moves by a median of
+    1e-6 .. 5e-6 and up to 4e-4 while keeping the same rank, and three mathematically identical ways of forming the
+    trace in NumPy differ by 1e-4 .. 1e-3 (profiles/r02_gcv_objective_sensitivity.txt).  Criterion:
+      (i) objective level: the rank our truncated pseudo-inverse keeps (status bits 16-23 under MET2_T2_FLAG_GCV_EVAL)
+          equals np.linalg.lstsq's on >= 95 % of the voxels, and on those our |d objective| is within 4x (median) /
+          10x (max) of the reference's own one-ulp sensitivity measured on the same voxels (floors 2e-5 / 2e-3);
       (ii) pipeline level: fraction of voxels with |dMWF| < 1e-4 is compared with the oracle's self-agreement under a
-          1e-13 perturbation (must be within 15 points of it)."""
+          1e-13 perturbation of the signal (must be within 15 points of it)."""
+    import json
+    import os
     sig = phantom_sig[:96]
     V = sig.shape[0]
+    rec = {}
     for rm in ("I", "L2"):
         plan = _plan(reg_method="GCV", reg_matrix=rm, FA_method="spline", npc=60)
         fa = plan.fa_fit(sig)
         idx = fa["fa_index"].cpu().numpy()
         Dic = plan.dict_hr.to_reference_layout()
+        rng = np.random.default_rng(1)
         for lam in (1e-5, 1e-3, 0.1, 3.8197):
             out = plan.t2_fit(sig, fa["fa_index"], flags=8, lambda_fixed=lam)
             og = out["reg"].cpu().numpy()
-            oref = np.zeros(V)
+            st = out["status"].cpu().numpy().astype(np.int64)
+            kept = (st >> 16) & 0xff
+            assert not (st & 0xffff).any()
+            oref, rank, self_d = np.zeros(V), np.zeros(V, dtype=int), np.zeros(V)
             for v in range(V):
                 D = np.ascontiguousarray(Dic[:, :, idx[v]])
                 M = sig[v] / sig[v, 0]
-                oref[v] = O.obj_nnls_gcv(lam, D, plan.Laplac, np.concatenate((M, np.zeros(60))), 32, np.eye(32))
+                oref[v], rank[v] = _gcv_objective_and_rank(lam, D, M, plan.Laplac)
+                pert, _ = _gcv_objective_and_rank(lam, D * (1.0 + 1.1e-16 * rng.standard_normal(D.shape)), M, plan.Laplac)
+                self_d[v] = abs(pert - oref[v])
+            same = kept == rank
             d = np.abs(og - oref)
-            assert np.median(d) < 1e-4 and (d < 1e-2).mean() > 0.97, (rm, lam, np.median(d), d.max())
+            r = dict(same_rank_fraction=float(same.mean()), ours_median=float(np.median(d[same])), ours_max=float(d[same].max()),
+                     reference_one_ulp_median=float(np.median(self_d)), reference_one_ulp_max=float(self_d.max()),
+                     ours_max_all=float(d.max()))
+            rec["%s_lam_%g" % (rm, lam)] = r
+            assert r["same_rank_fraction"] >= 0.95, (rm, lam, r)
+            # floor 2e-5 / 2e-3: three mathematically identical NumPy evaluations of tr(A) (lstsq, the eigen-formula,
+            # sum |Dr u_i|^2 / mu_i) differ by 1e-4 .. 1e-3 in the trace, i.e. 1e-5 .. 1e-4 in the objective
+            # (tests/test_oracle_restatements.py::test_gcv_trace_is_ill_conditioned)
+            assert r["ours_median"] <= max(4.0 * r["reference_one_ulp_median"], 2e-5), (rm, lam, r)
+            assert r["ours_max"] <= max(10.0 * r["reference_one_ulp_max"], 2e-3) and r["ours_max_all"] < 1e-2, (rm, lam, r)
+        outdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(outdir, exist_ok=True)
+        with open(os.path.join(outdir, "parity_gcv_objective.json"), "w") as fh:
+            json.dump(rec, fh, indent=1)
         t2 = plan.t2_fit(sig, fa["fa_index"])
         ok = np.ones(V)
         f_ref, _, reg_ref = O.fitting_slice_T2(ok, sig, idx.astype(float), V, Dic, plan.lambda_reg, 60, 32, "GCV", plan.Laplac)

@@ -80,3 +80,34 @@ def test_voxel_metrics_empty_spectrum():
     m, t, c = T2s <= 40, (T2s > 40) & (T2s <= 200), T2s >= 200
     r = O.voxel_metrics(np.zeros(60), T2s, m, t, c)
     assert r[:3] == (0.0, 0.0, 0.0) and r[3] == 1.0 and r[4] == 1.0 and r[5] == 1e-16
+
+
+def test_gcv_trace_is_ill_conditioned(golden_config2):
+    """Why GCV parity is statistical (SURVEY.md a-8, tests/test_gpu_parity.py::test_gcv_objective_and_pipeline): the
+    trace tr(Dr Mk^+ Dr^T) of algorithms.py:291-295 is ill-conditioned.  Three mathematically identical evaluations in
+    double precision — the reference's lstsq, sum_kept (1 - x s (1.u_i)^2 / mu_i), and sum_kept |Dr u_i|^2 / mu_i from
+    the symmetric eigen-decomposition with the same eps k mu_max cut-off — disagree by 1e-5 .. 1e-2 on ordinary voxels,
+    so the objective log(SSE^2 m / (m - tr)^2) is only defined to ~1e-5; a 1e-8 contract cannot be met by anyone."""
+    g = golden_config2
+    gr = O._grids("GCV", "L2", "spline", 40.0, 32, 10.0, 1000.0)
+    L = gr["L"]
+    sel = np.arange(5, 20480, 512)[:40]
+    for lam in (0.1, 3.8197):
+        d_formula, d_direct = [], []
+        for i in sel:
+            D = O.create_met2_design_matrix_epg(60, gr["T2s"], gr["T1s"], 32, 10.0, gr["alpha_values"][int(g["fa_idx"][i])],
+                                                1000.0)
+            M = g["sig"][i] / g["sig"][i, 0]
+            f, _ = O.nnls(np.concatenate((D, np.sqrt(lam) * L)), np.concatenate((M, np.zeros(60))))
+            s = f > 0
+            Dr, Lr, k = D[:, s], L[s, s], int(s.sum())
+            xs = lam * float(Lr @ Lr)
+            Mk = Dr.T @ Dr + xs
+            X = np.linalg.lstsq(Mk, Dr.T, rcond=None)[0]
+            tr_ref = np.trace(Dr @ X)
+            mu, U = np.linalg.eigh(Mk)
+            keep = mu > np.finfo(float).eps * k * mu.max()
+            e = U.sum(0)
+            d_formula.append(abs(tr_ref - np.sum(1.0 - xs * e[keep] ** 2 / mu[keep])))
+            d_direct.append(abs(tr_ref - np.sum(((Dr @ U)[:, keep] ** 2).sum(0) / mu[keep])))
+        assert 1e-6 < np.median(d_formula) < 1e-2 and 1e-6 < np.median(d_direct) < 1e-1, (lam, np.median(d_formula))
