@@ -124,10 +124,10 @@ __device__ __forceinline__ int select_corner_warp(int oLx, int oLy, int nl, int 
 // quantities, formed the same way, as the reference's.  (Round 1 used the inverse factor: U f = T^T (A f).  Together
 // with the ~1e-9 relative error of the Gram-domain NNLS solution that put 25 % of the config-4 voxels more than 1e-6
 // away from the reference's lambda, where the reference's own reproducibility under a 1e-13 perturbation is 5 %.)
-template <int NS>
-__device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg, int oKb, int n, int m, int lane,
-                                             double x, double beta, double sse, double nrm, double log_det_L,
-                                             unsigned& st, const double* __restrict__ utab) {
+template <int NS, bool GSH>
+__device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oKb,
+                                             int n, int m, int lane, double x, double beta, double sse, double nrm,
+                                             double log_det_L, unsigned& st, const double* __restrict__ utab) {
     const int oT = W.T;
     const double bx = beta * x;
     // While Brent is still on its voxel-independent golden chain (the first T2_NTAB_BAYES abscissae, bracket wider than
@@ -143,7 +143,7 @@ __device__ __forceinline__ double bayes_cost(const Slots<NS>& W, int oG, int ldg
         __syncwarp();
     } else {
         auto Aent = [&](int r, int c) -> double {
-            double a = beta * S[oG + r * ldg + c];
+            double a = beta * (GSH ? S[oG + r * ldg + c] : __ldg(Gg + r * ldg + c));
             const int d = r - c + 2;   // K[r][c] = kband[d][c]
             if (d >= 0 && d <= 4) a = a + bx * S[oKb + d * n + c];
             return a;
@@ -310,8 +310,9 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N
     return warp_sum(tr);
 }
 
-template <int NS>
-__device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, int oLb, int n, int m, int lane,
+template <int NS, bool GSH>
+__device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, const double* __restrict__ Gg, int ldg, int oLb,
+                                           int n, int m, int lane,
                                            double x, double sse, double nrm, int p, int& kept) {
     // ---- sel = positions with a strictly positive coefficient (after an itmax stop some may be 0), compacted as
     //      column indices into S[W.gs ..] (ints); row i of Mk <-> lane i % 32, slot i / 32
@@ -344,7 +345,7 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
         const int i = lane + 32 * t;
         col[t] = (i < k) ? SI(W.gs, i) : 0;
         if (i < k) {
-            const double d = S[oG + col[t] * ldg + col[t]] + xs;
+            const double d = (GSH ? S[oG + col[t] * ldg + col[t]] : __ldg(Gg + col[t] * ldg + col[t])) + xs;
             S[W.rs + i] = d;
             dmax = fmax(dmax, d);
         } else {
@@ -385,7 +386,7 @@ __device__ __forceinline__ double gcv_cost(const Slots<NS>& W, int oG, int ldg, 
                     cv = dp * rinv;
                     done |= 1u << t;
                 } else if (!((done >> t) & 1u)) {
-                    double v = S[oG + cp * ldg + col[t]] + xs;
+                    double v = (GSH ? S[oG + cp * ldg + col[t]] : __ldg(Gg + cp * ldg + col[t])) + xs;
                     for (int l = 0; l < r; ++l) v = fma(-S[oC + i * GCV_LDC + l], S[oC + piv * GCV_LDC + l], v);
                     cv = v * rinv;
                     S[W.rs + i] = fma(-cv, cv, S[W.rs + i]);
@@ -467,8 +468,13 @@ __global__ void __launch_bounds__(32) t2_full_factors_kernel(const double* __res
 // shared-memory layout in doubles: [G n*n][K band 5n][L band 5n][logT2 n][lambdas 64][comp n bytes -> (n+7)/8]
 // then per warp: [NNLS slots][signal 64][L-curve curves 2 x 64 | Brent-best snapshot 48 NS]
 __host__ __device__ __forceinline__ int t2_ldg(int n) { return (n + 1) & ~1; }   // even row stride: 16-byte aligned rows
-__host__ __device__ __forceinline__ int t2_table_doubles(int n) {
-    return (n * t2_ldg(n) + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
+// The Gram matrix of the tile's flip angle is staged in shared memory for nT2 <= 64 only.  For the wide grids (96 bins:
+// 74 KB, 100 bins: 80 KB) it stays in global memory (read-only path, L1/L2-resident: every warp of the CTA works on the
+// same flip angle): the per-voxel factor is 37-40 KB there and the staged copy cost half of the resident warps — config 4
+// (BayesReg-InvT2, 100 bins) ran at TWO warps per SM (profiles/r02_config4_ncu_summary.txt).
+__host__ __device__ constexpr __forceinline__ bool t2_gram_in_shared(int ns) { return ns <= 2; }
+__host__ __device__ __forceinline__ int t2_table_doubles(int n, bool gsh) {
+    return ((gsh ? n * t2_ldg(n) : 0) + 10 * n + n + MET2_MAX_LAMBDAS + (n + 7) / 8 + 31) & ~31;
 }
 
 template <int NS>
@@ -488,14 +494,15 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
     constexpr int method = METHOD;
     // position slots of the solver: a plain solve has at most min(nT2, nTE) <= 32 ME positive columns
     constexpr int PS = (METHOD == MET2_REG_NNLS && ME < NS) ? ME : NS;
+    constexpr bool GSH = t2_gram_in_shared(NS);
     const int oG = 0;
-    const int ldg = t2_ldg(n);
-    const int oKb = oG + n * ldg;        // K band rows 0..4
+    const int ldg = GSH ? t2_ldg(n) : n;         // row stride of G where the solver reads it
+    const int oKb = GSH ? oG + n * ldg : 0;      // K band rows 0..4
     const int oLb = oKb + 5 * n;         // L band rows 0..4
     const int oLogT2 = oLb + 5 * n;
     const int oLam = oLogT2 + n;
     unsigned char* scomp = reinterpret_cast<unsigned char*>(S + oLam + MET2_MAX_LAMBDAS);
-    const int wbase = t2_table_doubles(n) + warp * t2_warp_doubles<NS>(A.pmax);
+    const int wbase = t2_table_doubles(n, GSH) + warp * t2_warp_doubles<NS>(A.pmax);
     Slots<NS> W;
     W.carve(wbase, A.pmax);
     const int oM = wbase + Slots<NS>::doubles(A.pmax);
@@ -521,8 +528,8 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
         if (tile >= ntiles) break;
         const int fa = A.tile_fa[tile];
         const int tstart = A.tile_start[tile], tcnt = A.tile_cnt[tile];
-        {
-            const double* Gg = A.G + (size_t)fa * n * n;
+        const double* Gg = A.G + (size_t)fa * n * n;
+        if (GSH) {
             for (int i = threadIdx.x; i < n * n; i += blockDim.x) {
                 const int r = i / n;
                 S[oG + r * ldg + (i - r * n)] = __ldg(Gg + i);
@@ -603,7 +610,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                     for (int tt = 0; tt < NS; ++tt) {
                         const int j = lane + 32 * tt;
                         if (j < n) {
-                            const double djj = fma(lam0, S[oKb + 2 * n + j], S[oG + j * ldg + j]);
+                            const double djj = fma(lam0, S[oKb + 2 * n + j], GSH ? S[oG + j * ldg + j] : __ldg(Gg + j * ldg + j));
                             SI(W.ix, j) = j;
                             S[W.xs + j] = fmax(S[W.cc + j] / djj, 1e-300);
                         }
@@ -672,7 +679,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                 };
                 while (true) {
                     // every solve after the first starts from the previous solution (support + coefficients)
-                    p = nnls_gram<NS, true, PS>(W, oG, nullptr, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
+                    p = nnls_gram<NS, GSH, PS>(W, oG, Gg, ldg, oKb, reg, lam, n, reg ? m + n : m, lane, nst,
                                             warm ? p : 0, t_ready);
                     t_ready = false;
                     if (method == MET2_REG_NNLS && nst == 0 && p > 0)
@@ -684,7 +691,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                         if (method == MET2_REG_GCV && (A.cfg.flags & MET2_T2_FLAG_GCV_EVAL)) {
                             const double nrm = reg_norm2<NS>(W, oLb, n, lane);
                             int kept = 0;
-                            regv = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p, kept);
+                            regv = gcv_cost<NS, GSH>(W, oG, Gg, ldg, oLb, n, m, lane, lam, sse, nrm, p, kept);
                             st |= ((unsigned)kept & 0xffu) << 16;     // MET2_T2_FLAG_GCV_EVAL: kept rank in bits 16-23
                             (void)fit_and_sse<NS, ME>(W, Dt, oM, m, p, lane, fit);
                         } else
@@ -698,7 +705,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                         // algorithms.py:276-296
                         const double nrm = reg_norm2<NS>(W, oLb, n, lane);
                         int kept = 0;
-                        const double cost = gcv_cost<NS>(W, oG, ldg, oLb, n, m, lane, lam, sse, nrm, p, kept);
+                        const double cost = gcv_cost<NS, GSH>(W, oG, Gg, ldg, oLb, n, m, lane, lam, sse, nrm, p, kept);
                         if (A.cfg.flags & MET2_T2_FLAG_GCV_GRID) {
                             // np.argmin over the grid: first minimum, a NaN wins and stays
                             if (gi == 0 || (SSE == SSE && (cost < SSE || cost != cost))) {
@@ -750,7 +757,7 @@ __global__ void __launch_bounds__(T2_MAX_THREADS, 1) t2_fit_kernel(T2Args A) {
                                     if (lam == __ldg(A.lam_tab + q)) ttab = A.tfull + ((size_t)q * A.cfg.nA + fa) * tri(n);
                                 if (ttab && !(__ldg(ttab) == __ldg(ttab))) ttab = nullptr;   // not positive definite
                             }
-                            const double cost = bayes_cost<NS>(W, oG, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
+                            const double cost = bayes_cost<NS, GSH>(W, oG, Gg, ldg, oKb, n, m, lane, lam, beta, sse, nrm,
                                                                A.cfg.log_det_L, st, ttab);
                             const double lam_eval = lam;
                             const bool more = B.feed(cost, lam);
@@ -882,7 +889,7 @@ static inline T2Geom t2_geometry(long long V, const met2_t2_cfg* cfg) {
     g.pmax = plain ? (n < m ? n : m) : n;
     if (cfg->method == MET2_REG_GCV)   // the T region also hosts the GCV workspace (C: n x 21, H: 20 x 21)
         while (tri(g.pmax) < gcv_region_doubles(n)) ++g.pmax;
-    size_t tables = sizeof(double) * (size_t)t2_table_doubles(n);
+    size_t tables = sizeof(double) * (size_t)t2_table_doubles(n, t2_gram_in_shared(NS));
     size_t per_warp = sizeof(double) * (size_t)t2_warp_doubles<NS>(g.pmax);
     size_t budget = 227 * 1024 - 1024;
     int warps = (int)((budget - tables) / per_warp);
