@@ -204,6 +204,17 @@ def test_fa_stage_kernels_against_reference(setup):
     for other in outs[1:]:
         assert all(np.array_equal(out[k], other[k]) for k in ("fa_index", "fa_deg", "km", "status"))
         assert np.allclose(out["fsol_sum"], other["fsol_sum"], rtol=1e-13, atol=0)   # summation order follows the warps
+    # the search has two kernels: thread per voxel (default) and warp per voxel, which also redoes the voxels the first one
+    # hands back (positive set above its cap: forced here with a cap of 3 columns).  Same indices on every path.
+    for env in ({"MET2_FA_SEARCH": "warp"}, {"MET2_FA_THREAD_PCAP": "3"}):
+        os.environ.update(env)
+        try:
+            alt = emu.fa_fit(sig, setup["Dic"], gr["alpha_values"], DicLR, gr["alpha_spline"])
+        finally:
+            for k in env:
+                del os.environ[k]
+        assert all(np.array_equal(out[k], alt[k]) for k in ("fa_index", "fa_deg", "status")), env
+        assert np.max(np.abs(out["km"] - alt["km"]) / out["km"]) < 1e-12
     a91 = np.linspace(90.0, 180.0, 91)
     D91 = O.create_Dic_3D(60, gr["T2s"], gr["T1s"], 32, 10.0, a91, 1000.0)
     sig_b = sig[:5].copy()
@@ -214,6 +225,12 @@ def test_fa_stage_kernels_against_reference(setup):
     assert np.array_equal(out["fa_index"], idx.astype(np.int32)) and np.array_equal(out["fa_deg"], FA)
     assert np.max(np.abs(out["km"] - KM)) < 1e-8 * KM.max()
     assert np.max(np.abs(out["fsol_sum"] - F)) < 1e-6 * np.abs(F).max()
+    os.environ["MET2_FA_THREAD_PCAP"] = "3"
+    try:
+        alt = emu.fa_fit(sig_b, D91, a91)
+    finally:
+        del os.environ["MET2_FA_THREAD_PCAP"]
+    assert all(np.array_equal(out[k], alt[k]) for k in ("fa_index", "fa_deg", "status"))
 
 
 def _synthetic(npc, nte, nv, method, matrix, seed=3):

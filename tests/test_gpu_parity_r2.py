@@ -222,3 +222,33 @@ def test_echo_basis_reproduces_the_dictionary():
         eye[:, ii, ii] = nz
         assert np.abs(UtU - eye).max() < 1e-14
         assert np.abs(np.einsum("ake,aje->akj", U, C) - D).max() <= 2e-15 * np.abs(D).max()
+
+
+def test_fa_search_thread_kernel_equals_warp_kernel():
+    """The flip-angle search has two kernels (csrc/met2_fa.cu): thread per voxel (default) and warp per voxel, which also
+    redoes the voxels the first one hands back.  fa_estimation.py:35-112 — the chosen index must be the same whichever
+    path a voxel takes: the whole config-2 phantom (552 960 voxels, spline) and a 91-angle brute-force slab, each through
+    the default path, the warp kernel alone and a forced hand-back of most voxels (cap of 3 columns).  Fixtures of the
+    unmodified reference cover the default path elsewhere (test_config2_subset_vs_reference, ...)."""
+    from multicomponent_t2_toolbox_b200.phantom import make_phantom
+    ph = make_phantom((96, 96, 60), seed=2, fa_mode="b1", backend="gpu")
+    sig = torch.as_tensor(ph["data"].reshape(-1, 32)).cuda()
+    rec = {}
+    for fam, sl in (("spline", slice(None)), ("brute-force", slice(0, 96 * 96 * 4))):
+        plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="X2", reg_matrix="I", FA_method=fam)
+        x = sig[sl].contiguous()
+        base = plan.fa_fit(x)
+        assert int((base["status"] != 0).sum()) == 0
+        for env in ({"MET2_FA_SEARCH": "warp"}, {"MET2_FA_THREAD_PCAP": "3"}):
+            os.environ.update(env)
+            try:
+                alt = plan.fa_fit(x)
+            finally:
+                for k in env:
+                    del os.environ[k]
+            mism = int((alt["fa_index"] != base["fa_index"]).sum())
+            rec["%s_%s" % (fam, "_".join("%s=%s" % kv for kv in env.items()))] = dict(voxels=int(x.shape[0]), index_mismatches=mism)
+            assert mism == 0, (fam, env, mism)
+            assert torch.equal(alt["status"], base["status"])
+            assert float(((alt["km"] - base["km"]).abs() / base["km"].clamp_min(1e-300)).max()) < 1e-12
+    _record("parity_r2_fa_search_paths.json", rec)
