@@ -351,7 +351,8 @@ def run_ours(args):
                     "from": (NCU_RECORD + ":" + key) if r else None}
         r_t2 = kernel_roofline(t2_kernel, t2_ms, F["F_alg_t2_x2_I"], F.get("F_alg_t2_x2_I_sd"), HBM_BYTES_PER_VOXEL_T2,
                                "t2_echo_x2" if echo else "t2_fit_x2")
-        r_fa = kernel_roofline("fa_search_kernel<2,1> + fa_select_kernel<2,1>", fa_ms, F["F_alg_fa_spline"],
+        r_fa = kernel_roofline("fa_search_thread_kernel<32> + fa_search_kernel<2,1> (hand-backs) + fa_select_kernel<2,1>", fa_ms,
+                               F["F_alg_fa_spline"],
                                F.get("F_alg_fa_spline_sd"), HBM_BYTES_PER_VOXEL_FA, "fa_spline")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": n_warm, "warmup_requested": args.warmup, "ms_per_step": ms_per_step,
