@@ -38,7 +38,11 @@ extern "C" {
 #define MET2_MAX_NTE 64  /* echoes (reference data: 32; config 4 uses 48) */
 #define MET2_MAX_KNOTS 32
 #define MET2_MAX_LAMBDAS 64
-#define MET2_ECHO_RANK 24 /* rows of the reduced echo space (met2_echo_basis, met2_t2_fit_echo) */
+#define MET2_ECHO_RANK 24       /* rows of the reduced echo space (met2_echo_basis, met2_t2_fit_echo): exact to the rounding
+                                   of the dictionary's own entries for every protocol met so far */
+#define MET2_ECHO_RANK_SMALL 16 /* the smaller rank the echo-space kernels are also built for: valid when the residual of
+                                   the rank-16 reduction (`tail` of met2_echo_basis) is below 4e-12, as for the
+                                   reference's 32-echo protocol (1.6e-12); 19 % faster (met2_t2_cfg.echo_rank) */
 
 /* per-voxel status bits */
 #define MET2_ST_SKIPPED 1u      /* sum(M) <= 0 or M[0] <= 0: voxel not fitted (fa_estimation.py:100, motor...:124,131) */
@@ -104,7 +108,8 @@ typedef struct met2_t2_cfg {
     double brent_lo, brent_hi, brent_xatol; /* X2 [0,10]; GCV [1e-8,10]; BayesReg [1e-8,2]; xtol 1e-5 */
     double log_det_L;    /* BayesReg: log(det(L)) (bayesian_interpolation.py:100,123); -inf for L2 */
     int32_t flags;       /* MET2_T2_FLAG_* */
-    int32_t reserved;
+    int32_t echo_rank;   /* MET2_T2_FLAG_ECHO_SPACE: the R the tables of met2_echo_basis were built with — MET2_ECHO_RANK
+                            (also 0) or MET2_ECHO_RANK_SMALL; ignored otherwise */
 } met2_t2_cfg;
 
 /* Replaces epg/epg.py:155 create_Dic_3D (-> :47 create_met2_design_matrix_epg -> :64 epg_signal).
@@ -197,6 +202,9 @@ int met2_nesma_filter(const double* vol, const int32_t* mask, int nx, int ny, in
 /* Diagnostics */
 const char* met2_last_error(void);
 int met2_version(void);
+/* MET2_ECHO_RANK (small = 0) or MET2_ECHO_RANK_SMALL (small != 0) of this library: the values of R that
+ * met2_echo_basis / met2_t2_cfg.echo_rank accept for met2_t2_fit_echo. */
+int met2_echo_rank(int small);
 /* number of kernel launches enqueued by this library in this process so far (for bench.py's gpu_launches) */
 int64_t met2_launch_count(void);
 

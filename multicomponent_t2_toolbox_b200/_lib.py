@@ -22,7 +22,7 @@ class T2Cfg(ctypes.Structure):
                 ("nLambda", ctypes.c_int32), ("maxfun", ctypes.c_int32),
                 ("factor", ctypes.c_double), ("lambda_fixed", ctypes.c_double),
                 ("brent_lo", ctypes.c_double), ("brent_hi", ctypes.c_double), ("brent_xatol", ctypes.c_double),
-                ("log_det_L", ctypes.c_double), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("log_det_L", ctypes.c_double), ("flags", ctypes.c_int32), ("echo_rank", ctypes.c_int32)]
 
 
 # every symbol include/met2.h declares, with its ctypes signature
@@ -50,6 +50,7 @@ SIGNATURES = {
                                          ctypes.c_int, ctypes.c_double, c_void_p, c_void_p, c_void_p]),
     "met2_last_error": (ctypes.c_char_p, []),
     "met2_version": (ctypes.c_int, []),
+    "met2_echo_rank": (ctypes.c_int, [ctypes.c_int]),
     "met2_launch_count": (ctypes.c_int64, []),
 }
 

@@ -10,6 +10,7 @@ PyTorch is used only for device buffers and streams.  There is no CPU path: cons
 """
 import ctypes
 import math
+import os
 
 import numpy as np
 import torch
@@ -21,8 +22,14 @@ REG_METHOD_CODE = {"NNLS": 0, "T2SPARC": 1, "X2": 2, "L_curve": 3, "GCV": 4, "Ba
 
 ST_SKIPPED, ST_NONFINITE, ST_ITMAX, ST_SSE_ZERO, ST_NOT_PD = 1, 2, 4, 8, 16
 REG_IS_LAMBDA, NO_NORMALISE, COLD_START, GCV_EVAL, FULL_START, GCV_GRID, ECHO_SPACE = 1, 2, 4, 8, 16, 32, 64   # MET2_T2_FLAG_*
-ECHO_RANK = 24          # MET2_ECHO_RANK
-ECHO_TAIL_MAX = 1e-15   # largest sigma_{R+1} / sigma_1 for which the reduced echo space is taken as exact
+# Largest residual of the reduction (max_j |d_j - U C_j| / max_j |d_j| over the flip angles, measured by
+# met2_echo_basis) for which a rank of the reduced echo space is used.  24 (MET2_ECHO_RANK): the rounding of the
+# dictionary's own entries (8e-16 .. 1e-15 measured).  16 (MET2_ECHO_RANK_SMALL): 4e-12 — the reference's 32-echo
+# protocol measures 1.6e-12 (60 bins) / 1.9e-12 (96 bins) and reproduces the unmodified reference on 20 480 voxels with 0
+# active-set disagreements and spectra within 7.8e-9, the accuracy class of the Gram-domain kernels (1.7e-9), 19 % less
+# time per volume (profiles/r02_ab_echo_rank.json); the 48-echo protocol of config 4 measures 2.2e-11 and stays at rank
+# 24; a dictionary that misses that bound too runs the Gram-domain kernels.
+ECHO_TAIL_MAX = {24: 1e-15, 16: 4e-12}
 
 
 def _require_cuda(device):
@@ -177,22 +184,36 @@ class Dictionary:
                                             _stream()), "met2_gram_tables")
         return self
 
-    def echo_basis(self):
-        """Reduced echo basis of this dictionary (met2_echo_basis, built on first use): (basis [nA, nTE, R],
-        coef [nA, nT2, R]) or None when the dictionary is not numerically of rank <= R (then the echo-space kernels are
-        not used and the Gram-domain kernels run)."""
-        if not hasattr(self, "_echo"):
+    def echo_tables(self, R):
+        """met2_echo_basis at rank R (built on first use, kept): (basis [nA, nTE, R], coef [nA, nT2, R], tail) with
+        tail = the largest residual of the reduction over the flip angles, max_j |d_j - U C_j| / max_j |d_j|."""
+        cache = self.__dict__.setdefault("_echo_tables", {})
+        if R not in cache:
             lib = _lib.load()
             dev = self.dic.device
-            basis = torch.empty((self.nA, self.nTE, ECHO_RANK), dtype=torch.float64, device=dev)
-            coef = torch.empty((self.nA, self.nT2, ECHO_RANK), dtype=torch.float64, device=dev)
+            basis = torch.empty((self.nA, self.nTE, R), dtype=torch.float64, device=dev)
+            coef = torch.empty((self.nA, self.nT2, R), dtype=torch.float64, device=dev)
             tail = torch.empty(self.nA, dtype=torch.float64, device=dev)
             with torch.cuda.device(dev):
-                _lib.check(lib.met2_echo_basis(_ptr(self.dic), self.nA, self.nTE, self.nT2, ECHO_RANK, _ptr(basis),
+                _lib.check(lib.met2_echo_basis(_ptr(self.dic), self.nA, self.nTE, self.nT2, R, _ptr(basis),
                                                _ptr(coef), _ptr(tail), _stream()), "met2_echo_basis")
-            self.echo_tail = float(tail.max())
-            self._echo = (basis, coef) if self.echo_tail <= ECHO_TAIL_MAX else None
-        return self._echo
+            cache[R] = (basis, coef, float(tail.max()))
+        return cache[R]
+
+    def echo_basis(self, ranks=None):
+        """Reduced echo basis the echo-space kernels run on: (basis, coef, R) for the smallest rank R among `ranks`
+        (default: both ranks the library is built for, 16 and 24; MET2_ECHO_RANKS=24 restricts them for A/B runs) whose
+        measured residual is within ECHO_TAIL_MAX[R], or None when none is (then the Gram-domain kernels run)."""
+        if ranks is None:
+            lib = _lib.load()
+            ranks = (int(lib.met2_echo_rank(1)), int(lib.met2_echo_rank(0)))
+            if os.environ.get("MET2_ECHO_RANKS"):
+                ranks = [r for r in ranks if str(r) in os.environ["MET2_ECHO_RANKS"].split(",")]
+        for R in sorted(ranks):
+            basis, coef, tail = self.echo_tables(R)
+            if tail <= ECHO_TAIL_MAX[R]:
+                return basis, coef, R
+        return None
 
     def to_reference_layout(self):
         """Host copy in the reference's layout Dic_3D[nTE, nT2, nA] (epg/epg.py:155-162)."""
@@ -202,7 +223,8 @@ class Dictionary:
 class Met2Plan:
     def __init__(self, n_echoes, tau, TR, reg_method="X2", reg_matrix="I", FA_method="spline", myelin_T2=40.0,
                  npc=None, n_alphas=None, T1=1000.0, device=None, lambda_reg=None, Laplac=None, Dic_3D=None,
-                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None, t2_flags=0, echo_space=True):
+                 Dic_3D_LR=None, alpha_values=None, alpha_values_spline=None, T2s=None, t2_flags=0, echo_space=True,
+                 echo_ranks=None):
         """Tables for one reconstruction set-up.  By default everything is built like motor...:204-277 (EPG dictionary
         on the GPU); `Dic_3D` (+ `Dic_3D_LR`, `alpha_values`, `alpha_values_spline`, `T2s`, `Laplac`) lets a caller bring
         its own dictionary in the reference layout [nTE, nT2, nA] — used by the drop-in row workers and per-voxel API."""
@@ -217,6 +239,9 @@ class Met2Plan:
         # reduced-echo-space kernels wherever they apply (X2 and T2SPARC with a diagonal matrix: I, InvT2), where they
         # measured 1.4-3x faster than the Gram-domain ones (profiles/r02_ab_*); echo_space=False keeps the latter
         self.echo_space = bool(echo_space)
+        # ranks of the reduced space this plan may use (None: the smallest of 16 / 24 the dictionary is exact at, see
+        # ECHO_TAIL_MAX; (24,) pins the rank that is exact to the rounding of the dictionary's entries)
+        self.echo_ranks = None if echo_ranks is None else tuple(int(r) for r in echo_ranks)
         self.nTE, self.tau, self.TR = int(n_echoes), float(tau), float(TR)
         if Dic_3D is not None:
             Dic_3D = np.asarray(Dic_3D, dtype=np.float64)
@@ -282,7 +307,7 @@ class Met2Plan:
         method = self.reg_method if reg_method is None else reg_method
         cfg = _lib.T2Cfg(method=REG_METHOD_CODE[method], nTE=self.nTE, nT2=self.npc, nA=len(self.alpha_values),
                          nLambda=len(self.lambda_reg), maxfun=300, factor=1.02, lambda_fixed=1.8, brent_lo=0.0,
-                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=int(flags) | self.t2_flags, reserved=0)
+                         brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=int(flags) | self.t2_flags, echo_rank=0)
         if method == "GCV":
             cfg.brent_lo = 1e-8
         if method == "BayesReg":
@@ -382,9 +407,11 @@ class Met2Plan:
         if cfg.flags & ECHO_SPACE:
             if not self._diagonal_L():
                 raise ValueError("MET2_T2_FLAG_ECHO_SPACE needs a diagonal regularisation matrix (I, InvT2)")
-            red = hr.echo_basis()
+            red = hr.echo_basis(self.echo_ranks)
             if red is None:      # dictionary not of numerical rank <= 24: Gram-domain kernels
                 cfg.flags &= ~ECHO_SPACE
+            else:
+                cfg.echo_rank = red[2]
         with torch.cuda.device(dev):
             nbytes = self.lib.met2_t2_workspace_bytes(V, ctypes.byref(cfg))
             if nbytes < 0:

@@ -47,4 +47,5 @@ int sm_count() {
 
 extern "C" const char* met2_last_error(void) { return met2::g_err; }
 extern "C" int met2_version(void) { return MET2_VERSION; }
+extern "C" int met2_echo_rank(int small) { return small ? MET2_ECHO_RANK_SMALL : MET2_ECHO_RANK; }
 extern "C" int64_t met2_launch_count(void) { return (int64_t)met2::g_launches.load(); }

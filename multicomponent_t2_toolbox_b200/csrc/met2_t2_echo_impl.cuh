@@ -1,4 +1,4 @@
-// met2_t2_echo.cu — Tikhonov NNLS in REDUCED ECHO SPACE for a diagonal regularisation matrix (reg_matrix I and InvT2):
+// met2_t2_echo_impl.cuh — Tikhonov NNLS in REDUCED ECHO SPACE for a diagonal regularisation matrix (reg_matrix I and InvT2):
 // the X2 search (algorithms.py:211-233) and the fixed-lambda solve of T2SPARC (algorithms.py:262-269, motor...:138).
 // Selected with MET2_T2_FLAG_ECHO_SPACE; batched.Met2Plan sets the flag whenever the configuration is eligible.
 //
@@ -32,11 +32,23 @@
 //                    (s = +1: h >= 1, no cancellation; s = -1: h_k >= 1 - u.u > 0, rebuilt from M_P if that fails).
 // The plain NNLS of X2 (lam = 0: the SSE of algorithms.py:213-214) stays in the Gram domain (nnls_gram), with its
 // right-hand side, residual and D-space candidate test taken in the same reduced space.
+//
+// Compiled once per rank of the reduced space (met2_t2_echo_r16.cu, met2_t2_echo_r24.cu define MET2_ECHO_RD, a namespace
+// and the name of the launcher): RD = 16 whenever the rank-16 reduction leaves a residual below 4e-12 (the reference's
+// 32-echo protocol: 1.6e-12, sigma_17 / sigma_1 = 6e-13; measured on 20 480 voxels fitted by the unmodified reference: 0
+// active-set disagreements, spectra within 7.8e-9 — the accuracy class of the Gram-domain kernels — and 19 % less time
+// than RD = 24: two DMMA blocks per refactorisation instead of three, 16-step triangular products), RD = 24 otherwise
+// (exact to the rounding of the dictionary's entries: 1e-16).
 #include "met2_t2_impl.cuh"
 
-namespace met2 {
+#if !defined(MET2_ECHO_RD) || !defined(MET2_ECHO_NS) || !defined(MET2_ECHO_LAUNCH)
+#error "met2_t2_echo_impl.cuh is included by met2_t2_echo_r<rank>.cu, which define MET2_ECHO_RD / _NS / _LAUNCH"
+#endif
 
-constexpr int RD = MET2_ECHO_RANK;    // rows of the reduced system (3 DMMA blocks of 8)
+namespace met2 {
+namespace MET2_ECHO_NS {
+
+constexpr int RD = MET2_ECHO_RD;      // rows of the reduced system (DMMA blocks of 8)
 constexpr int EC_LDD = RD + 2;        // row stride of the staged Ct table [column][row]: even (16-byte rows for 128-bit
                                       // loads with lane = column: a quarter warp covers all 32 banks) and conflict-free
                                       // for lane = row
@@ -799,13 +811,6 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
     }
 }
 
-bool t2_echo_eligible(const met2_t2_cfg* cfg) {
-    if (!(cfg->flags & MET2_T2_FLAG_ECHO_SPACE)) return false;
-    if (cfg->method == MET2_REG_X2) return cfg->nT2 <= EC_NCOL && !(cfg->flags & MET2_T2_FLAG_COLD_START);
-    if (cfg->method == MET2_REG_T2SPARC) return cfg->nT2 <= 128;
-    return false;
-}
-
 static int echo_warps(size_t tables, size_t per_warp) {
     const size_t budget = 227 * 1024 - 1024;
     int warps = tables < budget ? (int)((budget - tables) / per_warp) : 0;
@@ -857,11 +862,13 @@ static int t2_launch_echo_me(const T2Args& A, cudaStream_t st) {
     return check_launch("t2_echo_x2_kernel");
 }
 
-int t2_launch_echo_x2(const T2Args& A, cudaStream_t st) {
+}  // namespace MET2_ECHO_NS
+
+int MET2_ECHO_LAUNCH(const T2Args& A, cudaStream_t st) {
     if (!A.red_basis || !A.red_coef)
         return set_error(MET2_ERR_ARG, "met2_t2_fit: MET2_T2_FLAG_ECHO_SPACE needs the reduced echo basis (met2_echo_basis)");
-    if (A.cfg.nTE <= 32) return t2_launch_echo_me<1>(A, st);
-    return t2_launch_echo_me<2>(A, st);
+    if (A.cfg.nTE <= 32) return MET2_ECHO_NS::t2_launch_echo_me<1>(A, st);
+    return MET2_ECHO_NS::t2_launch_echo_me<2>(A, st);
 }
 
 }  // namespace met2

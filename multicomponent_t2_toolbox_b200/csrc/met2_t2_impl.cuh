@@ -962,8 +962,9 @@ int t2_launch_x2(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_lcurve(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_bayesreg(const T2Args& A, const T2Geom& g, cudaStream_t st);
 int t2_launch_gcv(const T2Args& A, const T2Geom& g, cudaStream_t st);
-// met2_t2_echo.cu (experimental, MET2_T2_FLAG_ECHO_SPACE)
+// met2_t2_echo_r16.cu / met2_t2_echo_r24.cu (MET2_T2_FLAG_ECHO_SPACE; rank = cfg.echo_rank)
 bool t2_echo_eligible(const met2_t2_cfg* cfg);
-int t2_launch_echo_x2(const T2Args& A, cudaStream_t st);
+int t2_launch_echo_r16(const T2Args& A, cudaStream_t st);
+int t2_launch_echo_r24(const T2Args& A, cudaStream_t st);
 
 }  // namespace met2

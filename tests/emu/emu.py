@@ -27,7 +27,7 @@ class T2Cfg(ctypes.Structure):   # met2_t2_cfg of include/met2.h
                 ("nLambda", ctypes.c_int32), ("maxfun", ctypes.c_int32),
                 ("factor", ctypes.c_double), ("lambda_fixed", ctypes.c_double),
                 ("brent_lo", ctypes.c_double), ("brent_hi", ctypes.c_double), ("brent_xatol", ctypes.c_double),
-                ("log_det_L", ctypes.c_double), ("flags", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("log_det_L", ctypes.c_double), ("flags", ctypes.c_int32), ("echo_rank", ctypes.c_int32)]
 
 
 class FaCfg(ctypes.Structure):   # met2_fa_cfg of include/met2.h
@@ -177,8 +177,10 @@ def gram_tables(dic, L):
     return G, kband, int(err[0])
 
 
-def echo_basis(dic, R=24):
-    """met2_echo_basis -> (basis [nA][nTE][R], coef [nA][nT2][R], tail [nA])."""
+def echo_basis(dic, R=None):
+    """met2_echo_basis -> (basis [nA][nTE][R], coef [nA][nT2][R], tail [nA]); R defaults to the library's MET2_ECHO_RANK."""
+    if R is None:
+        R = int(lib().met2_echo_rank(0))
     dic = np.ascontiguousarray(dic, dtype=np.float64)
     nA, m, n = dic.shape
     basis = np.full((nA, m, R), np.nan)
@@ -191,7 +193,7 @@ def echo_basis(dic, R=24):
 
 
 def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lambdas=None, myelin_T2=40.0, warps=2,
-           factor=1.02, lambda_fixed=1.8):
+           factor=1.02, lambda_fixed=1.8, echo_rank=0):
     """met2_t2_fit on host arrays (counting sort, tile list, shared full-set factor tables and the fit kernel, all
     emulated).  `warps` caps the warps per block (MET2_T2_WARPS).  Returns dict(fsol, est_signal, reg, maps, status,
     counters)."""
@@ -207,7 +209,7 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
     lam = np.ascontiguousarray(lambdas if lambdas is not None else np.zeros(1), dtype=np.float64)
     cfg = T2Cfg(method=METHODS[method], nTE=m, nT2=n, nA=nA, nLambda=len(lam), maxfun=300, factor=factor,
                 lambda_fixed=lambda_fixed, brent_lo=0.0, brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0,
-                flags=int(flags) | (64 if echo else 0), reserved=0)
+                flags=int(flags) | (64 if echo else 0), echo_rank=int(echo_rank))
     if method == "GCV":                      # algorithms.py:280
         cfg.brent_lo = 1e-8
     if method == "BayesReg":                 # bayesian_interpolation.py:100-101
@@ -227,8 +229,8 @@ def t2_fit(sig, fa_index, Dic_3D, L, T2s, method="X2", flags=0, echo=False, lamb
         ws = gd.array(int(nbytes), np.uint8, 0xA5)               # poisoned like a fresh torch.empty
         basis = coef = None
         if echo:                                                 # reduced echo basis from the library's own kernel
-            basis, coef, tail = echo_basis(dic)
-            assert tail.max() <= 1e-15, tail.max()
+            basis, coef, tail = echo_basis(dic, echo_rank if echo_rank else None)
+            assert tail.max() <= (4e-12 if echo_rank == 16 else 1e-15), tail.max()      # batched.ECHO_TAIL_MAX
         fn = lib().met2_t2_fit_echo
         fn.argtypes = [P, P, ctypes.c_int64, ctypes.POINTER(T2Cfg)] + [P] * 16
         _check(fn(_ptr(sig), _ptr(fa_index), V, ctypes.byref(cfg), _ptr(dic), _ptr(dicT), _ptr(G), _ptr(kband),

@@ -104,7 +104,7 @@ def test_c_abi_argument_checks_and_empty_batches():
     L.met2_last_error.restype = ctypes.c_char_p
     n, m = 60, 32
     cfg = emu.T2Cfg(method=2, nTE=m, nT2=n, nA=1, nLambda=50, maxfun=300, factor=1.02, lambda_fixed=1.8, brent_lo=0.0,
-                    brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=0, reserved=0)
+                    brent_hi=10.0, brent_xatol=1e-5, log_det_L=0.0, flags=0, echo_rank=0)
     assert L.met2_t2_workspace_bytes(10, ctypes.byref(cfg)) > 0
     emu.counters(reset_only=True)
     for field, bad in (("nT2", 0), ("nT2", 129), ("nTE", 65), ("nA", 0), ("method", 6), ("method", -1)):

@@ -92,6 +92,10 @@ def test_echo_space_x2_kernel_against_reference(setup):
     assert np.allclose(outs[0]["est_signal"], np.einsum("vec,vc->ve", D, outs[0]["fsol"]), rtol=1e-10, atol=1e-9)
     nofull = _run("forward", sig[:6], fa[:6], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=0, echo=True)
     _check(nofull, g["f"][sel[:6]], g["reg"][sel[:6]], gr["ind_m"], tol_f=1e-8)
+    # rank 16 of the reduced space (what the plan picks for this protocol, batched.ECHO_TAIL_MAX): same active sets,
+    # spectra in the accuracy class of the Gram-domain kernel
+    r16 = _run("forward", sig[:6], fa[:6], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16, echo=True, echo_rank=16)
+    _check(r16, g["f"][sel[:6]], g["reg"][sel[:6]], gr["ind_m"], tol_f=1e-7)
     lam = _run("forward", sig[:3], fa[:3], setup["Dic"], gr["L"], gr["T2s"], "X2", flags=16 | 1, echo=True)
     for i in range(3):
         Dv = np.ascontiguousarray(setup["Dic"][:, :, fa[i]])
