@@ -319,7 +319,8 @@ class Met2Plan:
         if self.echo_space and self._diagonal_L() and not (cfg.flags & COLD_START):
             # measured on the config-2 volume (profiles/r02_ab_*): X2-I 365 -> 211 ms, X2-InvT2 262 -> 190 ms,
             # T2SPARC (96 bins) 282 -> 91 ms
-            if (method == "X2" and self.npc <= 64) or (method == "T2SPARC" and self.npc <= 128):
+            # L-curve and BayesReg (met2_t2_echo_reg_impl.cuh): see profiles/r02_ab_echo_reg.json
+            if (method == "X2" and self.npc <= 64) or (method in ("T2SPARC", "L_curve", "BayesReg") and self.npc <= 128):
                 cfg.flags |= ECHO_SPACE
         for k, v in overrides.items():   # e.g. factor=..., lambda_fixed=..., maxfun=...
             setattr(cfg, k, v)

@@ -59,11 +59,14 @@ __global__ void t2_scatter_kernel(const int* __restrict__ fa_index, long long V,
     perm[pos] = (int)v;
 }
 
-// X2 (nT2 <= 64 columns staged per CTA) and T2SPARC with MET2_T2_FLAG_ECHO_SPACE run in the reduced echo space
+// X2 (nT2 <= 64 columns staged per CTA), T2SPARC, L-curve and BayesReg with MET2_T2_FLAG_ECHO_SPACE run in the reduced
+// echo space
 bool t2_echo_eligible(const met2_t2_cfg* cfg) {
     if (!(cfg->flags & MET2_T2_FLAG_ECHO_SPACE)) return false;
     if (cfg->method == MET2_REG_X2) return cfg->nT2 <= 64 && !(cfg->flags & MET2_T2_FLAG_COLD_START);
     if (cfg->method == MET2_REG_T2SPARC) return cfg->nT2 <= 128;
+    if (cfg->method == MET2_REG_LCURVE || cfg->method == MET2_REG_BAYESREG)
+        return cfg->nT2 <= 128 && !(cfg->flags & MET2_T2_FLAG_COLD_START);
     return false;
 }
 
@@ -199,8 +202,12 @@ static int t2_fit_impl(const double* sig, const int32_t* fa_index, int64_t V, co
     MET2_LAUNCH(nb, tb, 0, st, t2_scatter_kernel)(fa_index, V, cfg->nA, A.bin_start, A.cursor, A.perm);
     count_launch();
     if ((rc = check_launch("t2_scatter_kernel"))) return rc;
-    if (t2_echo_eligible(cfg))
-        return (cfg->echo_rank == MET2_ECHO_RANK_SMALL) ? t2_launch_echo_r16(A, st) : t2_launch_echo_r24(A, st);
+    if (t2_echo_eligible(cfg)) {
+        const bool small = (cfg->echo_rank == MET2_ECHO_RANK_SMALL);
+        if (cfg->method == MET2_REG_LCURVE || cfg->method == MET2_REG_BAYESREG)
+            return small ? t2_launch_echo_reg_r16(A, st) : t2_launch_echo_reg_r24(A, st);
+        return small ? t2_launch_echo_r16(A, st) : t2_launch_echo_r24(A, st);
+    }
     switch (cfg->method) {
         case MET2_REG_NNLS: return t2_launch_nnls(A, g, st);
         case MET2_REG_T2SPARC: return t2_launch_t2sparc(A, g, st);

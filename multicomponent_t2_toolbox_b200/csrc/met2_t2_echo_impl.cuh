@@ -44,6 +44,12 @@
 #if !defined(MET2_ECHO_RD) || !defined(MET2_ECHO_NS) || !defined(MET2_ECHO_LAUNCH)
 #error "met2_t2_echo_impl.cuh is included by met2_t2_echo_r<rank>.cu, which define MET2_ECHO_RD / _NS / _LAUNCH"
 #endif
+// MET2_ECHO_PART 1 (default): the X2 / T2SPARC kernels of this file; 2: the L-curve / BayesReg kernel of
+// met2_t2_echo_reg_impl.cuh (met2_t2_echo_reg_r<rank>.cu) on the same device functions — separate translation units so
+// that they compile in parallel.
+#ifndef MET2_ECHO_PART
+#define MET2_ECHO_PART 1
+#endif
 
 namespace met2 {
 namespace MET2_ECHO_NS {
@@ -107,8 +113,8 @@ __device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, d
 }
 
 // v = T (T^T bt), g = Ct^T v.  lane = position / row for the triangular products.
-template <int NC>
-__device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, int lane, double (&g)[NC], double& y,
+template <int NC, int NS>
+__device__ __forceinline__ void echo_solve(const Slots<NS>& W, const EchoOff& O, int lane, double (&g)[NC], double& y,
                                            bool& y_ok) {
     // y = T^T bt: fresh after a refactorisation, otherwise carried through the rank-one updates (echo_change)
     if (!y_ok) {
@@ -128,7 +134,8 @@ __device__ __forceinline__ void echo_solve(const Slots<2>& W, const EchoOff& O, 
 }
 
 // T <- inverse Cholesky factor of M_P + lam I.  Returns false if a pivot is not positive.
-__device__ __forceinline__ bool echo_refactor(const Slots<2>& W, const EchoOff& O, double lam, int lane) {
+template <int NS>
+__device__ __forceinline__ bool echo_refactor(const Slots<NS>& W, const EchoOff& O, double lam, int lane) {
     auto Aent = [&](int r, int c) -> double {
         const int hi = (r > c) ? r : c, lo = (r > c) ? c : r;
         double a = S[O.Mp + tri(hi) + lo];
@@ -136,7 +143,7 @@ __device__ __forceinline__ bool echo_refactor(const Slots<2>& W, const EchoOff& 
         return a;
     };
     __syncwarp();
-    return rebuild_T_blocked<2>(W, Aent, RD, lane);
+    return rebuild_T_blocked<NS>(W, Aent, RD, lane);
 }
 
 // M_P += sgn d d^T on the packed lower triangle, d = column j of the staged Ct table; leaves d in S[O.D..].
@@ -158,7 +165,8 @@ __device__ __forceinline__ void echo_mp_rank1(const EchoOff& O, int j, double sg
 }
 
 // Column j enters (sgn = +1) or leaves (sgn = -1) the positive set: M_P += sgn d d^T and the matching update of T.
-__device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O, int j, double sgn, double lam, int lane,
+template <int NS>
+__device__ __forceinline__ bool echo_change(const Slots<NS>& W, const EchoOff& O, int j, double sgn, double lam, int lane,
                                             double& y, bool& y_ok) {
     echo_mp_rank1(O, j, sgn, lane);
     // ---- u = T^T d, prefix sums of u^2
@@ -210,8 +218,8 @@ __device__ __forceinline__ bool echo_change(const Slots<2>& W, const EchoOff& O,
 // block_drop: the entry set is the FULL column set — drop every column whose unconstrained coefficient is not positive
 // in one go before the usual interpolation loop (x stays feasible on the reduced set).
 // On exit inP / x hold the solution (scaled unknowns xt = l * x).
-template <int NC>
-__device__ __forceinline__ void echo_nnls(const Slots<2>& W, const EchoOff& O, int n, double lam, int lane,
+template <int NC, int NS>
+__device__ __forceinline__ void echo_nnls(const Slots<NS>& W, const EchoOff& O, int n, double lam, int lane,
                                           unsigned& inP, double (&x)[NC], int& status, bool block_drop) {
     const int itmax = 3 * n;
     int iter = 0;
@@ -467,6 +475,19 @@ __device__ __forceinline__ void echo_stage_diag(const T2Args& A, int ncol, int n
 #define MET2_ECHO_MAX_THREADS 640       // A/B switch: 512 = 16 warps at 128 registers, 640 = 20 warps at 96 registers
 #endif
 constexpr int ECHO_MAX_THREADS = MET2_ECHO_MAX_THREADS;
+
+static int echo_warps(size_t tables, size_t per_warp) {
+    const size_t budget = 227 * 1024 - 1024;
+    int warps = tables < budget ? (int)((budget - tables) / per_warp) : 0;
+    if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
+    if (const char* ev = getenv("MET2_T2_WARPS")) {
+        const int w = atoi(ev);
+        if (w >= 1 && w < warps) warps = w;
+    }
+    return warps;
+}
+
+#if MET2_ECHO_PART == 1
 
 template <int ME>
 __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args A) {
@@ -811,17 +832,6 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
     }
 }
 
-static int echo_warps(size_t tables, size_t per_warp) {
-    const size_t budget = 227 * 1024 - 1024;
-    int warps = tables < budget ? (int)((budget - tables) / per_warp) : 0;
-    if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
-    if (const char* ev = getenv("MET2_T2_WARPS")) {
-        const int w = atoi(ev);
-        if (w >= 1 && w < warps) warps = w;
-    }
-    return warps;
-}
-
 template <int NC, int ME>
 static int t2_launch_echo_tik(const T2Args& A, cudaStream_t st) {
     const size_t tables = sizeof(double) * (size_t)echo_tik_table_doubles<NC>(A.cfg.nTE);
@@ -872,3 +882,11 @@ int MET2_ECHO_LAUNCH(const T2Args& A, cudaStream_t st) {
 }
 
 }  // namespace met2
+
+#else   // MET2_ECHO_PART == 2
+
+}  // namespace MET2_ECHO_NS
+}  // namespace met2
+#include "met2_t2_echo_reg_impl.cuh"
+
+#endif

@@ -966,5 +966,8 @@ int t2_launch_gcv(const T2Args& A, const T2Geom& g, cudaStream_t st);
 bool t2_echo_eligible(const met2_t2_cfg* cfg);
 int t2_launch_echo_r16(const T2Args& A, cudaStream_t st);
 int t2_launch_echo_r24(const T2Args& A, cudaStream_t st);
+// met2_t2_echo_reg_r16.cu / met2_t2_echo_reg_r24.cu (L-curve and BayesReg in the reduced echo space)
+int t2_launch_echo_reg_r16(const T2Args& A, cudaStream_t st);
+int t2_launch_echo_reg_r24(const T2Args& A, cudaStream_t st);
 
 }  // namespace met2

@@ -119,6 +119,31 @@ def test_echo_space_invt2_and_rejects_non_diagonal(setup):
     assert np.all(bad["status"] == (1 | 32)) and not bad["fsol"].any() and not bad["est_signal"].any()
 
 
+def test_echo_space_lcurve_and_bayesreg_against_oracle(setup):
+    """t2_echo_reg_kernel (met2_t2_echo_reg_impl.cuh): L-curve (algorithms.py:88-113) and BayesReg
+    (bayesian_interpolation.py:84-126, evidence by the structured Cholesky sweep) in the reduced echo space, both ranks,
+    I and InvT2, against the oracle: active sets bit-exact, the L-curve corner identical, BayesReg's lambda within the
+    reproducibility of its flat evidence (InvT2: DESIGN.md §5)."""
+    g, gr = setup["g"], setup["gr"]
+    sel, sig, fa = _pick(g, 3, offset=5)
+    Dv = [np.ascontiguousarray(setup["Dic"][:, :, a]) for a in fa]
+    for method, rm, rank, tol_f, tol_reg in (("L_curve", "I", 16, 1e-8, 1e-12), ("L_curve", "InvT2", 24, 1e-8, 1e-12),
+                                             ("BayesReg", "I", 16, 1e-7, 1e-6), ("BayesReg", "InvT2", 24, 1e-6, 1e-6)):
+        grm = O._grids(method, rm, "spline", 40.0, 32, 10.0, 1000.0)
+        out = _run("shuffle", sig, fa, setup["Dic"], grm["L"], gr["T2s"], method, echo=True, echo_rank=rank,
+                   lambdas=gr["lambda_reg"])
+        if rank == 16 and method == "BayesReg":
+            again = _run("reverse", sig, fa, setup["Dic"], grm["L"], gr["T2s"], method, echo=True, echo_rank=rank,
+                         lambdas=gr["lambda_reg"])
+            assert _same(out, again)
+        for i in range(len(sel)):
+            f_ref, s_ref, reg_ref = O.t2_fit_voxel(sig[i], Dv[i], method, grm["L"], gr["lambda_reg"])
+            assert out["status"][i] == 0 and np.array_equal(out["fsol"][i] > 0, f_ref > 0), (method, rm, i)
+            assert np.max(np.abs(out["fsol"][i] - f_ref)) < tol_f * np.abs(f_ref).max(), (method, rm, i)
+            assert np.max(np.abs(out["est_signal"][i] - s_ref)) < 1e-6 * np.abs(s_ref).max()
+            assert abs(out["reg"][i] - reg_ref) <= tol_reg * max(1.0, abs(reg_ref)), (method, rm, i)
+
+
 def test_edge_voxels_both_kernels(setup):
     """Empty / NaN / M[0] = 0 voxels and a bad FA index: flagged, all-zero outputs, neighbours unaffected
     (motor...:124-131, algorithms.py:56)."""
@@ -254,16 +279,18 @@ def _synthetic(npc, nte, nv, method, matrix, seed=3):
     return gr, Dic, sig, fa
 
 
-@pytest.mark.parametrize("method,matrix,npc,nte,nv,tol", [
-    ("T2SPARC", "InvT2", 96, 32, 3, 1e-6),       # the reference's T2SPARC grid: three column slots per lane
-    ("NNLS", "I", 100, 48, 3, 1e-6),             # BASELINE.json config 4 sizes: four column slots, two echo slots
-    ("X2", "I", 100, 48, 2, 1e-6),
-    ("BayesReg", "InvT2", 100, 48, 2, 1e-3),     # flat evidence: the reference does not reproduce itself
+@pytest.mark.parametrize("method,matrix,npc,nte,nv,tol,echo", [
+    ("T2SPARC", "InvT2", 96, 32, 3, 1e-6, False),    # the reference's T2SPARC grid: three column slots per lane
+    ("NNLS", "I", 100, 48, 3, 1e-6, False),          # BASELINE.json config 4 sizes: four column slots, two echo slots
+    ("X2", "I", 100, 48, 2, 1e-6, False),
+    ("BayesReg", "InvT2", 100, 48, 2, 1e-3, False),  # flat evidence: the reference does not reproduce itself
+    ("BayesReg", "InvT2", 100, 48, 2, 1e-3, True),   # config 4 in the reduced echo space (t2_echo_reg_kernel<5, 4, 2>)
+    ("L_curve", "I", 100, 48, 2, 1e-6, True),
 ])
-def test_production_kernels_large_sizes(method, matrix, npc, nte, nv, tol):
+def test_production_kernels_large_sizes(method, matrix, npc, nte, nv, tol, echo):
     emu.build()
     gr, Dic, sig, fa = _synthetic(npc, nte, nv, method, matrix)
-    out = _run("shuffle", sig, fa, Dic, gr["L"], gr["T2s"], method, lambdas=gr["lambda_reg"])
+    out = _run("shuffle", sig, fa, Dic, gr["L"], gr["T2s"], method, lambdas=gr["lambda_reg"], echo=echo)
     assert np.all(out["status"] == 0)
     for i in range(nv):
         f_ref, s_ref, reg_ref = O.t2_fit_voxel(sig[i], np.ascontiguousarray(Dic[:, :, fa[i]]), method, gr["L"],

@@ -392,8 +392,11 @@ def test_config3b_gcv_lambda_grid_and_half_degree_fa(phantom_sig):
     assert not t2["status"].cpu().numpy().any()
 
 
-METHOD_CASES = [("NNLS", "I", "brute-force", 60), ("L_curve", "I", "spline", 60), ("BayesReg", "I", "spline", 60),
-                ("X2", "L2", "spline", 60), ("T2SPARC", "InvT2", "spline", 96), ("GCV", "L2", "brute-force", 60)]
+# (method, matrix, FA method, bins, kernel family): L-curve and BayesReg with a diagonal matrix run in the reduced echo
+# space by default (t2_echo_reg_kernel); "gram" pins the Gram-domain kernel (echo_space=False) on the same voxels
+METHOD_CASES = [("NNLS", "I", "brute-force", 60, ""), ("L_curve", "I", "spline", 60, ""), ("BayesReg", "I", "spline", 60, ""),
+                ("L_curve", "I", "spline", 60, "gram"), ("BayesReg", "I", "spline", 60, "gram"),
+                ("X2", "L2", "spline", 60, ""), ("T2SPARC", "InvT2", "spline", 96, ""), ("GCV", "L2", "brute-force", 60, "")]
 
 
 def test_methods_subset_vs_reference(golden_methods):
@@ -407,9 +410,10 @@ def test_methods_subset_vs_reference(golden_methods):
     sig = g["sig"]
     V = sig.shape[0]
     rec = {}
-    for method, rm, fam, npc in METHOD_CASES:
+    for method, rm, fam, npc, family in METHOD_CASES:
         key = "%s_%s" % (method, rm)
-        plan = _plan(reg_method=method, reg_matrix=rm, FA_method=fam, npc=npc)
+        plan = _plan(reg_method=method, reg_matrix=rm, FA_method=fam, npc=npc, echo_space=(family != "gram"))
+        assert bool(plan.t2_cfg().flags & 64) == (family != "gram" and method in ("L_curve", "BayesReg", "T2SPARC"))
         fa, t2 = plan.fit(sig)
         idx_ref = g["fa_%s_%d" % (fam, npc)].astype(np.int64)
         fa_bad = fa["fa_index"].cpu().numpy() != idx_ref
@@ -426,7 +430,7 @@ def test_methods_subset_vs_reference(golden_methods):
                  reg_rel_err_max_agreeing=float(dreg[good].max()) if method != "NNLS" else 0.0,
                  max_abs_dMWF_agreeing=float(dmwf[good].max()), max_abs_dMWF_all=float(dmwf.max()),
                  frac_dMWF_below_1e4=float((dmwf < ABS_MAPS).mean()), status_nonzero=int((t2["status"] != 0).sum()))
-        rec[key] = r
+        rec[key + ("_" + family if family else "")] = r
     outdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     os.makedirs(outdir, exist_ok=True)
     with open(os.path.join(outdir, "parity_methods_subset.json"), "w") as fh:

@@ -93,38 +93,48 @@ def test_config4_subset_vs_reference(golden_config4):
     nn = plan.t2_fit(sig, idx_ref, reg_method="NNLS")
     fn, fn_ref = nn["fsol"].cpu().numpy(), g["f_nnls"]
     nn_bad = np.any((fn > 0) != (fn_ref > 0), axis=1)
-    t2 = plan.t2_fit(sig, idx_ref)
-    f, f_ref, f_p = t2["fsol"].cpu().numpy(), g["f_bayes"], g["f_bayesp"]
-    reg = t2["reg"].cpu().numpy()
-    sup_bad = np.any((f > 0) != (f_ref > 0), axis=1)
-    sup_self = np.any((f_p > 0) != (f_ref > 0), axis=1)
-    d_ours, d_self = _rel_err(f, f_ref), _rel_err(f_p, f_ref)
-    l_ours = np.abs(reg - g["bayes_reg"]) / g["bayes_reg"]
-    l_self = np.abs(g["bayesp_reg"] - g["bayes_reg"]) / g["bayes_reg"]
-    dmwf = np.abs(_mwf(f, plan) - _mwf(f_ref, plan))
-    dmwf_self = np.abs(_mwf(f_p, plan) - _mwf(f_ref, plan))
     rec = dict(voxels=int(V), fa_index_mismatches=int(fa_bad.sum()),
-               nnls_active_set_disagreements=int(nn_bad.sum()), nnls_spectrum_rel_err_max=float(_rel_err(fn, fn_ref).max()),
-               bayes=dict(active_set_disagreements=int(sup_bad.sum()), reference_self_disagreements=int(sup_self.sum()),
-                          spectrum_rel_over_1e6=int((d_ours > 1e-6).sum()), reference_self_over_1e6=int((d_self > 1e-6).sum()),
-                          spectrum_rel_median=float(np.median(d_ours)), reference_self_median=float(np.median(d_self)),
-                          spectrum_rel_max=float(d_ours.max()), reference_self_max=float(d_self.max()),
-                          lambda_rel_over_1e6=int((l_ours > 1e-6).sum()), reference_self_lambda_over_1e6=int((l_self > 1e-6).sum()),
-                          lambda_rel_max=float(l_ours.max()), reference_self_lambda_max=float(l_self.max()),
-                          max_abs_dMWF=float(dmwf.max()), reference_self_max_abs_dMWF=float(dmwf_self.max()),
-                          status_nonzero=int((t2["status"] != 0).sum())))
+               nnls_active_set_disagreements=int(nn_bad.sum()), nnls_spectrum_rel_err_max=float(_rel_err(fn, fn_ref).max()))
+    f_ref, f_p = g["f_bayes"], g["f_bayesp"]
+    sup_self = np.any((f_p > 0) != (f_ref > 0), axis=1)
+    d_self = _rel_err(f_p, f_ref)
+    l_self = np.abs(g["bayesp_reg"] - g["bayes_reg"]) / g["bayes_reg"]
+    dmwf_self = np.abs(_mwf(f_p, plan) - _mwf(f_ref, plan))
+    # both kernel families: reduced echo space (rank 24 for this protocol; the plan's default) and Gram domain
+    for key, echo in (("bayes", True), ("bayes_gram", False)):
+        pk = plan if echo else batched.Met2Plan(48, 8.0, 1000.0, reg_method="BayesReg", reg_matrix="InvT2",
+                                                FA_method="brute-force", npc=100, echo_space=False)
+        assert bool(pk.t2_cfg().flags & ECHO) == echo
+        t2 = pk.t2_fit(sig, idx_ref)
+        f = t2["fsol"].cpu().numpy()
+        reg = t2["reg"].cpu().numpy()
+        sup_bad = np.any((f > 0) != (f_ref > 0), axis=1)
+        d_ours = _rel_err(f, f_ref)
+        l_ours = np.abs(reg - g["bayes_reg"]) / g["bayes_reg"]
+        dmwf = np.abs(_mwf(f, plan) - _mwf(f_ref, plan))
+        rec[key] = dict(active_set_disagreements=int(sup_bad.sum()), reference_self_disagreements=int(sup_self.sum()),
+                        spectrum_rel_over_1e6=int((d_ours > 1e-6).sum()), reference_self_over_1e6=int((d_self > 1e-6).sum()),
+                        spectrum_rel_median=float(np.median(d_ours)), reference_self_median=float(np.median(d_self)),
+                        spectrum_rel_max=float(d_ours.max()), reference_self_max=float(d_self.max()),
+                        lambda_rel_over_1e6=int((l_ours > 1e-6).sum()), reference_self_lambda_over_1e6=int((l_self > 1e-6).sum()),
+                        lambda_rel_max=float(l_ours.max()), reference_self_lambda_max=float(l_self.max()),
+                        max_abs_dMWF=float(dmwf.max()), reference_self_max_abs_dMWF=float(dmwf_self.max()),
+                        status_nonzero=int((t2["status"] != 0).sum()))
+        if echo:
+            rec[key]["echo_rank"] = int(pk.dict_hr.echo_basis(pk.echo_ranks)[2])
     _record("parity_r2_config4_subset.json", rec)
-    b = rec["bayes"]
     assert rec["fa_index_mismatches"] == 0 and rec["nnls_active_set_disagreements"] == 0, rec
     assert rec["nnls_spectrum_rel_err_max"] < REL_SPECTRUM, rec
-    assert b["status_nonzero"] == 0, rec
-    assert b["active_set_disagreements"] <= b["reference_self_disagreements"] + 2, rec
     slack = int(0.01 * V)
-    assert b["spectrum_rel_over_1e6"] <= 2 * b["reference_self_over_1e6"] + slack, rec
-    assert b["lambda_rel_over_1e6"] <= 2 * b["reference_self_lambda_over_1e6"] + slack, rec
-    assert b["spectrum_rel_median"] <= 3.0 * b["reference_self_median"] + 1e-9, rec
-    assert b["spectrum_rel_max"] <= 10.0 * b["reference_self_max"], rec
-    assert b["max_abs_dMWF"] < ABS_MAPS, rec
+    for key in ("bayes", "bayes_gram"):
+        b = rec[key]
+        assert b["status_nonzero"] == 0, rec
+        assert b["active_set_disagreements"] <= b["reference_self_disagreements"] + 2, rec
+        assert b["spectrum_rel_over_1e6"] <= 2 * b["reference_self_over_1e6"] + slack, rec
+        assert b["lambda_rel_over_1e6"] <= 2 * b["reference_self_lambda_over_1e6"] + slack, rec
+        assert b["spectrum_rel_median"] <= 3.0 * b["reference_self_median"] + 1e-9, rec
+        assert b["spectrum_rel_max"] <= 10.0 * b["reference_self_max"], rec
+        assert b["max_abs_dMWF"] < ABS_MAPS, rec
 
 
 def test_echo_space_and_gram_kernels_vs_reference(golden_config2, golden_methods):
@@ -207,6 +217,51 @@ def test_echo_space_and_gram_kernels_vs_reference(golden_config2, golden_methods
         r = rec[name]
         assert r["status_nonzero"] == 0 and r["active_set_disagreements"] == 0, rec
         assert r["spectrum_rel_err_max_agreeing"] < REL_SPECTRUM and r["max_abs_dMWF"] < ABS_MAPS, rec
+
+
+def test_lcurve_corner_echo_equals_gram_full_volume():
+    """The L-curve corner (algorithms.py:88-113, 150-206) is a discrete choice that looks at neighbouring grid points:
+    the reduced-echo-space kernel (default) and the Gram-domain kernel must pick the same lambda over the whole config-2
+    volume.  (The first echo-space version solved the whole grid in echo space and picked a spurious corner at
+    lambda <= 2.4e-8 in 531 of 552 960 voxels with InvT2, where the oracle sided with the Gram-domain kernel in all 121
+    voxels examined — profiles/r02_lcurve_arbiter.json; the small end of the grid now stays in the Gram domain.)
+    40 of the voxels are also checked against the oracle."""
+    from multicomponent_t2_toolbox_b200.phantom import make_phantom
+    ph = make_phantom((96, 96, 60), seed=2, fa_mode="b1", backend="gpu")
+    sig_h = ph["data"].reshape(-1, 32)
+    sig = torch.as_tensor(sig_h).cuda()
+    rec = {}
+    fa = None
+    for rm in ("I", "InvT2"):
+        reg = {}
+        for name, echo in (("echo", True), ("gram", False)):
+            plan = batched.Met2Plan(32, 10.0, 1000.0, reg_method="L_curve", reg_matrix=rm, FA_method="spline", echo_space=echo)
+            assert bool(plan.t2_cfg().flags & ECHO) == echo
+            if fa is None:
+                fa = plan.fa_fit(sig)
+            out = plan.t2_fit(sig, fa["fa_index"])
+            assert int((out["status"] != 0).sum()) == 0
+            reg[name] = out["reg"].cpu().numpy()
+            if echo:
+                f_echo = out["fsol"]
+            else:
+                rel = float(((f_echo - out["fsol"]).abs().max(dim=1).values /
+                             out["fsol"].abs().max(dim=1).values.clamp_min(1e-300))[torch.as_tensor(reg["echo"] == reg["gram"]).cuda()].max())
+        differ = int((reg["echo"] != reg["gram"]).sum())
+        idx = fa["fa_index"].cpu().numpy()
+        Dic = plan.dict_hr.to_reference_layout()
+        pick = np.random.default_rng(3).choice(len(idx), 40, replace=False)
+        bad_or = 0
+        for v in pick:
+            _, _, reg_ref = O.t2_fit_voxel(sig_h[v], np.ascontiguousarray(Dic[:, :, idx[v]]), "L_curve", plan.Laplac, plan.lambda_reg)
+            bad_or += int(reg["echo"][v] != reg_ref)
+        rec["L_curve_" + rm] = dict(voxels=int(len(idx)), corner_differs_echo_vs_gram=differ,
+                                    spectrum_rel_max_same_corner=rel, oracle_voxels=40, echo_corner_differs_from_oracle=bad_or)
+    _record("parity_r2_lcurve_corner.json", rec)
+    for key, r in rec.items():
+        assert r["corner_differs_echo_vs_gram"] <= 3, rec          # <= 5e-6 of the voxels
+        assert r["echo_corner_differs_from_oracle"] == 0, rec
+        assert r["spectrum_rel_max_same_corner"] < REL_SPECTRUM, rec
 
 
 def test_echo_basis_reproduces_the_dictionary():

@@ -1,0 +1,60 @@
+"""A/B of the reduced-echo-space L-curve / BayesReg kernel (t2_echo_reg_kernel, the plan's default for a diagonal
+regularisation matrix) against the Gram-domain kernels over whole volumes: the config-2 volume (552 960 voxels, 32 echoes,
+60 bins; L-curve and BayesReg with I and InvT2) and config 4 (48 echoes, 100 bins, BayesReg + InvT2, brute-force FA).
+T2-stage time, voxels whose active set / lambda differ, spectrum and MWF differences.
+
+    gpurun --timeout 900 -- 'timeout 800 python tools/gpu_ab_echo_reg.py > gpurun_out/ab_echo_reg.log 2>&1'
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from multicomponent_t2_toolbox_b200 import batched  # noqa: E402
+from multicomponent_t2_toolbox_b200.phantom import make_phantom  # noqa: E402
+
+rep = {}
+cases = [("config2", 32, 10.0, None, "spline", m, rm) for m in ("L_curve", "BayesReg") for rm in ("I", "InvT2")]
+cases.append(("config4", 48, 8.0, 100, "brute-force", "BayesReg", "InvT2"))
+which = os.environ.get("WHICH")
+sigs = {}
+for cfg, nte, tau, npc, fam, method, rm in cases:
+    key = "%s_%s_%s" % (cfg, method, rm)
+    if which and key not in which.split(","):
+        continue
+    if cfg not in sigs:
+        ph = make_phantom((96, 96, 60), n_echoes=nte, tau=tau, seed=2 if cfg == "config2" else 4, fa_mode="b1", backend="gpu")
+        sigs[cfg] = torch.as_tensor(ph["data"].reshape(-1, nte)).cuda()
+    sig = sigs[cfg]
+    res = {}
+    for name, kw in (("echo", {}), ("gram", dict(echo_space=False))):
+        plan = batched.Met2Plan(nte, tau, 1000.0, reg_method=method, reg_matrix=rm, FA_method=fam, npc=npc, **kw)
+        fa = plan.fa_fit(sig)
+        for _ in range(2):
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = plan.t2_fit(sig, fa["fa_index"])
+            e1.record()
+            torch.cuda.synchronize()
+        red = plan.dict_hr.echo_basis(plan.echo_ranks) if name == "echo" else None
+        res[name] = dict(ms=e0.elapsed_time(e1), out={k: v.clone() for k, v in out.items()}, rank=(red[2] if red else 0))
+        del out
+    e, g = res["echo"]["out"], res["gram"]["out"]
+    scale = g["fsol"].abs().max(dim=1).values.clamp_min(1e-300)
+    rel = (e["fsol"] - g["fsol"]).abs().max(dim=1).values / scale
+    bad = ((e["fsol"] > 0) != (g["fsol"] > 0)).any(dim=1)
+    dl = (e["reg"] - g["reg"]).abs() / g["reg"].abs().clamp_min(1e-300)
+    dm = (e["maps"][:, 0] - g["maps"][:, 0]).abs()
+    rep[key] = dict(voxels=int(sig.shape[0]), echo_rank=res["echo"]["rank"], t2_ms_echo=res["echo"]["ms"], t2_ms_gram=res["gram"]["ms"],
+                    status_nonzero_echo=int((e["status"] != 0).sum()), status_nonzero_gram=int((g["status"] != 0).sum()),
+                    active_set_differs=int(bad.sum()), lambda_differs=int((dl > 0).sum()), lambda_rel_gt_1e6=int((dl > 1e-6).sum()),
+                    lambda_rel_max=float(dl.max()), spectrum_rel_gt_1e6=int((rel > 1e-6).sum()),
+                    spectrum_rel_median=float(rel.median()), spectrum_rel_max_agreeing=float(rel[~bad].max()),
+                    mwf_abs_gt_1e4=int((dm > 1e-4).sum()), mwf_abs_max=float(dm.max()))
+    print(json.dumps({key: rep[key]}), flush=True)
+    del res, e, g
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(rep, open(os.path.join(ROOT, "gpurun_out", "ab_echo_reg.json"), "w"), indent=1)
