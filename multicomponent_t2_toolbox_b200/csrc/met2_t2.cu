@@ -170,6 +170,8 @@ static int t2_fit_impl(const double* sig, const int32_t* fa_index, int64_t V, co
     A.lam_tab = nullptr;
     A.ntab = 0;
     A.ntab_use = 0;
+    A.lcurve_switch = T2_LCURVE_SWITCH;
+    if (const char* ev = getenv("MET2_LCURVE_SWITCH")) A.lcurve_switch = atof(ev);   // tuning / A-B runs
     if (const int ntab = t2_full_tables(cfg)) {
         double* lam_tab = reinterpret_cast<double*>(w);  w += align256(sizeof(double) * T2_NTAB_MAX);
         double* tfull = reinterpret_cast<double*>(w);

@@ -26,10 +26,13 @@
 // of (lam I + M_P) with a rank-deficient M_P (condition number up to 4e14 for InvT2 at lam = 1e-8) is accurate to
 // 1e-8 .. 2e-6 there, with errors that are independent from one grid point to the next, and produced a spurious corner
 // at lambda <= 2.4e-8 in 531 of 552 960 voxels (InvT2; 1 with I) where the Gram-domain kernel agreed with the reference
-// in all 121 voxels examined (profiles/r02_lcurve_arbiter.json).  Grid points below EV_LCURVE_SWITCH = 1e-3 are therefore
-// solved by nnls_gram on G + lam K in the same reduced space (warm-started, supports of 4-15 columns: cheap), the rest —
-// where supports reach 40-60 columns and the Gram-domain factor is expensive — in echo space (error <= 2e-9 at 1e-3,
-// against neighbour differences of 1e-4).
+// in all 121 voxels examined (profiles/r02_lcurve_arbiter.json).  Grid points below T2Args::lcurve_switch = 1e-5 are
+// therefore solved by nnls_gram on G + lam K in the same reduced space (warm-started, supports of 4-10 columns), the
+// rest in echo space.  The noise-to-difference ratio falls as 1 / lambda^2: at 1e-5 it is 6e-6 of its value at the
+// largest failing lambda.  Measured over the whole config-2 volume with I and with InvT2 (2 x 552 960 voxels): the chosen
+// corner equals the Gram-domain kernel's in every voxel for a switch at 1e-6, 1e-5, 1e-4 and 1e-3
+// (profiles/r02_ab_lcurve_switch.json; T2 stage 348 / 394 / 413 / 441 ms with I against 290 ms all-echo and 565 ms
+// Gram-domain).
 #pragma once
 
 namespace met2 {
@@ -38,7 +41,6 @@ namespace MET2_ECHO_NS {
 constexpr int EV_RR = RD / 8;   // rows of the evidence state S_j per lane: rg + 8 a, rg = lane & 7
 constexpr int EV_CC = RD / 4;   // columns per lane: cb EV_CC + b, cb = lane >> 3
 
-constexpr double EV_LCURVE_SWITCH = 1e-3;   // L-curve grid points below this lambda: Gram domain (see the header)
 constexpr int EV_LCURVE_PMAX = 32;          // positions of the Gram-domain factor of the L-curve kernel (one slot per lane)
 template <int METHOD>
 struct EchoRegPmax {
@@ -292,101 +294,50 @@ __global__ void __launch_bounds__(EchoRegThreads<NC>::value, 1) t2_echo_reg_kern
                     __syncwarp();
                 }
                 set_dspace<NC>(W, Cg, O.B, lane);     // candidate test in the reduced space: rows of C, right-hand side bt
-                int nst = 0;
-                int p = nnls_gram<NC, GSH, 1>(W, oG, Gg, ldg, 0, false, 0.0, n, RD, lane, nst, 0, false);   // <= RD positions
-                // xt0 = l * x0 -> W.xc and the snapshot; SSE0 = |Ct xt0 - bt|^2 + |b_perp|^2
+                // ---- lambda-search driver: a small state machine around ONE inlined Gram-domain call site (nnls_gram) and
+                //      ONE inlined echo-space call site (echo_refactor + echo_nnls) — the kernel with a call site per use was
+                //      18.8 k SASS instructions and instruction-fetch bound (config-2 L-curve 541 ms against 270 ms for the
+                //      same counted work)
+                //   PH_PLAIN : plain NNLS (algorithms.py:55-82) -> SSE0, support; BayesReg: beta
+                //   PH_GRID  : L-curve grid (algorithms.py:88-113), below A.lcurve_switch in the Gram domain
+                //   PH_FINAL : L-curve solve at the corner (algorithms.py:262-269)
+                //   PH_BRENT : BayesReg evidence search (bayesian_interpolation.py:84-105)
+                enum { PH_PLAIN = 0, PH_GRID = 1, PH_FINAL = 2, PH_BRENT = 3 };
+                int phase = PH_PLAIN;
+                int nst = 0, est = 0, p = 0, gi = 0;
                 unsigned inP = 0u;
                 double x[NC];
-                int nnz = 0;
 #pragma unroll
-                for (int s = 0; s < NC; ++s) {
-                    const int j = lane + 32 * s;
-                    const double xv = (j < n) ? S[W.xc + j] * S[oL + j] : 0.0;
-                    x[s] = (xv > 0.0) ? xv : 0.0;
-                    if (xv > 0.0) ++nnz;
-                }
-                __syncwarp();
+                for (int s = 0; s < NC; ++s) x[s] = 0.0;
+                bool in_echo = false;
+                double SSE0 = 0.0, beta = 0.0, lam_cur = 0.0, lam = 0.0;
+                const int nl = A.cfg.nLambda;
+                Brent B;
+                while (true) {
+                    double sse = SSE0, nrm = 0.0;
+                    bool done = false;
+                    if (METHOD == MET2_REG_LCURVE && phase != PH_PLAIN && !(lam_cur > 0.0)) {
+                        // lambda_reg[0] = 0 (motor...:248-251): the plain solution, kept in the snapshot
+                        double a = 0.0;
 #pragma unroll
-                for (int s = 0; s < NC; ++s) {
-                    S[oSnap + lane + 32 * s] = x[s];
-                    S[W.xc + lane + 32 * s] = x[s];
-                }
-                __syncwarp();
-                const double SSE0 = echo_fit_sse(oSnap, O, n, lane, -1) + perp;
-                // enter echo space from the scaled solution xt in S[W.xc ..]: support, coefficients, M_P by rank-one terms
-                auto to_echo = [&]() {
-                    inP = 0u;
-#pragma unroll
-                    for (int s = 0; s < NC; ++s) {
-                        const double xv = S[W.xc + lane + 32 * s];
-                        x[s] = (xv > 0.0) ? xv : 0.0;
-                        if (xv > 0.0) inP |= 1u << s;
-                    }
-                    for (int i = lane; i < tri(RD); i += 32) S[O.Mp + i] = 0.0;
-                    __syncwarp();
-                    for (int j = 0; j < n; ++j) {
-                        const bool in = (__shfl_sync(FULL_MASK, inP, j & 31) >> (j >> 5)) & 1u;
-                        if (in) echo_mp_rank1(O, j, 1.0, lane);
-                    }
-                    __syncwarp();
-                };
-                int est = 0;
-                // one Tikhonov solve at lam > 0 from the current set; returns the residual |D f - M|^2
-                auto solve = [&](double lam) -> double {
-                    if (!echo_refactor<NC>(W, O, lam, lane)) st |= MET2_ST_NOT_PD;
-                    echo_nnls<NC>(W, O, n, lam, lane, inP, x, est, false);
-#pragma unroll
-                    for (int s = 0; s < NC; ++s) S[W.xc + lane + 32 * s] = x[s];
-                    __syncwarp();
-                    // bt - Ct xt = lam v exactly (push-through identity); the explicit product only after an itmax stop
-                    if (est & 1) return echo_fit_sse(W.xc, O, n, lane, -1) + perp;
-                    const double ve = (lane < RD) ? S[O.V + lane] : 0.0;
-                    return fma(lam * lam, warp_sum(ve * ve), perp);
-                };
-                auto norm2 = [&]() -> double {       // |L f|^2 = |xt|^2
-                    double a = 0.0;
-#pragma unroll
-                    for (int s = 0; s < NC; ++s) a = fma(x[s], x[s], a);
-                    return warp_sum(a);
-                };
-                double lam = 0.0;
-                if (METHOD == MET2_REG_BAYESREG) {
-                    // bayesian_interpolation.py:84-105: beta from the plain solution, Brent on the evidence over [1e-8, 2]
-                    nnz = (int)__reduce_add_sync(FULL_MASK, (unsigned)nnz);
-                    const double dof = fmax((double)(m - nnz), 1.0);
-                    const double sigma = sqrt(SSE0 / dof);
-                    const double beta = 1.0 / (sigma * sigma);
-                    Brent B;
-                    lam = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
-                    to_echo();
-                    while (true) {
-                        const double sse = solve(lam);
-                        const double nrm = norm2();
-                        const double cost = echo_bayes_cost<NC>(W, O, oL, n, m, lane, lam, beta, sse, nrm, A.cfg.log_det_L, st);
-                        const double lam_eval = lam;
-                        const bool more = B.feed(cost, lam);
-                        if (B.xf == lam_eval) {
-                            // the reference re-solves at Brent's best abscissa: keep that evaluation's solution instead
-#pragma unroll
-                            for (int s = 0; s < NC; ++s) S[oSnap + lane + 32 * s] = x[s];
+                        for (int s = 0; s < NC; ++s) {
+                            const double xv = S[oSnap + lane + 32 * s];
+                            a = fma(xv, xv, a);
                         }
-                        __syncwarp();
-                        if (!more) break;
-                    }
-                    lam = B.xf;
-                } else {
-                    // algorithms.py:88-113: the curves over the lambda grid, corner by the triangle method, final solve.
-                    // Below EV_LCURVE_SWITCH in the Gram domain (warm-started from the previous point), then echo space.
-                    const int nl = A.cfg.nLambda;
-                    bool in_echo = false;
-                    // one Gram-domain Tikhonov solve from the carried-over positions; false if the factor is full
-                    auto gram_solve = [&](double lg, double& sse, double& nrm) -> bool {
-                        const int pn = nnls_gram<NC, GSH, 1>(W, oG, Gg, ldg, oKb, true, lg, n, PMAX, lane, nst, p, false);
+                        nrm = warp_sum(a);
+                        done = true;
+                    } else if (phase == PH_PLAIN ||
+                               (METHOD == MET2_REG_LCURVE && !in_echo && lam_cur < A.lcurve_switch && p < PMAX)) {
+                        // Gram domain: the plain solve from the empty set (<= RD positions), or a Tikhonov solve on
+                        // G + lam K from the carried-over positions (<= PMAX; a full factor sends the point to echo space)
+                        const bool plain = (METHOD == MET2_REG_BAYESREG) ? true : (phase == PH_PLAIN);   // BayesReg: compile-time
+                        const int pn = nnls_gram<NC, GSH, 1>(W, oG, Gg, ldg, oKb, !plain, lam_cur, n, plain ? RD : PMAX, lane,
+                                                              nst, plain ? 0 : p, false);
                         double a = 0.0;
 #pragma unroll
                         for (int s = 0; s < NC; ++s) {
                             const int j = lane + 32 * s;
-                            const double xv = (j < n) ? S[W.xc + j] * S[oL + j] : 0.0;
+                            const double xv = (j < n) ? S[W.xc + j] * S[oL + j] : 0.0;     // xt = l * x
                             x[s] = (xv > 0.0) ? xv : 0.0;
                             a = fma(x[s], x[s], a);
                         }
@@ -395,56 +346,107 @@ __global__ void __launch_bounds__(EchoRegThreads<NC>::value, 1) t2_echo_reg_kern
                         for (int s = 0; s < NC; ++s) S[W.xc + lane + 32 * s] = x[s];
                         __syncwarp();
                         p = pn;
-                        if (pn >= PMAX) return false;
-                        nrm = warp_sum(a);
-                        sse = echo_fit_sse(W.xc, O, n, lane, -1) + perp;
-                        return true;
-                    };
-                    for (int gi = 0; gi < nl; ++gi) {
-                        const double lg = S[oLam + gi];
-                        double sse = SSE0, nrm = 0.0;
-                        bool done = false;
-                        if (!(lg > 0.0)) {        // lambda_reg[0] = 0 (motor...:248-251): the plain solution
-                            double a = 0.0;
+                        if (plain || pn < PMAX) {
+                            nrm = warp_sum(a);
+                            sse = echo_fit_sse(W.xc, O, n, lane, -1) + perp;     // |Ct xt - bt|^2 + |b_perp|^2
+                            done = true;
+                        }
+                    }
+                    if (!done) {
+                        if (!in_echo) {
+                            // enter echo space from the scaled solution xt in S[W.xc ..]: support, coefficients, M_P
+                            inP = 0u;
 #pragma unroll
                             for (int s = 0; s < NC; ++s) {
-                                const double xv = S[oSnap + lane + 32 * s];
-                                a = fma(xv, xv, a);
+                                const double xv = S[W.xc + lane + 32 * s];
+                                x[s] = (xv > 0.0) ? xv : 0.0;
+                                if (xv > 0.0) inP |= 1u << s;
                             }
-                            nrm = warp_sum(a);
-                            done = true;
-                        } else if (!in_echo && lg < EV_LCURVE_SWITCH && p < PMAX) {
-                            done = gram_solve(lg, sse, nrm);
-                        }
-                        if (!done) {
-                            if (!in_echo) {
-                                to_echo();
-                                in_echo = true;
+                            for (int i = lane; i < tri(RD); i += 32) S[O.Mp + i] = 0.0;
+                            __syncwarp();
+                            for (int j = 0; j < n; ++j) {
+                                const bool in = (__shfl_sync(FULL_MASK, inP, j & 31) >> (j >> 5)) & 1u;
+                                if (in) echo_mp_rank1(O, j, 1.0, lane);
                             }
-                            sse = solve(lg);
-                            nrm = norm2();
+                            __syncwarp();
+                            in_echo = true;
                         }
+                        if (!echo_refactor<NC>(W, O, lam_cur, lane)) st |= MET2_ST_NOT_PD;
+                        echo_nnls<NC>(W, O, n, lam_cur, lane, inP, x, est, false);
+                        double a = 0.0;
+#pragma unroll
+                        for (int s = 0; s < NC; ++s) {
+                            S[W.xc + lane + 32 * s] = x[s];
+                            a = fma(x[s], x[s], a);
+                        }
+                        __syncwarp();
+                        nrm = warp_sum(a);       // |L f|^2 = |xt|^2
+                        // bt - Ct xt = lam v exactly (push-through identity); the explicit product only after an itmax stop
+                        if (est & 1) {
+                            sse = echo_fit_sse(W.xc, O, n, lane, -1) + perp;
+                        } else {
+                            const double ve = (lane < RD) ? S[O.V + lane] : 0.0;
+                            sse = fma(lam_cur * lam_cur, warp_sum(ve * ve), perp);
+                        }
+                    }
+                    // ---- consume the solve
+                    if (phase == PH_PLAIN) {
+                        SSE0 = sse;
+#pragma unroll
+                        for (int s = 0; s < NC; ++s) S[oSnap + lane + 32 * s] = x[s];
+                        __syncwarp();
+                        if (METHOD == MET2_REG_BAYESREG) {
+                            // bayesian_interpolation.py:84-105: beta from the plain solution, Brent over [1e-8, 2]
+                            int nnz = 0;
+#pragma unroll
+                            for (int s = 0; s < NC; ++s)
+                                if (x[s] > 0.0) ++nnz;
+                            nnz = (int)__reduce_add_sync(FULL_MASK, (unsigned)nnz);
+                            const double dof = fmax((double)(m - nnz), 1.0);
+                            const double sigma = sqrt(SSE0 / dof);
+                            beta = 1.0 / (sigma * sigma);
+                            lam_cur = B.start(A.cfg.brent_lo, A.cfg.brent_hi, A.cfg.brent_xatol, A.cfg.maxfun);
+                            phase = PH_BRENT;
+                        } else {
+                            gi = 0;
+                            lam_cur = S[oLam];
+                            phase = PH_GRID;
+                        }
+                    } else if (phase == PH_BRENT) {
+                        const double cost = echo_bayes_cost<NC>(W, O, oL, n, m, lane, lam_cur, beta, sse, nrm, A.cfg.log_det_L, st);
+                        const double lam_eval = lam_cur;
+                        const bool more = B.feed(cost, lam_cur);
+                        if (B.xf == lam_eval) {
+                            // the reference re-solves at Brent's best abscissa: keep that evaluation's solution instead
+#pragma unroll
+                            for (int s = 0; s < NC; ++s) S[oSnap + lane + 32 * s] = x[s];
+                        }
+                        __syncwarp();
+                        if (!more) {
+                            lam = B.xf;
+                            break;
+                        }
+                    } else if (phase == PH_GRID) {
                         if (lane == 0) {
                             S[oLx + gi] = log(sse + 1e-200);
                             S[oLy + gi] = log(nrm + 1e-200);
                         }
                         __syncwarp();
-                    }
-                    lam = S[oLam + select_corner_warp(oLx, oLy, nl, lane)];
-                    if (lam > 0.0) {
-                        // final solve (algorithms.py:262-269 at the corner): same rule; the Gram-domain positions are
-                        // still those of its last grid point (the echo-space solves do not touch them)
-                        double sse, nrm;
-                        bool done = false;
-                        if (lam < EV_LCURVE_SWITCH && p < PMAX) done = gram_solve(lam, sse, nrm);
-                        if (!done) {
-                            if (!in_echo) to_echo();
-                            (void)solve(lam);
+                        ++gi;
+                        if (gi < nl) {
+                            lam_cur = S[oLam + gi];
+                        } else {
+                            lam = S[oLam + select_corner_warp(oLx, oLy, nl, lane)];
+                            if (!(lam > 0.0)) break;       // the plain solution, already in the snapshot
+                            lam_cur = lam;
+                            phase = PH_FINAL;
                         }
+                    } else {   // PH_FINAL
 #pragma unroll
                         for (int s = 0; s < NC; ++s) S[oSnap + lane + 32 * s] = x[s];
+                        __syncwarp();
+                        break;
                     }
-                    __syncwarp();
                 }
                 // ---- hand out the solution in the snapshot: fitted signal U (Ct xt), x = xt / l
                 __syncwarp();

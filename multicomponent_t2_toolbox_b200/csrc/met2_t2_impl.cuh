@@ -44,12 +44,15 @@ struct T2Args {
     const double* lam_tab;   // [ntab]
     int ntab;                // tables built
     int ntab_use;            // how many of them the NNLS full-set starts consult
+    double lcurve_switch;    // echo-space L-curve: grid points below this lambda are solved in the Gram domain
+                             // (met2_t2_echo_reg_impl.cuh); MET2_LCURVE_SWITCH overrides it for A/B runs
 };
 
 constexpr int T2_NTAB_X2 = 3;      // measured on config 2 (T2 stage): no table 444 ms, 2 tables 398, 3 tables 390, 4 tables 390
 constexpr int T2_NTAB_BAYES = 9;   // BayesReg: the evidence needs the FULL-set factor at every abscissa, so every tabulated
                                    // abscissa saves a whole n x n factorisation (bayes_cost)
 constexpr int T2_NTAB_MAX = 16;
+constexpr double T2_LCURVE_SWITCH = 1e-5;   // see T2Args::lcurve_switch
 
 // ---------------------------------------------------------------------------------------------- L-curve corner
 // Triangle method of algorithms.py:150-206 (select_corner + scale_curve) on curves of length nl at S[oLx..], S[oLy..].
