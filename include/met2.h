@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MET2_VERSION 110 /* 0.1.1: met2_echo_basis, met2_t2_fit_echo */
+#define MET2_VERSION 120 /* 0.1.2: met2_t2_cfg.echo_rank, met2_echo_rank; L-curve / BayesReg in the reduced echo space */
 
 /* error codes */
 #define MET2_OK 0
@@ -88,13 +88,14 @@ typedef struct met2_fa_cfg {
 #define MET2_T2_FLAG_FULL_START 16    /* X2: start the solves at Brent's first (voxel-independent) abscissae from the full
                                         column set, with inverse-Cholesky factors shared per flip angle
                                         (worth it when L = I; same minimiser) */
-#define MET2_T2_FLAG_ECHO_SPACE 64    /* X2 (nT2 <= 64) and T2SPARC (nT2 <= 128) with a DIAGONAL L (I, InvT2; asserted by
-                                        the caller): Tikhonov solves in the reduced echo space (24 x 24 factor per
-                                        voxel, csrc/met2_t2_echo.cu) instead of the Gram domain (nT2 x nT2).  Needs
-                                        the tables of met2_echo_basis -> call met2_t2_fit_echo.  A non-diagonal L
-                                        skips every voxel with MET2_ST_ECHO_BAD_L.  Same minimiser as the Gram-domain
-                                        path; measured faster for X2-I and T2SPARC (profiles/r02_ab_*), which is why
-                                        batched.Met2Plan sets it for those by default */
+#define MET2_T2_FLAG_ECHO_SPACE 64    /* X2 (nT2 <= 64), T2SPARC, L-curve and BayesReg (nT2 <= 128) with a DIAGONAL L (I,
+                                        InvT2; asserted by the caller): Tikhonov solves in the reduced echo space (16 x 16
+                                        or 24 x 24 factor per voxel, csrc/met2_t2_echo_impl.cuh, met2_t2_echo_reg_impl.cuh)
+                                        instead of the Gram domain (nT2 x nT2).  Needs the tables of met2_echo_basis ->
+                                        call met2_t2_fit_echo with cfg.echo_rank = their R.  A non-diagonal L skips every
+                                        voxel with MET2_ST_ECHO_BAD_L; every other method ignores the flag.  Same
+                                        minimiser as the Gram-domain path; measured 1.4-3.6x faster (profiles/r02_ab_*),
+                                        which is why batched.Met2Plan sets it by default for these methods */
 #define MET2_T2_FLAG_COLD_START 4    /* start every NNLS of a lambda search from the empty set like the reference,
                                         instead of warm-starting from the previous solution (same minimiser) */
 
@@ -161,12 +162,13 @@ int met2_t2_fit(const double* sig, const int32_t* fa_index, int64_t V, const met
  * orthonormal and C_a = U_a^T D_a (column-pivoted Gram-Schmidt, csrc/met2_basis.cu).
  * basis [nA][nTE][R], coef [nA][nT2][R] (C_a[e][j] stored at [j][e]), tail [nA] = max_j |d_j - U C_j| / max_j |d_j|
  * per angle (may be NULL): the measured residual of the reduction, which the caller checks against its tolerance
- * (batched.Dictionary: 1e-15) before using the echo-space kernels.  R must be MET2_ECHO_RANK for met2_t2_fit_echo. */
+ * (batched.ECHO_TAIL_MAX: 1e-15 at rank 24, 4e-12 at rank 16) before using the echo-space kernels.  For met2_t2_fit_echo R
+ * must be MET2_ECHO_RANK or MET2_ECHO_RANK_SMALL (met2_echo_rank) and be passed in cfg.echo_rank. */
 int met2_echo_basis(const double* dic, int nA, int nTE, int nT2, int R, double* basis, double* coef, double* tail,
                     void* stream);
 
-/* met2_t2_fit with the tables of met2_echo_basis: required when cfg->flags has MET2_T2_FLAG_ECHO_SPACE (the X2 / T2SPARC
- * Tikhonov solves then run in the reduced echo space); otherwise identical to met2_t2_fit. */
+/* met2_t2_fit with the tables of met2_echo_basis: required when cfg->flags has MET2_T2_FLAG_ECHO_SPACE (the X2 / T2SPARC /
+ * L-curve / BayesReg Tikhonov solves then run in the reduced echo space); otherwise identical to met2_t2_fit. */
 int met2_t2_fit_echo(const double* sig, const int32_t* fa_index, int64_t V, const met2_t2_cfg* cfg, const double* dic,
                      const double* dicT, const double* G, const double* kband, const double* lambdas,
                      const double* logT2, const uint8_t* comp, const double* red_basis, const double* red_coef,

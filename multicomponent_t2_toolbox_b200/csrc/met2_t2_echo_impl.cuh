@@ -164,11 +164,12 @@ __device__ __forceinline__ void echo_mp_rank1(const EchoOff& O, int j, double sg
     __syncwarp();
 }
 
-// Column j enters (sgn = +1) or leaves (sgn = -1) the positive set: M_P += sgn d d^T and the matching update of T.
+// The update of T that goes with M_P += sgn d d^T (echo_mp_rank1 has left d in S[O.D..]): T' = T Q, and y' = Q^T y when y
+// is valid.  Returns false — T untouched — if the downdate lost positivity in floating point; the caller then
+// refactors from the (already updated) M_P.
 template <int NS>
-__device__ __forceinline__ bool echo_change(const Slots<NS>& W, const EchoOff& O, int j, double sgn, double lam, int lane,
-                                            double& y, bool& y_ok) {
-    echo_mp_rank1(O, j, sgn, lane);
+__device__ __forceinline__ bool echo_update_T(const Slots<NS>& W, const EchoOff& O, double sgn, int lane, double& y,
+                                              bool y_ok) {
     // ---- u = T^T d, prefix sums of u^2
     double u[1];
     tmul_transposed<1>(W.T, O.D, RD, lane, u);
@@ -178,11 +179,7 @@ __device__ __forceinline__ bool echo_change(const Slots<NS>& W, const EchoOff& O
     double hm1 = __shfl_up_sync(FULL_MASK, h, 1);
     if (lane == 0) hm1 = 1.0;
     const bool okh = (h > 0.0) && (hm1 > 0.0);
-    if (!__all_sync(FULL_MASK, okh)) {
-        // downdate lost positivity in floating point: refactor from the (already updated) M_P
-        y_ok = false;
-        return echo_refactor(W, O, lam, lane);
-    }
+    if (!__all_sync(FULL_MASK, okh)) return false;
     const double delta = sqrt(hm1 / h);
     const double q = -sgn * u[0] / (h * delta);
     if (y_ok) {
@@ -213,68 +210,86 @@ __device__ __forceinline__ bool echo_change(const Slots<NS>& W, const EchoOff& O
     return true;
 }
 
-// Lawson-Hanson in echo space for one lambda.  On entry T is the factor of M_P + lam I for the set `inP` (bit s of lane
-// l = column l + 32 s) and x[s] holds a feasible point on it (x > 0 on P, 0 elsewhere); an empty set is allowed.
+// Lawson-Hanson in echo space for one lambda.  On entry M_P belongs to the set `inP` (bit s of lane l = column l + 32 s)
+// and x[s] holds a feasible point on it (x > 0 on P, 0 elsewhere); an empty set is allowed.  refactor: T has to be
+// rebuilt from M_P + lam I first (a new lambda); otherwise T is the factor for `inP` already.
 // block_drop: the entry set is the FULL column set — drop every column whose unconstrained coefficient is not positive
 // in one go before the usual interpolation loop (x stays feasible on the reduced set).
-// On exit inP / x hold the solution (scaled unknowns xt = l * x).
+// On exit inP / x hold the solution (scaled unknowns xt = l * x); status bit 0: itmax, bit 1: a pivot was not positive.
+//
+// One loop with ONE inlined site each for the refactorisation, the rank-one change and the solve (the version with
+// nnls.f's two nested loops inlined the solve and the change twice and the blocked refactorisation three times: the
+// kernels are instruction-fetch bound): A. apply the pending set changes — the entering column or the
+// leaving ones, lowest column first; B. solve; C. `secondary`: the feasibility test / interpolation step of nnls.f's
+// inner loop; D. otherwise: the entering column, arg-max of the dual over the zero set (outer loop).
 template <int NC, int NS>
 __device__ __forceinline__ void echo_nnls(const Slots<NS>& W, const EchoOff& O, int n, double lam, int lane,
-                                          unsigned& inP, double (&x)[NC], int& status, bool block_drop) {
+                                          unsigned& inP, double (&x)[NC], int& status, bool block_drop, bool refactor) {
     const int itmax = 3 * n;
     int iter = 0;
-    bool secondary_first = __any_sync(FULL_MASK, inP != 0u);
-    bool have_g = false;   // g is the solve for the current set (left by an accepted interpolation loop)
+    bool secondary = __any_sync(FULL_MASK, inP != 0u);   // a non-empty entry set is checked for feasibility first
     double g[NC];
     double y = 0.0;        // y = T^T bt of the current factor (lane = position), valid when y_ok
     bool y_ok = false;
+    int enter_j = -1;      // column that enters next
+    unsigned outm = 0u;    // columns that leave next
     while (true) {
-        if (!secondary_first) {
-            if ((int)__reduce_add_sync(FULL_MASK, (unsigned)__popc(inP)) >= n) break;
-            // ---- entering column: arg-max of the dual w = lam g over the zero set (lam > 0: same order as g)
-            if (!have_g) echo_solve<NC>(W, O, lane, g, y, y_ok);
-            double bv = 0.0;
-            int bj = -1;
+        // ---- A. pending set changes
+        while (true) {
+            int k;
+            double sgn;
+            if (enter_j >= 0) {
+                k = enter_j;
+                sgn = 1.0;
+                enter_j = -1;
+            } else {
+                k = 0x7fffffff;
 #pragma unroll
-            for (int s = 0; s < NC; ++s) {
-                const int col = lane + 32 * s;
-                if (col < n && !((inP >> s) & 1u) && g[s] > bv) {
-                    bv = g[s];
-                    bj = col;
+                for (int s = NC - 1; s >= 0; --s)
+                    if ((outm >> s) & 1u) k = lane + 32 * s;
+                k = (int)__reduce_min_sync(FULL_MASK, (unsigned)k);
+                if (k == 0x7fffffff) break;
+                sgn = -1.0;
+                if ((k & 31) == lane) {
+                    const unsigned bit = 1u << (k >> 5);
+                    outm &= ~bit;
+                    inP &= ~bit;
+#pragma unroll
+                    for (int s = 0; s < NC; ++s)
+                        if (s == (k >> 5)) x[s] = 0.0;
                 }
             }
-            const int j = warp_argmax_pos(bv, bj);
-            if (j < 0) break;
-            if ((j & 31) == lane) inP |= 1u << (j >> 5);
-            if (!echo_change(W, O, j, 1.0, lam, lane, y, y_ok)) status |= 2;
+            echo_mp_rank1(O, k, sgn, lane);
+            // a downdate that loses positivity in floating point: T is rebuilt from the updated M_P below
+            if (!refactor && !echo_update_T(W, O, sgn, lane, y, y_ok)) refactor = true;
         }
-        secondary_first = false;
-        have_g = false;
-        bool stop = false;
-        while (true) {
+        if (refactor) {
+            if (!echo_refactor(W, O, lam, lane)) status |= 2;
+            refactor = false;
+            y_ok = false;
+        }
+        // ---- B. solve for the current set
+        if (secondary) {
             ++iter;
             if (iter > itmax) {
                 status |= 1;
-                stop = true;
                 break;
             }
-            echo_solve<NC>(W, O, lane, g, y, y_ok);
+        }
+        echo_solve<NC>(W, O, lane, g, y, y_ok);
+        // ---- C. feasibility on P (interpolation loop of nnls.f)
+        if (secondary) {
             const bool drop_now = block_drop;
             block_drop = false;
             unsigned negm = 0u;
 #pragma unroll
             for (int s = 0; s < NC; ++s)
                 if (((inP >> s) & 1u) && g[s] <= 0.0) negm |= 1u << s;
-            if (!__any_sync(FULL_MASK, negm != 0u)) {
-#pragma unroll
-                for (int s = 0; s < NC; ++s) x[s] = ((inP >> s) & 1u) ? g[s] : 0.0;
-                have_g = true;
-                break;
-            }
-            unsigned outm = 0u;   // columns that leave now
-            if (drop_now) {
-                outm = negm;
-            } else {
+            if (__any_sync(FULL_MASK, negm != 0u)) {
+                if (drop_now) {
+                    outm = negm;
+                    continue;
+                }
                 double bt = 2.0;
                 int bi = -1;
 #pragma unroll
@@ -289,7 +304,10 @@ __device__ __forceinline__ void echo_nnls(const Slots<NS>& W, const EchoOff& O, 
                 }
                 double alpha = 0.0;
                 const int jb = warp_argmin_nonneg(bt, bi, alpha);
-                if (jb < 0) break;
+                if (jb < 0) {          // no step found: back to the outer loop with a fresh solve (nnls.f leaves the loop)
+                    secondary = false;
+                    continue;
+                }
 #pragma unroll
                 for (int s = 0; s < NC; ++s) {
                     if ((inP >> s) & 1u) {
@@ -297,27 +315,29 @@ __device__ __forceinline__ void echo_nnls(const Slots<NS>& W, const EchoOff& O, 
                         if (x[s] <= 0.0 || lane + 32 * s == jb) outm |= 1u << s;
                     }
                 }
+                continue;
             }
-            // ---- remove them one by one (lowest column first)
-            while (true) {
-                int k = 0x7fffffff;
 #pragma unroll
-                for (int s = NC - 1; s >= 0; --s)
-                    if ((outm >> s) & 1u) k = lane + 32 * s;
-                k = (int)__reduce_min_sync(FULL_MASK, (unsigned)k);
-                if (k == 0x7fffffff) break;
-                if ((k & 31) == lane) {
-                    const unsigned bit = 1u << (k >> 5);
-                    outm &= ~bit;
-                    inP &= ~bit;
+            for (int s = 0; s < NC; ++s) x[s] = ((inP >> s) & 1u) ? g[s] : 0.0;
+            secondary = false;
+        }
+        // ---- D. entering column: arg-max of the dual w = lam g over the zero set (lam > 0: same order as g)
+        if ((int)__reduce_add_sync(FULL_MASK, (unsigned)__popc(inP)) >= n) break;
+        double bv = 0.0;
+        int bj = -1;
 #pragma unroll
-                    for (int s = 0; s < NC; ++s)
-                        if (s == (k >> 5)) x[s] = 0.0;
-                }
-                if (!echo_change(W, O, k, -1.0, lam, lane, y, y_ok)) status |= 2;
+        for (int s = 0; s < NC; ++s) {
+            const int col = lane + 32 * s;
+            if (col < n && !((inP >> s) & 1u) && g[s] > bv) {
+                bv = g[s];
+                bj = col;
             }
         }
-        if (stop) break;
+        const int j = warp_argmax_pos(bv, bj);
+        if (j < 0) break;
+        if ((j & 31) == lane) inP |= 1u << (j >> 5);
+        enter_j = j;
+        secondary = true;
     }
 }
 
@@ -658,8 +678,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_x2_kernel(T2Args 
                 double sse_snap = 0.0;
                 int est = 0;
                 while (true) {
-                    if (!echo_refactor(W, O, lam, lane)) st |= MET2_ST_NOT_PD;
-                    echo_nnls<2>(W, O, n, lam, lane, inP, x, est, block_drop);
+                    echo_nnls<2>(W, O, n, lam, lane, inP, x, est, block_drop, true);
                     block_drop = false;
 #pragma unroll
                     for (int s = 0; s < 2; ++s) S[W.xc + lane + 32 * s] = x[s];
@@ -814,7 +833,7 @@ __global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args
 #pragma unroll
                 for (int s = 0; s < NC; ++s) x[s] = 0.0;
                 int est = 0;
-                echo_nnls<NC>(W, O, n, lam, lane, inP, x, est, false);
+                echo_nnls<NC>(W, O, n, lam, lane, inP, x, est, false, false);
 #pragma unroll
                 for (int s = 0; s < NC; ++s) S[oX + lane + 32 * s] = x[s];
                 __syncwarp();

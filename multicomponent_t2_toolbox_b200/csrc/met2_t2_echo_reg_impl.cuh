@@ -371,8 +371,7 @@ __global__ void __launch_bounds__(EchoRegThreads<NC>::value, 1) t2_echo_reg_kern
                             __syncwarp();
                             in_echo = true;
                         }
-                        if (!echo_refactor<NC>(W, O, lam_cur, lane)) st |= MET2_ST_NOT_PD;
-                        echo_nnls<NC>(W, O, n, lam_cur, lane, inP, x, est, false);
+                        echo_nnls<NC>(W, O, n, lam_cur, lane, inP, x, est, false, true);
                         double a = 0.0;
 #pragma unroll
                         for (int s = 0; s < NC; ++s) {

@@ -26,7 +26,7 @@ def test_header_symbols_exported_and_bound():
     for s in syms:
         assert hasattr(lib, s), "libmet2.so does not export %s" % s
     assert set(_lib.SIGNATURES) == set(syms)
-    assert lib.met2_version() == 110
+    assert lib.met2_version() == 120
 
 
 def test_struct_layout_matches_header():
@@ -77,7 +77,7 @@ def test_c_host_program_links_and_fails_loudly_without_cuda():
     report the ABI version and stop with an error — not compute anything on the CPU."""
     import subprocess
     r = subprocess.run([_c_host_binary()], capture_output=True, text=True, timeout=120)
-    assert "met2 C-ABI version 110" in r.stdout
+    assert "met2 C-ABI version 120" in r.stdout
     assert r.returncode != 0 and ("error" in r.stderr.lower())
 
 

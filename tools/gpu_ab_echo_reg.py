@@ -32,15 +32,17 @@ for cfg, nte, tau, npc, fam, method, rm in cases:
     for name, kw in (("echo", {}), ("gram", dict(echo_space=False))):
         plan = batched.Met2Plan(nte, tau, 1000.0, reg_method=method, reg_matrix=rm, FA_method=fam, npc=npc, **kw)
         fa = plan.fa_fit(sig)
-        for _ in range(2):
+        best = None
+        for _ in range(3):      # the first call of a process has run at half speed now and then: best of three
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             out = plan.t2_fit(sig, fa["fa_index"])
             e1.record()
             torch.cuda.synchronize()
+            best = e0.elapsed_time(e1) if best is None else min(best, e0.elapsed_time(e1))
         red = plan.dict_hr.echo_basis(plan.echo_ranks) if name == "echo" else None
-        res[name] = dict(ms=e0.elapsed_time(e1), out={k: v.clone() for k, v in out.items()}, rank=(red[2] if red else 0))
+        res[name] = dict(ms=best, out={k: v.clone() for k, v in out.items()}, rank=(red[2] if red else 0))
         del out
     e, g = res["echo"]["out"], res["gram"]["out"]
     scale = g["fsol"].abs().max(dim=1).values.clamp_min(1e-300)
