@@ -10,10 +10,12 @@ met2_gaussian_smooth); the data behind the mean-spectrum figure (:375-403) is co
 table (Mean_spectrum_from_all_voxels.txt) instead of a PNG (no matplotlib here).
 """
 import os
+import threading
+from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
-from .. import batched, nifti_io, pipeline
+from .. import _lib, batched, nifti_io, pipeline
 from ..reference_api import create_Laplacian_matrix, fitting_slice_T2  # noqa: F401
 
 OUTPUTS = ("MWF", "IEWF", "FWF", "T2_M", "T2_IE", "TWC", "FA", "fsol_4D", "Est_Signal", "reg_param")
@@ -45,10 +47,26 @@ def n_gpus_from_num_cores(num_cores):
     return min(int(num_cores), avail)
 
 
+def _warm_gpus(n_gpus):
+    """Create the CUDA contexts of the GPUs the fit will use and load libmet2.so — run in a thread beside the NIfTI
+    load (gunzip releases the GIL).  Errors are left for the fit itself to raise."""
+    try:
+        import torch
+        _lib.load()
+        for i in range(min(int(n_gpus), torch.cuda.device_count())):
+            torch.zeros(1, device="cuda:%d" % i)
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+
+
 def motor_recon_met2(TE_array, path_to_data, path_to_mask, path_to_save_data, TR, reg_method, reg_matrix, denoise,
                      FA_method, FA_smooth, myelin_T2, num_cores):
     """Same arguments as the reference.  `num_cores` selects the number of GPUs (-1 = all visible; see
     n_gpus_from_num_cores): the masked voxels of the volume are spread over them by pipeline.MultiGpuFit."""
+    n_gpus = n_gpus_from_num_cores(num_cores)
+    warm = threading.Thread(target=_warm_gpus, args=(n_gpus,), daemon=True)   # CUDA contexts + libmet2.so while the files load
+    warm.start()
     img = nifti_io.load(path_to_data)
     data = img.get_fdata().astype(np.float64, copy=False)
     mask = nifti_io.load(path_to_mask).get_fdata().astype(np.int64, copy=False)
@@ -63,7 +81,7 @@ def motor_recon_met2(TE_array, path_to_data, path_to_mask, path_to_save_data, TR
         raise SystemExit(1)
     join = (lambda name: path_to_save_data + name) if path_to_save_data.endswith('/') else \
         (lambda name: os.path.join(path_to_save_data, name))
-    n_gpus = n_gpus_from_num_cores(num_cores)
+    warm.join()
     print('Using ', n_gpus, ' GPU(s)')
     if denoise == 'TV':
         print('Step #1: Denoising using Total Variation:')
@@ -82,8 +100,11 @@ def motor_recon_met2(TE_array, path_to_data, path_to_mask, path_to_save_data, TR
                                 FA_method, myelin_T2=myelin_T2, data_fa=data_fa, diagnostics=True, premasked=True,
                                 n_gpus=n_gpus)
     print('Step #4: Estimation of quantitative metrics')
-    for name in OUTPUTS:
-        nifti_io.save(vol[name], join(name + '.nii.gz'), affine=img.affine)
+    # the ten volumes (motor...:474-503) are written concurrently, largest first: every writer deflates with all cores
+    # (nifti_io), but the eight 3-D maps are too small to keep them busy one at a time (2.2 s -> 1.2 s on 8 cores)
+    order = sorted(OUTPUTS, key=lambda name: -vol[name].size)
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        list(pool.map(lambda name: nifti_io.save(vol[name], join(name + '.nii.gz'), affine=img.affine), order))
     dg = vol.get("diagnostics")
     if dg is not None:
         np.savetxt(join('Mean_spectrum_from_all_voxels.txt'),
