@@ -1,5 +1,7 @@
 """pipeline.MultiGpuFit on ONE config-2 volume, standalone (one process, all visible GPUs): wall time per call for 1..N
-devices with a per-device phase trace (MET2_MULTI_TRACE=1).  -> gpurun_out/multi_time.json"""
+devices with a per-device phase trace (MET2_MULTI_TRACE=1).  -> gpurun_out/multi_time.json
+env: SHAPE (96,96,60), TILE (replication factor per axis: 2 -> the 4.42 M-voxel volume of config 5), METHOD / RM / NPC,
+REPS (timed calls, default 5), OUT (file name under gpurun_out/)."""
 import json
 import os
 import sys
@@ -15,19 +17,24 @@ from multicomponent_t2_toolbox_b200.phantom import make_phantom  # noqa: E402
 
 shape = tuple(int(x) for x in os.environ.get("SHAPE", "96,96,60").split(","))
 ph = make_phantom(shape, seed=2, fa_mode="b1", backend="gpu")
-vol = torch.as_tensor(ph["data"].reshape(-1, 32)).pin_memory()
+tile = int(os.environ.get("TILE", "1"))
+data = np.tile(ph["data"], (tile, tile, tile, 1)) if tile > 1 else ph["data"]
+method, rm = os.environ.get("METHOD", "X2"), os.environ.get("RM", "I")
+npc = int(os.environ["NPC"]) if "NPC" in os.environ else None
+reps = int(os.environ.get("REPS", "5"))
+vol = torch.as_tensor(data.reshape(-1, 32)).pin_memory()
 V = vol.shape[0]
 n_all = torch.cuda.device_count()
-rec = {"voxels": int(V), "devices_visible": n_all, "runs": []}
+rec = {"voxels": int(V), "devices_visible": n_all, "method": method, "reg_matrix": rm, "runs": []}
 bufs = None
 for n in sorted({1, 2, 4, n_all} & set(range(1, n_all + 1))):
-    multi = pipeline.MultiGpuFit.create(n, 32, 10.0, 1000.0, reg_method="X2", reg_matrix="I", FA_method="spline")
+    multi = pipeline.MultiGpuFit.create(n, 32, 10.0, 1000.0, reg_method=method, reg_matrix=rm, FA_method="spline", npc=npc)
     if bufs is None:
         bufs = pipeline.host_buffers(multi.plans[0], V)
-    for _ in range(3):
+    for _ in range(2 if tile > 1 else 3):
         multi.fit(vol, out=bufs)
     ts = []
-    for _ in range(5):
+    for _ in range(reps):
         t0 = time.perf_counter()
         r = multi.fit(vol, out=bufs)
         ts.append(1e3 * (time.perf_counter() - t0))
@@ -38,5 +45,5 @@ t1 = rec["runs"][0]["ms_median"]
 for r in rec["runs"]:
     r["strong_efficiency"] = t1 / (r["gpus"] * r["ms_median"])
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(rec, open(os.path.join(ROOT, "gpurun_out", "multi_time.json"), "w"), indent=1)
+json.dump(rec, open(os.path.join(ROOT, "gpurun_out", os.environ.get("OUT", "multi_time.json")), "w"), indent=1)
 print(json.dumps({r["gpus"]: (round(r["ms_median"], 1), round(r["strong_efficiency"], 3)) for r in rec["runs"]}))
