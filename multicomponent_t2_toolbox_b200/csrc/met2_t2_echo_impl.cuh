@@ -495,11 +495,19 @@ __device__ __forceinline__ void echo_stage_diag(const T2Args& A, int ncol, int n
 #define MET2_ECHO_MAX_THREADS 640       // A/B switch: 512 = 16 warps at 128 registers, 640 = 20 warps at 96 registers
 #endif
 constexpr int ECHO_MAX_THREADS = MET2_ECHO_MAX_THREADS;
+// Per-kernel launch bounds, measured on the config-2 volume (profiles/r02_ab_echo_warps.json; 640 / 768 / 896 / 1024
+// threads = 20 / 24 / 28 / 30 warps per SM at 96 / 80 / 72 / 64 registers): X2 136.6 / 146.1 / 142.2 / 141.3 ms and the
+// L-curve 293 / 344 / 363 / 394 ms are best at 640 (more resident warps sit in more phases of the kernel: instruction
+// fetch), T2SPARC 56.8 / 54.6 / 52.3 / 51.4 ms and BayesReg (60 bins) 366 / 353 / 353 / 339 ms at 1024.
+#ifndef MET2_ECHO_TIK_MAX_THREADS
+#define MET2_ECHO_TIK_MAX_THREADS 1024
+#endif
+constexpr int ECHO_TIK_MAX_THREADS = MET2_ECHO_TIK_MAX_THREADS;
 
-static int echo_warps(size_t tables, size_t per_warp) {
+static int echo_warps(size_t tables, size_t per_warp, int max_threads = ECHO_MAX_THREADS) {
     const size_t budget = 227 * 1024 - 1024;
     int warps = tables < budget ? (int)((budget - tables) / per_warp) : 0;
-    if (warps > ECHO_MAX_THREADS / 32) warps = ECHO_MAX_THREADS / 32;
+    if (warps > max_threads / 32) warps = max_threads / 32;
     if (const char* ev = getenv("MET2_T2_WARPS")) {
         const int w = atoi(ev);
         if (w >= 1 && w < warps) warps = w;
@@ -743,7 +751,7 @@ __host__ __device__ __forceinline__ int echo_tik_table_doubles(int m) {
 }
 
 template <int NC, int ME>
-__global__ void __launch_bounds__(ECHO_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args A) {
+__global__ void __launch_bounds__(ECHO_TIK_MAX_THREADS, 1) t2_echo_tik_kernel(T2Args A) {
     __shared__ int s_tile, s_next, s_badL;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = A.cfg.nT2, m = A.cfg.nTE;
@@ -855,7 +863,7 @@ template <int NC, int ME>
 static int t2_launch_echo_tik(const T2Args& A, cudaStream_t st) {
     const size_t tables = sizeof(double) * (size_t)echo_tik_table_doubles<NC>(A.cfg.nTE);
     const size_t per_warp = sizeof(double) * (size_t)echo_tik_warp_doubles<NC>();
-    const int warps = echo_warps(tables, per_warp);
+    const int warps = echo_warps(tables, per_warp, ECHO_TIK_MAX_THREADS);
     if (warps < 1) return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit (echo space): tables do not fit in shared memory");
     const size_t smem = tables + per_warp * warps;
     int sms = sm_count();

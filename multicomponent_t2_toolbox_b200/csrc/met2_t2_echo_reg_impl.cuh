@@ -178,13 +178,15 @@ __device__ __forceinline__ double echo_bayes_cost(const Slots<NC>& W, const Echo
     return pd ? (cost1 + cost2) : INFINITY;
 }
 
-template <int NC>
+// launch bounds (profiles/r02_ab_echo_warps.json): the L-curve is best at 640 threads (96 registers), BayesReg at 60 bins
+// at 1024 (64 registers; 30 warps fit beside the tables); 100 bins: shared memory allows 12-15 warps -> 512 (128 registers)
+template <int METHOD, int NC>
 struct EchoRegThreads {
-    static constexpr int value = (NC <= 2) ? ECHO_MAX_THREADS : 512;   // 100 bins: shared memory allows ~15 warps; 128 registers
+    static constexpr int value = (NC > 2) ? 512 : (METHOD == MET2_REG_BAYESREG ? 1024 : ECHO_MAX_THREADS);
 };
 
 template <int METHOD, int NC, int ME>
-__global__ void __launch_bounds__(EchoRegThreads<NC>::value, 1) t2_echo_reg_kernel(T2Args A) {
+__global__ void __launch_bounds__(EchoRegThreads<METHOD, NC>::value, 1) t2_echo_reg_kernel(T2Args A) {
     static_assert(NC == 2 || NC == 4, "column slots");
     static_assert(METHOD == MET2_REG_LCURVE || METHOD == MET2_REG_BAYESREG, "method");
     constexpr bool GSH = (NC == 2);
@@ -471,8 +473,7 @@ template <int METHOD, int NC, int ME>
 static int t2_launch_echo_reg_one(const T2Args& A, cudaStream_t st) {
     const size_t tables = sizeof(double) * (size_t)echo_reg_table_doubles<NC>(A.cfg.nT2, A.cfg.nTE);
     const size_t per_warp = sizeof(double) * (size_t)echo_reg_warp_doubles<METHOD, NC>();
-    int warps = echo_warps(tables, per_warp);
-    if (warps > EchoRegThreads<NC>::value / 32) warps = EchoRegThreads<NC>::value / 32;
+    const int warps = echo_warps(tables, per_warp, EchoRegThreads<METHOD, NC>::value);
     if (warps < 1) return set_error(MET2_ERR_UNSUPPORTED, "met2_t2_fit (echo space): tables do not fit in shared memory");
     const size_t smem = tables + per_warp * warps;
     int sms = sm_count();

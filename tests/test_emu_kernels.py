@@ -142,6 +142,22 @@ def test_echo_space_lcurve_and_bayesreg_against_oracle(setup):
             assert np.max(np.abs(out["fsol"][i] - f_ref)) < tol_f * np.abs(f_ref).max(), (method, rm, i)
             assert np.max(np.abs(out["est_signal"][i] - s_ref)) < 1e-6 * np.abs(s_ref).max()
             assert abs(out["reg"][i] - reg_ref) <= tol_reg * max(1.0, abs(reg_ref)), (method, rm, i)
+    # L-curve with the Gram-domain / echo-space switch moved above the grid (MET2_LCURVE_SWITCH): every point is tried
+    # in the Gram domain until the 32-position factor is full, which sends the rest of the grid to echo space — the
+    # fall-back path of the driver; and with the switch at 0: the whole grid in echo space
+    grm = O._grids("L_curve", "I", "spline", 40.0, 32, 10.0, 1000.0)
+    for sw in ("100", "0"):
+        os.environ["MET2_LCURVE_SWITCH"] = sw
+        try:
+            out = _run("forward", sig[:2], fa[:2], setup["Dic"], grm["L"], gr["T2s"], "L_curve", echo=True, echo_rank=16,
+                       lambdas=gr["lambda_reg"])
+        finally:
+            del os.environ["MET2_LCURVE_SWITCH"]
+        for i in range(2):
+            f_ref, _, reg_ref = O.t2_fit_voxel(sig[i], Dv[i], "L_curve", grm["L"], gr["lambda_reg"])
+            assert out["status"][i] == 0 and np.array_equal(out["fsol"][i] > 0, f_ref > 0), (sw, i)
+            assert np.max(np.abs(out["fsol"][i] - f_ref)) < 1e-8 * np.abs(f_ref).max(), (sw, i)
+            assert out["reg"][i] == reg_ref, (sw, i)
 
 
 def test_edge_voxels_both_kernels(setup):
