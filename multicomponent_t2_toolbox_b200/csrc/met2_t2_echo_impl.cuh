@@ -112,22 +112,69 @@ __device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, d
     for (int s = 0; s < NC; ++s) g[s] = g0[s] + g1[s];
 }
 
+// The two triangular products of the RD x RD factor with compile-time triangle offsets and 128-bit broadcast loads of the
+// vector (S[oV ..], oV even: every per-warp region starts on an even offset and tri(16), tri(24), 64 and RD are even).
+// Same association as tmul / tmul_transposed of met2_nnls.cuh (even columns in one accumulator, odd in the other), so the
+// results are bitwise the same; those keep a runtime trip count and per-iteration triangle arithmetic because they serve
+// any p — here they were 17 % of the X2 kernel's instructions.  Measured (GPU call 24, config-2 volume): X2-I 136.5 ->
+// 131.1 ms, T2SPARC 51.3 -> 49.9 ms; but the L-curve / BayesReg kernel, which is bound by instruction fetch, lost what
+// the +128 SASS instructions per call site cost (L-curve 293 -> 323 ms, BayesReg 339 -> 346 ms): MET2_ECHO_PART 2 keeps
+// the compact generic products.
+constexpr bool ECHO_UNROLLED_TRI = (MET2_ECHO_PART == 1);
+// out_r = sum_{c >= r} T(r, c) v_c  (lane = row r; lanes >= RD get 0)
+__device__ __forceinline__ double echo_tmul(int oT, int oV, int lane) {
+    if (!ECHO_UNROLLED_TRI) {
+        double v[1];
+        tmul<1>(oT, oV, RD, lane, v);
+        return v[0];
+    }
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < RD; c += 2) {
+        double vv[2];
+        lds_vec<2>(oV + c, vv);
+        const double e0 = (lane <= c) ? S[oT + tri(c) + lane] : 0.0;
+        const double e1 = (lane <= c + 1) ? S[oT + tri(c + 1) + lane] : 0.0;
+        a0 = fma(e0, vv[0], a0);
+        a1 = fma(e1, vv[1], a1);
+    }
+    return a0 + a1;
+}
+// out_i = sum_{k <= i} T(k, i) v_k  (lane = column i; lanes >= RD get 0)
+__device__ __forceinline__ double echo_tmul_t(int oT, int oV, int lane) {
+    if (!ECHO_UNROLLED_TRI) {
+        double v[1];
+        tmul_transposed<1>(oT, oV, RD, lane, v);
+        return v[0];
+    }
+    const int base = oT + tri(lane);
+    const int kmax = (lane < RD) ? lane : -1;
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < RD; k += 2) {
+        double vv[2];
+        lds_vec<2>(oV + k, vv);
+        const double t0 = (k <= kmax) ? S[base + k] : 0.0;
+        const double t1 = (k + 1 <= kmax) ? S[base + k + 1] : 0.0;
+        a0 = fma(t0, vv[0], a0);
+        a1 = fma(t1, vv[1], a1);
+    }
+    return a0 + a1;
+}
+
 // v = T (T^T bt), g = Ct^T v.  lane = position / row for the triangular products.
 template <int NC, int NS>
 __device__ __forceinline__ void echo_solve(const Slots<NS>& W, const EchoOff& O, int lane, double (&g)[NC], double& y,
                                            bool& y_ok) {
     // y = T^T bt: fresh after a refactorisation, otherwise carried through the rank-one updates (echo_change)
     if (!y_ok) {
-        double yy[1];
-        tmul_transposed<1>(W.T, O.B, RD, lane, yy);
-        y = yy[0];
+        y = echo_tmul_t(W.T, O.B, lane);
         y_ok = true;
     }
-    double v[1];
     if (lane < RD) S[W.rs + lane] = y;
     __syncwarp();
-    tmul<1>(W.T, W.rs, RD, lane, v);
-    if (lane < RD) S[O.V + lane] = v[0];
+    const double v = echo_tmul(W.T, W.rs, lane);
+    if (lane < RD) S[O.V + lane] = v;
     __syncwarp();
     echo_gprod<NC>(O, O.V, lane, g);
     __syncwarp();
@@ -171,8 +218,7 @@ template <int NS>
 __device__ __forceinline__ bool echo_update_T(const Slots<NS>& W, const EchoOff& O, double sgn, int lane, double& y,
                                               bool y_ok) {
     // ---- u = T^T d, prefix sums of u^2
-    double u[1];
-    tmul_transposed<1>(W.T, O.D, RD, lane, u);
+    const double u[1] = {echo_tmul_t(W.T, O.D, lane)};
     double tau[1] = {u[0] * u[0]};
     warp_scan_positions<1>(tau, lane);
     const double h = fma(sgn, tau[0], 1.0);
