@@ -89,6 +89,9 @@ __host__ __device__ __forceinline__ int echo_table_doubles(int n, int m) {
     return (n * t2_ldg(n) + EC_NCOL * EC_LDD + m * RD + tri(RD) + 3 * 64 + 8 + EC_RC_DOUBLES + 31) & ~31;
 }
 
+// unrolled, compile-time-indexed inner products in the X2 / T2SPARC kernels only (see echo_tmul below)
+constexpr bool ECHO_UNROLLED_TRI = (MET2_ECHO_PART == 1);
+
 // g = Ct^T v for v at S[oV .. oV + RD): lane + 32 s = column (NC column slots per lane: nT2 <= 32 NC).
 template <int NC>
 __device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, double (&g)[NC]) {
@@ -96,7 +99,7 @@ __device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, d
 #pragma unroll
     for (int s = 0; s < NC; ++s) g0[s] = g1[s] = 0.0;
     const int r0 = O.Ct + lane * EC_LDD;
-#pragma unroll 1
+#pragma unroll (ECHO_UNROLLED_TRI ? RD / 2 : 1)
     for (int e = 0; e < RD; e += 2) {
         double vv[2];
         lds_vec<2>(oV + e, vv);
@@ -120,7 +123,6 @@ __device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, d
 // 131.1 ms, T2SPARC 51.3 -> 49.9 ms; but the L-curve / BayesReg kernel, which is bound by instruction fetch, lost what
 // the +128 SASS instructions per call site cost (L-curve 293 -> 323 ms, BayesReg 339 -> 346 ms): MET2_ECHO_PART 2 keeps
 // the compact generic products.
-constexpr bool ECHO_UNROLLED_TRI = (MET2_ECHO_PART == 1);
 // out_r = sum_{c >= r} T(r, c) v_c  (lane = row r; lanes >= RD get 0)
 __device__ __forceinline__ double echo_tmul(int oT, int oV, int lane) {
     if (!ECHO_UNROLLED_TRI) {
@@ -242,7 +244,26 @@ __device__ __forceinline__ bool echo_update_T(const Slots<NS>& W, const EchoOff&
     }
     __syncwarp();
     // ---- T' = T Q, one row of T per lane (row r has entries in columns j >= r)
-    if (lane < RD) {
+    if (ECHO_UNROLLED_TRI) {
+        // compile-time column index: constant triangle offsets, (delta, q, u) of two columns per 128-bit broadcast load
+        double acc = 0.0;
+#pragma unroll
+        for (int c = 0; c < RD; c += 2) {
+            double dl[2], qq[2], uu[2];
+            lds_vec<2>(W.gs + c, dl);
+            lds_vec<2>(W.gs + 32 + c, qq);
+            lds_vec<2>(W.rs + c, uu);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (lane <= c + h) {
+                    const int a = W.T + tri(c + h) + lane;
+                    const double t = S[a];
+                    S[a] = fma(dl[h], t, qq[h] * acc);
+                    acc = fma(t, uu[h], acc);
+                }
+            }
+        }
+    } else if (lane < RD) {
         double acc = 0.0;
 #pragma unroll 1
         for (int c = lane; c < RD; ++c) {
