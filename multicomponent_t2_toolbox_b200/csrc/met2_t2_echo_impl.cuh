@@ -122,7 +122,9 @@ __device__ __forceinline__ void echo_gprod(const EchoOff& O, int oV, int lane, d
 // any p — here they were 17 % of the X2 kernel's instructions.  Measured (GPU call 24, config-2 volume): X2-I 136.5 ->
 // 131.1 ms, T2SPARC 51.3 -> 49.9 ms; but the L-curve / BayesReg kernel, which is bound by instruction fetch, lost what
 // the +128 SASS instructions per call site cost (L-curve 293 -> 323 ms, BayesReg 339 -> 346 ms): MET2_ECHO_PART 2 keeps
-// the compact generic products.
+// the compact generic products.  Unrolling further does not pay either: the seven steps of the 8 x 8 diagonal-block
+// elimination and the M_P update with compile-time offsets (+ 976 SASS instructions) took X2-I from 128 to 166 ms
+// (GPU call 27) — the kernel sits at the edge of what the instruction caches hold.
 // out_r = sum_{c >= r} T(r, c) v_c  (lane = row r; lanes >= RD get 0)
 __device__ __forceinline__ double echo_tmul(int oT, int oV, int lane) {
     if (!ECHO_UNROLLED_TRI) {
