@@ -7,7 +7,7 @@
 // Why: the Gram-domain kernel keeps an n x n packed factor per voxel (tri(100) = 5 050 doubles at config 4's 100 bins) and
 // BayesReg adds a dense n x n Cholesky factorisation per evidence evaluation, so config 4 ran at TWO warps per SM
 // (profiles/r02_config4_ncu_summary.txt).  Here a voxel's state is ~6 KB (RD = 16, 60 bins) to ~12 KB (RD = 24, 100
-// bins): 15-20 warps per SM.
+// bins): 15-30 warps per SM.
 //
 // BayesReg evidence without the n x n factor.  With xt = l * f (l = diag L) and Ct = C diag(1/l) (RD x n):
 //     A = beta B + beta x K = beta diag(l) (x I + Ct^T Ct) diag(l),   U = chol(A) = sqrt(beta) Ut diag(l),
