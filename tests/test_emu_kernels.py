@@ -370,6 +370,16 @@ def test_echo_basis_kernel():
             nz = np.diag(UtU) > 0.5
             assert np.abs(UtU - np.diag(nz.astype(float))).max() < 1e-14
             assert np.abs(U[a] @ C[a].T - dic[a]).max() <= 2e-15 * np.abs(dic[a]).max()
+        # rank 16 (MET2_ECHO_RANK_SMALL): the measured residual decides — the 32-echo protocol is inside the 4e-12 bound of
+        # batched.ECHO_TAIL_MAX (and far above the rank-24 bound, so the two ranks cannot be confused), the 48-echo one is not
+        U16, C16, tail16 = emu.echo_basis(dic, 16)
+        for a in range(3):
+            resid = np.abs(U16[a] @ C16[a].T - dic[a]).max() / np.abs(dic[a]).max()
+            assert resid <= 4.0 * tail16[a] + 1e-15            # the kernel's own measure is honest
+        if nte == 32:
+            assert 1e-14 < tail16.max() <= 4e-12, tail16
+        else:
+            assert tail16.max() > 4e-12, tail16
     few = emu.echo_basis(np.random.default_rng(0).uniform(size=(1, 8, 12)))      # fewer echoes than R: zero directions
     assert np.abs(few[0][0] @ few[1][0].T - np.random.default_rng(0).uniform(size=(1, 8, 12))[0]).max() < 1e-14
     assert few[2][0] <= 1e-15
