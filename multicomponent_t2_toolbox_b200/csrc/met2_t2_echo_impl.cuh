@@ -91,6 +91,11 @@ __host__ __device__ __forceinline__ int echo_table_doubles(int n, int m) {
 
 // unrolled, compile-time-indexed inner products in the X2 / T2SPARC kernels only (see echo_tmul below)
 constexpr bool ECHO_UNROLLED_TRI = (MET2_ECHO_PART == 1);
+#ifndef MET2_ECHO_REG_UNROLL_UPD
+#define MET2_ECHO_REG_UNROLL_UPD 0     // A/B switch: the unrolled factor update in the L-curve / BayesReg kernel too —
+                                       // measured slower (GPU call 28: L-curve 296 -> 319 ms, BayesReg 340 -> 350 ms)
+#endif
+constexpr bool ECHO_UNROLLED_UPD = ECHO_UNROLLED_TRI || (MET2_ECHO_REG_UNROLL_UPD != 0);
 
 // g = Ct^T v for v at S[oV .. oV + RD): lane + 32 s = column (NC column slots per lane: nT2 <= 32 NC).
 template <int NC>
@@ -246,7 +251,7 @@ __device__ __forceinline__ bool echo_update_T(const Slots<NS>& W, const EchoOff&
     }
     __syncwarp();
     // ---- T' = T Q, one row of T per lane (row r has entries in columns j >= r)
-    if (ECHO_UNROLLED_TRI) {
+    if (ECHO_UNROLLED_UPD) {
         // compile-time column index: constant triangle offsets, (delta, q, u) of two columns per 128-bit broadcast load
         double acc = 0.0;
 #pragma unroll
