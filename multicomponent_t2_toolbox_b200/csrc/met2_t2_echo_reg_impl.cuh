@@ -41,6 +41,10 @@ namespace MET2_ECHO_NS {
 constexpr int EV_RR = RD / 8;   // rows of the evidence state S_j per lane: rg + 8 a, rg = lane & 7
 constexpr int EV_CC = RD / 4;   // columns per lane: cb EV_CC + b, cb = lane >> 3
 
+#ifndef MET2_LCURVE_GRAM_COLD
+#define MET2_LCURVE_GRAM_COLD 0   // A/B switch: cold-start the Gram-domain grid points (prunes nnls_gram's warm-start code,
+                                  // 9.2 k -> 8.7 k SASS instructions) — measured much slower (GPU call 29: 293 -> 466 ms)
+#endif
 constexpr int EV_LCURVE_PMAX = 32;          // positions of the Gram-domain factor of the L-curve kernel (one slot per lane)
 template <int METHOD>
 struct EchoRegPmax {
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(EchoRegThreads<METHOD, NC>::value, 1) t2_echo_
                         // G + lam K from the carried-over positions (<= PMAX; a full factor sends the point to echo space)
                         const bool plain = (METHOD == MET2_REG_BAYESREG) ? true : (phase == PH_PLAIN);   // BayesReg: compile-time
                         const int pn = nnls_gram<NC, GSH, 1>(W, oG, Gg, ldg, oKb, !plain, lam_cur, n, plain ? RD : PMAX, lane,
-                                                              nst, plain ? 0 : p, false);
+                                                              nst, (MET2_LCURVE_GRAM_COLD || plain) ? 0 : p, false);
                         double a = 0.0;
 #pragma unroll
                         for (int s = 0; s < NC; ++s) {
