@@ -55,6 +55,17 @@ def golden_methods(golden_config2):
     return g
 
 
+@pytest.fixture(scope="session")
+def golden_methods_invt2(golden_config2):
+    """The same 2 048 voxels fitted by the unmodified reference with X2 / L_curve / BayesReg and reg_matrix InvT2, plus
+    BayesReg-InvT2 on the signals perturbed by 1e-13 (oracle/make_golden_methods_invt2.py)."""
+    import numpy as np
+    g = dict(np.load(os.path.join(GOLDEN, "methods_invt2_subset.npz")))
+    g["sig"] = np.ascontiguousarray(golden_config2["sig"][::int(g["stride"])])
+    g["spectrum"] = lambda key: _unpack(g, key, 60)
+    return g
+
+
 def _unpack(g, key, npc):
     import numpy as np
     sup = np.unpackbits(g[key + "_support"], axis=1)[:, :npc].astype(bool)
