@@ -132,7 +132,7 @@ def test_echo_space_lcurve_and_bayesreg_against_oracle(setup):
         grm = O._grids(method, rm, "spline", 40.0, 32, 10.0, 1000.0)
         out = _run("shuffle", sig, fa, setup["Dic"], grm["L"], gr["T2s"], method, echo=True, echo_rank=rank,
                    lambdas=gr["lambda_reg"])
-        if rank == 16 and method == "BayesReg":
+        if rank == 16:       # lane-order invariance: a missing barrier between lanes shows up as a difference
             again = _run("reverse", sig, fa, setup["Dic"], grm["L"], gr["T2s"], method, echo=True, echo_rank=rank,
                          lambdas=gr["lambda_reg"])
             assert _same(out, again)
