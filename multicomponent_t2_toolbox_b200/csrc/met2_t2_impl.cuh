@@ -243,11 +243,16 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N
                     c = 1.0 / sqrt(1.0 + tt * tt);
                     s = tt * c;
                 }
-                // the functional transforms like a row of W: e_p' = c e_p - s e_q, e_q' = s e_p + c e_q
-                const double ep = S[W.rs + pp], eq = S[W.rs + qq];
-                S[W.rs + pp] = c * ep - s * eq;
-                S[W.rs + qq] = s * ep + c * eq;
+                // the functional transforms like a row of W: e_p' = c e_p - s e_q, e_q' = s e_p + c e_q  (identity, and
+                // no write at all, for a skipped rotation: a round without rotations touches no shared memory)
+                if (s != 0.0) {
+                    const double ep = S[W.rs + pp], eq = S[W.rs + qq];
+                    S[W.rs + pp] = c * ep - s * eq;
+                    S[W.rs + qq] = s * ep + c * eq;
+                }
             }
+            // a round in which no pair rotates changes nothing (the last sweep consists of such rounds only)
+            if (!__any_sync(FULL_MASK, s != 0.0)) continue;
             if (lane < half) {
                 S[W.gs + 3 * lane] = c;
                 S[W.gs + 3 * lane + 1] = s;
@@ -262,8 +267,8 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N
                 const int i = i0 + sub;
                 if (i < half) {
                     const int p2 = SI(W.gs + 3 * i + 2, 0), q2 = SI(W.gs + 3 * i + 2, 1);
-                    if (p2 >= 0) {
-                        const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                    const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                    if (p2 >= 0 && si != 0.0) {   // a skipped rotation is exactly the identity (c = 1, s = 0): nothing to do
                         for (int r = l16; r < N; r += 16) {
                             const double xv = S[oA + r * LD + p2], yv = S[oA + r * LD + q2];
                             S[oA + r * LD + p2] = ci * xv - si * yv;
@@ -278,8 +283,8 @@ __device__ __forceinline__ double jacobi_trace(const Slots<NS>& W, int oA, int N
                 const int i = i0 + sub;
                 if (i < half) {
                     const int p2 = SI(W.gs + 3 * i + 2, 0), q2 = SI(W.gs + 3 * i + 2, 1);
-                    if (p2 >= 0) {
-                        const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                    const double ci = S[W.gs + 3 * i], si = S[W.gs + 3 * i + 1];
+                    if (p2 >= 0 && si != 0.0) {
                         for (int cc = l16; cc < N; cc += 16) {
                             const double xv = S[oA + p2 * LD + cc], yv = S[oA + q2 * LD + cc];
                             S[oA + p2 * LD + cc] = ci * xv - si * yv;
