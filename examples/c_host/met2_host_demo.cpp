@@ -9,6 +9,7 @@
 // write; the Python package does exactly the same calls through ctypes (multicomponent_t2_toolbox_b200/_lib.py).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -135,6 +136,52 @@ int main() {
     CK(cudaMemcpy(maps.data(), d_maps, maps.size() * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(reg.data(), d_reg, V * 8, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(fsol.data(), d_fsol, fsol.size() * 8, cudaMemcpyDeviceToHost));
+    // ---- the same fit in the reduced echo space (met2_echo_basis + met2_t2_fit_echo, MET2_T2_FLAG_ECHO_SPACE): the rank is
+    //      chosen from the measured residual of the reduction, as batched.Dictionary.echo_basis does
+    int bad_echo = 0;
+    {
+        int R = met2_echo_rank(1);
+        double *d_basis = dev_alloc<double>((size_t)nA * nTE * MET2_ECHO_RANK), *d_coef = dev_alloc<double>((size_t)nA * nT2 * MET2_ECHO_RANK);
+        double* d_tail = dev_alloc<double>(nA);
+        std::vector<double> tail(nA);
+        double tmax = 0.0;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            MK(met2_echo_basis(d_dic, nA, nTE, nT2, R, d_basis, d_coef, d_tail, nullptr));
+            CK(cudaMemcpy(tail.data(), d_tail, nA * 8, cudaMemcpyDeviceToHost));
+            tmax = 0.0;
+            for (int a = 0; a < nA; ++a) tmax = std::max(tmax, tail[a]);
+            if (tmax <= (R == met2_echo_rank(1) ? 4e-12 : 1e-15)) break;
+            R = met2_echo_rank(0);
+        }
+        met2_t2_cfg ecfg = tcfg;
+        ecfg.flags |= MET2_T2_FLAG_ECHO_SPACE;
+        ecfg.echo_rank = R;
+        double *d_fsol2 = dev_alloc<double>((size_t)V * nT2), *d_est2 = dev_alloc<double>((size_t)V * nTE);
+        double *d_reg2 = dev_alloc<double>(V), *d_maps2 = dev_alloc<double>((size_t)V * 6);
+        uint32_t* d_st3 = dev_alloc<uint32_t>(V);
+        MK(met2_t2_fit_echo(d_sig, d_idx, V, &ecfg, d_dic, d_dicT, d_G, d_kband, nullptr, d_logT2, d_comp, d_basis, d_coef, d_fsol2,
+                            d_est2, d_reg2, d_maps2, d_st3, d_ws_t2, nullptr));
+        CK(cudaDeviceSynchronize());
+        std::vector<double> fsol2((size_t)V * nT2);
+        std::vector<uint32_t> st3(V);
+        CK(cudaMemcpy(fsol2.data(), d_fsol2, fsol2.size() * 8, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(st3.data(), d_st3, V * 4, cudaMemcpyDeviceToHost));
+        double worst = 0.0;
+        for (int v = 1; v < V; ++v) {
+            double fmax = 0.0, dmax = 0.0;
+            bool same = (st3[v] == 0);
+            for (int j = 0; j < nT2; ++j) {
+                const double a = fsol[(size_t)v * nT2 + j], b = fsol2[(size_t)v * nT2 + j];
+                fmax = std::max(fmax, std::fabs(a));
+                dmax = std::max(dmax, std::fabs(a - b));
+                if ((a > 0.0) != (b > 0.0)) same = false;
+            }
+            worst = std::max(worst, dmax / fmax);
+            if (!same || dmax > 1e-6 * fmax) ++bad_echo;
+        }
+        std::printf("echo space (rank %d, residual of the reduction %.1e): %d/%d voxels differ from the Gram-domain fit, "
+                    "largest relative spectrum difference %.1e\n", R, tmax, bad_echo, V - 1, worst);
+    }
     // ---- checks
     if (!(st[0] & MET2_ST_SKIPPED) || !(st2[0] & MET2_ST_SKIPPED)) { std::printf("empty voxel not skipped\n"); ++fails; }
     for (int j = 0; j < nT2; ++j) if (fsol[j] != 0.0) { std::printf("empty voxel has a spectrum\n"); ++fails; break; }
@@ -159,7 +206,7 @@ int main() {
                 V - 1, bad_fit, bad_map);
     std::printf("voxel 1: FA %d (true %d), MWF %.4f, k_est %.4f; kernel launches so far: %lld\n", idx[1], a_true[1],
                 maps[6], reg[1], (long long)met2_launch_count());
-    fails += bad_idx + bad_fit + bad_map;
+    fails += bad_idx + bad_fit + bad_map + bad_echo;
     std::printf(fails ? "FAILED (%d)\n" : "OK\n", fails);
     return fails ? 1 : 0;
 }
